@@ -1,0 +1,144 @@
+"""``CorrBlock`` / ``EfficientCorrBlock`` with the reference's names, signatures and tensor layouts
+(comet/models/track_modules/blocks.py:351-484), computed by the fused sm_100a kernels.
+
+Differences a caller can observe: none in results (parity tests) -- but the correlation volume is never
+materialised by ``corr()``/``sample()``; ``corrs_pyramid`` is produced lazily only if somebody reads it."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._dev import f32c, inner_contig, pad_mode, prec_mode, require_cuda, stream_ptr
+
+lib = _lib.lib
+
+
+class _Pyramid:
+    """Level 0 is the caller's tensor; levels 1..L-1 live back to back in one buffer (one allocation,
+    written once per tracker call by comet_pyramid_f32)."""
+
+    def __init__(self, fmaps: torch.Tensor, num_levels: int):
+        require_cuda(fmaps, "fmaps")
+        assert fmaps.dim() == 5, "fmaps must be (B, S, C, H, W)"
+        B, S, C, H, W = fmaps.shape
+        assert 1 <= num_levels <= _lib.MAX_LEVELS, f"num_levels must be in [1, {_lib.MAX_LEVELS}]"
+        self.B, self.S, self.C, self.H, self.W = B, S, C, H, W
+        self.num_levels = num_levels
+        self.fmaps0 = f32c(fmaps)
+        n = lib.comet_pyramid_elems(B * S, C, H, W, num_levels)
+        assert n >= 0
+        self.pyr = torch.empty(max(n, 1), dtype=torch.float32, device=fmaps.device)
+        with torch.cuda.device(fmaps.device):
+            _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W, num_levels,
+                                             stream_ptr(fmaps.device)))
+        self.levels: List[torch.Tensor] = [fmaps]
+        h, w = H, W
+        for l in range(1, num_levels):
+            h, w = h // 2, w // 2
+            off = lib.comet_pyramid_offset(B * S, C, H, W, l)
+            self.levels.append(self.pyr[off: off + B * S * C * h * w].view(B, S, C, h, w))
+
+
+def _fused_lookup(pyr: _Pyramid, targets, coords, radius, padding, level_stride=0):
+    B, S, N, D = coords.shape
+    assert D == 2
+    require_cuda(coords, "coords")
+    require_cuda(targets, "targets")
+    t = inner_contig(targets)
+    c = inner_contig(coords)
+    Wr = 2 * radius + 1
+    out = torch.empty((B, S, N, pyr.num_levels * Wr * Wr), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(coords.device):
+        _lib.check(lib.comet_corr_lookup_f32(
+            pyr.fmaps0.data_ptr(), pyr.pyr.data_ptr(),
+            t.data_ptr(), t.stride(0), t.stride(1), t.stride(2), level_stride,
+            c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
+            out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
+            B, S, N, pyr.C, pyr.H, pyr.W, pyr.num_levels, radius, pad_mode(padding), prec_mode(),
+            stream_ptr(coords.device)))
+    return out
+
+
+class CorrBlock:
+    """Drop-in for blocks.py:351-429.  Plain class (not an nn.Module), no parameters, stateful between
+    ``corr()`` and ``sample()``."""
+
+    def __init__(self, fmaps, num_levels=4, radius=4, multiple_track_feats=False, padding_mode="zeros"):
+        B, S, C, H, W = fmaps.shape
+        self.S, self.C, self.H, self.W = S, C, H, W
+        self.padding_mode = padding_mode
+        self.num_levels = num_levels
+        self.radius = radius
+        self.multiple_track_feats = multiple_track_feats
+        pad_mode(padding_mode)  # validate early
+        assert 0 <= radius <= _lib.MAX_RADIUS, f"radius must be in [0, {_lib.MAX_RADIUS}]"
+        self._pyr = _Pyramid(fmaps, num_levels)
+        self.fmaps_pyramid = self._pyr.levels
+        self._targets: Optional[torch.Tensor] = None
+        self._volumes: Optional[List[torch.Tensor]] = None
+
+    def corr(self, targets):
+        B, S, N, C = targets.shape
+        if self.multiple_track_feats:
+            C = C // self.num_levels
+        assert C == self.C
+        assert S == self.S
+        require_cuda(targets, "targets")
+        self._targets = targets
+        self._volumes = None
+
+    @property
+    def corrs_pyramid(self):
+        """List of (B,S,N,H_l,W_l) volumes, as the reference stores after ``corr()`` (blocks.py:420-429).
+        Materialised on first access only; ``sample()`` does not need it."""
+        if self._targets is None:
+            raise AttributeError("'CorrBlock' object has no attribute 'corrs_pyramid' (call corr() first)")
+        if self._volumes is None:
+            p = self._pyr
+            B, S, N, _ = self._targets.shape
+            t = f32c(self._targets).view(B * S, N, -1)
+            vols = []
+            mode = prec_mode()
+            with torch.cuda.device(t.device):
+                for l, f in enumerate(self.fmaps_pyramid):
+                    h, w = f.shape[-2:]
+                    tl = t[..., l * self.C:(l + 1) * self.C] if self.multiple_track_feats else t
+                    fl = p.fmaps0 if l == 0 else f
+                    v = torch.empty((B, S, N, h, w), dtype=torch.float32, device=t.device)
+                    for b0 in range(0, B * S, 32768):  # gridDim.z limit
+                        nb = min(32768, B * S - b0)
+                        _lib.check(lib.comet_corr_volume_f32(
+                            tl[b0:].data_ptr(), tl.stride(0), tl.stride(1),
+                            fl.reshape(B * S, self.C, h * w)[b0:].data_ptr(),
+                            v.view(B * S, N, h * w)[b0:].data_ptr(), nb, N, self.C, h * w, mode,
+                            stream_ptr(t.device)))
+                    vols.append(v.to(torch.bfloat16) if mode == _lib.PREC_BF16_AUTOCAST else v)
+            self._volumes = vols
+        return self._volumes
+
+    def sample(self, coords):
+        B, S, N, D = coords.shape
+        assert D == 2
+        if self._targets is None:
+            raise AttributeError("'CorrBlock' object has no attribute 'corrs_pyramid' (call corr() first)")
+        return _fused_lookup(self._pyr, self._targets, coords, self.radius, self.padding_mode,
+                             self.C if self.multiple_track_feats else 0)
+
+
+class EfficientCorrBlock:
+    """Drop-in for blocks.py:432-484: same pyramid, ``sample(coords, target)`` with *border* padding."""
+
+    def __init__(self, fmaps, num_levels=4, radius=4):
+        self.num_levels = num_levels
+        self.radius = radius
+        assert 0 <= radius <= _lib.MAX_RADIUS, f"radius must be in [0, {_lib.MAX_RADIUS}]"
+        self._pyr = _Pyramid(fmaps, num_levels)
+        self.fmaps_pyramid = self._pyr.levels
+
+    def sample(self, coords, target):
+        B, S, N, D = coords.shape
+        assert D == 2
+        assert target.shape[-1] == self._pyr.C and target.shape[1] == self._pyr.S
+        return _fused_lookup(self._pyr, target, coords, self.radius, "border")

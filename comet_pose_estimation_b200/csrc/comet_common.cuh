@@ -1,0 +1,107 @@
+// Shared host/device helpers for the COMET B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+
+#include "../../include/comet_b200.h"
+
+namespace comet {
+
+// ---- error plumbing ---------------------------------------------------
+char* last_error_buf();  // thread-local, defined in cabi.cu
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define COMET_REQUIRE(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ::comet::fail(COMET_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+#define COMET_CUDA(call)                                                                        \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::comet::fail(COMET_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));    \
+  } while (0)
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(COMET_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return COMET_OK;
+}
+
+// ---- pyramid geometry (host) -------------------------------------------
+struct Levels {
+  int L;
+  int H[COMET_MAX_LEVELS];
+  int W[COMET_MAX_LEVELS];
+  long long off[COMET_MAX_LEVELS];  // element offset of level l inside `pyr` (off[0] unused)
+};
+inline Levels make_levels(int BS, int C, int H, int W, int L) {
+  Levels lv{};
+  lv.L = L;
+  long long o = 0;
+  for (int l = 0; l < L && l < COMET_MAX_LEVELS; ++l) {
+    lv.H[l] = H;
+    lv.W[l] = W;
+    lv.off[l] = (l == 0) ? 0 : o;
+    if (l >= 1) o += (long long)BS * C * H * W;
+    H /= 2;
+    W /= 2;
+  }
+  return lv;
+}
+
+// ---- device helpers ----------------------------------------------------
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// Per-axis description of a (2r+1)-wide window of bilinear samples whose centre is `p`
+// (grid_sample semantics, align_corners=True, restated from ATen GridSampler):
+//   grid position g in [0, 2r+2): integer tap  i0 + g  (zeros: masked when outside; border: clamped)
+//   window index  i in [0, 2r+1): value = w0(i) * V[g=i] + w1(i) * V[g=i+1]
+struct AxisWindow {
+  int i0;     // floor(p) - r
+  float p;    // centre coordinate
+  float f;    // p - floor(p)
+  int size;   // map extent along this axis
+  int r;
+  bool border;
+  __device__ __forceinline__ void init(float centre, int size_, int r_, bool border_) {
+    size = size_;
+    r = r_;
+    border = border_;
+    // keep float->int conversion defined for wild coordinates; such windows are entirely off the map
+    centre = fminf(fmaxf(centre, -1.0e6f), 1.0e6f);
+    if (size == 1) centre = 0.f;  // bilinear_sampler scales by 2/max(size-1,1) and grid_sample by (size-1)/2 = 0
+    p = centre;
+    float fl = floorf(centre);
+    f = centre - fl;
+    i0 = (int)fl - r;
+  }
+  // integer tap of grid position g; returns false when the tap contributes zero
+  __device__ __forceinline__ bool tap(int g, int& pos) const {
+    pos = i0 + g;
+    if (size == 1) { pos = 0; return true; }
+    if (border) {
+      pos = min(max(pos, 0), size - 1);
+      return true;
+    }
+    return pos >= 0 && pos < size;
+  }
+  __device__ __forceinline__ void weights(int i, float& w0, float& w1) const {
+    w0 = 1.f - f;
+    w1 = f;
+    if (size == 1) { w0 = 1.f; w1 = 0.f; return; }
+    if (border) {
+      float c = p + (float)(i - r);
+      if (c < 0.f || c > (float)(size - 1)) { w0 = 1.f; w1 = 0.f; }
+    }
+  }
+};
+
+}  // namespace comet

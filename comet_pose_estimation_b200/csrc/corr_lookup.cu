@@ -1,0 +1,270 @@
+// Fused correlation + multi-level window lookup (+ optional track-token epilogue), SIMT float32.
+//
+// Replaces CorrBlock.corr + CorrBlock.sample (comet/models/track_modules/blocks.py:376-429),
+// EfficientCorrBlock.sample (blocks.py:446-484) and, with TOKENS, the token assembly of
+// BaseTrackerPredictor.forward (base_track_predictor.py:165-224).
+//
+// Formulation.  Every entry of the (2r+1)^2 window of level l is a bilinear blend of the correlation
+// volume V_l at four integer taps, and all entries share the same fractional offsets, so the window
+// only needs V_l on a (2r+2)^2 integer grid around the query.  One warp owns one (b, s, n) query:
+//   1. lanes <- grid positions; each lane accumulates dot(T[b,s,n,:], F_l[b,s,:,y,x]) over channels
+//      (target vector broadcast from shared memory, feature reads coalesced along x);
+//   2. the grid goes to shared memory, lanes <- window entries, blend, coalesced store.
+// The volume is never written to global memory.  This is the general path (any C, H, W, L, r<=7, both
+// padding modes, strided views) and the HBM-bound path of the fine tracker (one query per map, GEMV-shaped);
+// the dense coarse shapes go through the tcgen05 kernel in corr_tc.cu when available.
+#include "comet_common.cuh"
+
+namespace comet {
+
+struct LookupParams {
+  const float* fmaps;
+  const float* pyr;
+  const float* targets;
+  long long t_sb, t_ss, t_sn;
+  int t_level_stride;
+  const float* coords;
+  long long c_sb, c_ss, c_sn;
+  float* out;
+  long long o_sb, o_ss, o_sn;
+  const float* pos;  // TOKENS: (B,N,D_tok)
+  int D_tok;
+  int B, S, N, C, L, r;
+  int pad_border, bf16;
+  int lvlH[COMET_MAX_LEVELS], lvlW[COMET_MAX_LEVELS];
+  long long lvlOff[COMET_MAX_LEVELS];
+  float sqrt_c;
+};
+
+template <int KPL, bool TOKENS>
+__global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) {
+  extern __shared__ float smem[];
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = 2 * p.r + 2, Wr = 2 * p.r + 1;
+  const int GG = G * G, WW = Wr * Wr;
+  float* Ts = smem + (size_t)warp * (p.C + GG);  // target vector of this warp's query
+  float* Vs = Ts + p.C;                          // (2r+2)^2 grid of correlations
+
+  const long long q = (long long)blockIdx.x * warps_per_block + warp;
+  const long long total = (long long)p.B * p.S * p.N;
+  if (q >= total) return;
+  const int n = (int)(q % p.N);
+  const int s = (int)((q / p.N) % p.S);
+  const int b = (int)(q / ((long long)p.N * p.S));
+  const long long bs = (long long)b * p.S + s;
+
+  const float* cp = p.coords + b * p.c_sb + s * p.c_ss + n * p.c_sn;
+  const float cx = __ldg(cp), cy = __ldg(cp + 1);
+  const float* tp = p.targets + b * p.t_sb + s * p.t_ss + n * p.t_sn;
+
+  float* op;
+  const float* pp = nullptr;
+  int corr_off = 0;
+  if (TOKENS) {
+    op = p.out + (((long long)b * p.N + n) * p.S + s) * p.D_tok;
+    pp = p.pos + ((long long)b * p.N + n) * p.D_tok;
+    corr_off = p.C + 2;
+  } else {
+    op = p.out + b * p.o_sb + s * p.o_ss + n * p.o_sn;
+  }
+
+  for (int l = 0; l < p.L; ++l) {
+    const int Hl = p.lvlH[l], Wl = p.lvlW[l];
+    const long long HW = (long long)Hl * Wl;
+    const float* F = (l == 0 ? p.fmaps : p.pyr + p.lvlOff[l]) + bs * p.C * HW;
+
+    // stage the target vector (per level only when multiple_track_feats splits channels)
+    if (l == 0 || p.t_level_stride != 0) {
+      __syncwarp();
+      const float* tl = tp + (long long)l * p.t_level_stride;
+      for (int c = lane; c < p.C; c += 32) {
+        float t = __ldg(tl + c);
+        Ts[c] = p.bf16 ? round_bf16(t) : t;
+      }
+      __syncwarp();
+    }
+
+    const float inv = 1.f / (float)(1 << l);
+    AxisWindow ax, ay;
+    ax.init(cx * inv, Wl, p.r, p.pad_border);
+    ay.init(cy * inv, Hl, p.r, p.pad_border);
+
+    // 1. correlations on the integer grid
+    long long offs[KPL];
+    bool ok[KPL];
+    float acc[KPL];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int idx = lane + 32 * k;
+      int gx = 0, gy = 0;
+      bool v = idx < GG;
+      if (v) {
+        const int a = idx / G, bb = idx - a * G;
+        const bool vx = ax.tap(bb, gx), vy = ay.tap(a, gy);
+        v = vx && vy;
+      }
+      ok[k] = v;
+      offs[k] = v ? (long long)gy * Wl + gx : 0;
+      acc[k] = 0.f;
+    }
+    if (!p.bf16) {
+#pragma unroll 4
+      for (int c = 0; c < p.C; ++c) {
+        const float t = Ts[c];
+        const float* Fc = F + (long long)c * HW;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k)
+          if (ok[k]) acc[k] = fmaf(t, __ldg(Fc + offs[k]), acc[k]);
+      }
+    } else {
+#pragma unroll 4
+      for (int c = 0; c < p.C; ++c) {
+        const float t = Ts[c];
+        const float* Fc = F + (long long)c * HW;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k)
+          if (ok[k]) acc[k] = fmaf(t, round_bf16(__ldg(Fc + offs[k])), acc[k]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < GG) {
+        float v = acc[k];
+        if (p.bf16) v = round_bf16(v);           // matmul result is stored in bf16 under autocast
+        v = __fdiv_rn(v, p.sqrt_c);              // blocks.py:428 divides after the matmul
+        if (p.bf16) v = round_bf16(v);
+        Vs[idx] = ok[k] ? v : 0.f;
+      }
+    }
+    __syncwarp();
+
+    // 2. blend: out[l*WW + i*Wr + j], i <-> x offset (slow), j <-> y offset (fast)
+    for (int o = lane; o < WW; o += 32) {
+      const int i = o / Wr, j = o - i * Wr;
+      float wx0, wx1, wy0, wy1;
+      ax.weights(i, wx0, wx1);
+      ay.weights(j, wy0, wy1);
+      const float* v = Vs + j * G + i;
+      // ATen accumulation order: nw, ne, sw, se
+      float val = v[0] * (wx0 * wy0);
+      val += v[1] * (wx1 * wy0);
+      val += v[G] * (wx0 * wy1);
+      val += v[G + 1] * (wx1 * wy1);
+      const int d = corr_off + l * WW + o;
+      if (TOKENS) val += __ldg(pp + d);
+      op[d] = val;
+    }
+  }
+
+  if (TOKENS) {
+    // [ sin/cos(flow * div) (C) | flow (2) | fcorrs | track_feats (C) | zero pad ] + pos_emb
+    // get_2d_embedding (utils.py:65-101) with C_emb = latent/2, called at base_track_predictor.py:176-181.
+    const float* c0 = p.coords + b * p.c_sb + n * p.c_sn;  // frame 0
+    const float fx = cx - __ldg(c0), fy = cy - __ldg(c0 + 1);
+    const int Ce = p.C >> 1;
+    const float step = 1000.0f / (float)Ce;
+    for (int e = lane; e < p.C; e += 32) {
+      const int axis = e / Ce, w = e - axis * Ce;
+      const float div = (float)(w & ~1) * step;
+      const float arg = __fmul_rn(axis ? fy : fx, div);
+      const float v = (w & 1) ? cosf(arg) : sinf(arg);
+      op[e] = v + __ldg(pp + e);
+    }
+    if (lane < 2) op[p.C + lane] = (lane ? fy : fx) + __ldg(pp + p.C + lane);
+    const int feat_off = corr_off + p.L * WW;
+    for (int c = lane; c < p.C; c += 32) op[feat_off + c] = __ldg(tp + c) + __ldg(pp + feat_off + c);
+    for (int d = feat_off + p.C + lane; d < p.D_tok; d += 32) op[d] = __ldg(pp + d);
+  }
+}
+
+template <bool TOKENS>
+static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
+  const int G = 2 * p.r + 2;
+  const int kpl = (G * G + 31) / 32;
+  const int warps = 8;
+  const size_t smem = (size_t)warps * (p.C + G * G) * sizeof(float);
+  const long long total = (long long)p.B * p.S * p.N;
+  if (total == 0) return COMET_OK;
+  const long long blocks = (total + warps - 1) / warps;
+  if (blocks > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many queries for one launch");
+  if (smem > 200 * 1024) return fail(COMET_ERR_UNSUPPORTED, "C=%d too large for the lookup kernel", p.C);
+#define COMET_LAUNCH(K)                                                                                   \
+  do {                                                                                                    \
+    if (smem > 48 * 1024)                                                                                 \
+      COMET_CUDA(cudaFuncSetAttribute(corr_lookup_kernel<K, TOKENS>,                                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    corr_lookup_kernel<K, TOKENS><<<(unsigned)blocks, warps * 32, smem, stream>>>(p);                     \
+  } while (0)
+  if (kpl <= 1) COMET_LAUNCH(1);
+  else if (kpl <= 2) COMET_LAUNCH(2);
+  else if (kpl <= 4) COMET_LAUNCH(4);
+  else COMET_LAUNCH(8);
+#undef COMET_LAUNCH
+  return launch_status("corr_lookup_kernel");
+}
+
+static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, const float* targets, long long t_sb,
+                       long long t_ss, long long t_sn, int t_level_stride, const float* coords, long long c_sb,
+                       long long c_ss, long long c_sn, int B, int S, int N, int C, int H, int W, int L, int r,
+                       int pad_mode, int prec_mode) {
+  COMET_REQUIRE(B >= 0 && S >= 0 && N >= 0, "negative batch dimension");
+  COMET_REQUIRE(C >= 1 && H >= 1 && W >= 1, "C, H, W must be positive (got %d, %d, %d)", C, H, W);
+  COMET_REQUIRE(L >= 1 && L <= COMET_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", COMET_MAX_LEVELS, L);
+  COMET_REQUIRE(r >= 0 && r <= COMET_MAX_RADIUS, "radius must be in [0, %d] (got %d)", COMET_MAX_RADIUS, r);
+  COMET_REQUIRE(pad_mode == COMET_PAD_ZEROS || pad_mode == COMET_PAD_BORDER, "bad pad_mode %d", pad_mode);
+  COMET_REQUIRE(prec_mode == COMET_PREC_F32 || prec_mode == COMET_PREC_BF16_AUTOCAST, "bad prec_mode %d", prec_mode);
+  COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
+  const long long total = (long long)B * S * N;
+  COMET_REQUIRE(total == 0 || (fmaps && targets && coords), "null input pointer");
+  COMET_REQUIRE(total == 0 || L == 1 || pyr, "pyr is null but num_levels > 1");
+  p.fmaps = fmaps; p.pyr = pyr; p.targets = targets;
+  p.t_sb = t_sb; p.t_ss = t_ss; p.t_sn = t_sn; p.t_level_stride = t_level_stride;
+  p.coords = coords; p.c_sb = c_sb; p.c_ss = c_ss; p.c_sn = c_sn;
+  p.B = B; p.S = S; p.N = N; p.C = C; p.L = L; p.r = r;
+  p.pad_border = pad_mode == COMET_PAD_BORDER;
+  p.bf16 = prec_mode == COMET_PREC_BF16_AUTOCAST;
+  Levels lv = make_levels(B * S, C, H, W, L);
+  for (int l = 0; l < L; ++l) { p.lvlH[l] = lv.H[l]; p.lvlW[l] = lv.W[l]; p.lvlOff[l] = lv.off[l]; }
+  p.sqrt_c = sqrtf((float)C);
+  p.pos = nullptr; p.D_tok = 0;
+  return COMET_OK;
+}
+
+}  // namespace comet
+
+using namespace comet;
+
+extern "C" int comet_corr_lookup_f32(const float* fmaps, const float* pyr, const float* targets, long long t_sb,
+                                     long long t_ss, long long t_sn, int t_level_stride, const float* coords,
+                                     long long c_sb, long long c_ss, long long c_sn, float* out, long long o_sb,
+                                     long long o_ss, long long o_sn, int B, int S, int N, int C, int H, int W, int L,
+                                     int r, int pad_mode, int prec_mode, comet_stream_t stream) {
+  LookupParams p{};
+  int rc = fill_params(p, fmaps, pyr, targets, t_sb, t_ss, t_sn, t_level_stride, coords, c_sb, c_ss, c_sn, B, S, N,
+                       C, H, W, L, r, pad_mode, prec_mode);
+  if (rc != COMET_OK) return rc;
+  COMET_REQUIRE(t_level_stride == 0 || t_level_stride == C, "t_level_stride must be 0 or C");
+  COMET_REQUIRE((long long)B * S * N == 0 || out, "null output pointer");
+  p.out = out; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sn = o_sn;
+  return launch_lookup<false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int comet_track_tokens_f32(const float* fmaps, const float* pyr, const float* track_feats, long long t_sb,
+                                      long long t_ss, long long t_sn, const float* coords, long long c_sb,
+                                      long long c_ss, long long c_sn, const float* pos_emb, float* tokens, int B,
+                                      int S, int N, int C, int H, int W, int L, int r, int pad_mode, int prec_mode,
+                                      int D_tok, comet_stream_t stream) {
+  LookupParams p{};
+  int rc = fill_params(p, fmaps, pyr, track_feats, t_sb, t_ss, t_sn, 0, coords, c_sb, c_ss, c_sn, B, S, N, C, H, W,
+                       L, r, pad_mode, prec_mode);
+  if (rc != COMET_OK) return rc;
+  const int need = 2 * C + 2 + L * (2 * r + 1) * (2 * r + 1);
+  COMET_REQUIRE(C % 4 == 0, "latent_dim must be a multiple of 4 for the flow embedding (got %d)", C);
+  COMET_REQUIRE(D_tok >= need, "D_tok=%d smaller than the %d token channels", D_tok, need);
+  COMET_REQUIRE((long long)B * S * N == 0 || (tokens && pos_emb), "null tokens / pos_emb pointer");
+  p.out = tokens; p.pos = pos_emb; p.D_tok = D_tok;
+  return launch_lookup<true>(p, (cudaStream_t)stream);
+}

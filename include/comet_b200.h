@@ -1,0 +1,129 @@
+/*
+ * comet_b200.h -- C ABI of the B200-native COMET tracking hot path.
+ *
+ * The reference (wulibingbinglin/COMET-Pose-Estimation) is pure Python/PyTorch
+ * and has no FFI: its "plugin interface" for this path is the set of Python
+ * symbols listed in SURVEY.md section 8(b).  Every entry point below replaces
+ * the arithmetic behind one of those symbols; the Python mirror in
+ * comet_pose_estimation_b200/ binds them with ctypes (see INTEGRATION.md for
+ * the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are float32, innermost dimension contiguous; where a tensor may
+ *     be a permuted view the element strides of its outer dimensions are
+ *     passed explicitly (sb, ss, sn = batch, frame, track);
+ *   - coordinates are (x, y) pairs in level-0 cell units;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns COMET_OK (0) or an error code and never throws;
+ *     comet_last_error() returns a thread-local description of the last
+ *     failure.  Launches are asynchronous on `stream`.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with COMET_ERR_CUDA.
+ *
+ * Reference citations are file:line into the reference repository.
+ */
+#ifndef COMET_B200_H
+#define COMET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COMET_OK 0
+#define COMET_ERR_INVALID 1     /* bad argument (the reference would raise AssertionError) */
+#define COMET_ERR_CUDA 2        /* CUDA runtime / launch failure */
+#define COMET_ERR_UNSUPPORTED 3 /* shape outside what the kernels implement */
+
+#define COMET_PAD_ZEROS 0  /* CorrBlock default, blocks.py:357 */
+#define COMET_PAD_BORDER 1 /* EfficientCorrBlock / bilinear_sampler default, utils.py:874 */
+
+#define COMET_PREC_F32 0           /* float32 arithmetic everywhere (parity bar 1e-4) */
+#define COMET_PREC_BF16_AUTOCAST 1 /* what torch.autocast(bf16) makes of CorrBlock.corr: bf16 operands,
+                                      f32 accumulate, volume rounded to bf16, f32 lookup (bar 2e-2) */
+
+#define COMET_MAX_LEVELS 8
+#define COMET_MAX_RADIUS 7
+
+typedef void* comet_stream_t;
+
+/* ---- library ---------------------------------------------------------- */
+int comet_version(void);
+const char* comet_last_error(void);
+/* 1 if the tcgen05/TMEM/TMA correlation kernels were compiled in and the current device is sm_100. */
+int comet_has_tensor_path(void);
+
+/* ---- feature pyramid: CorrBlock.__init__ / EfficientCorrBlock.__init__,
+ *      comet/models/track_modules/blocks.py:352-374 and :433-444 ------------
+ * Level 0 is the caller's `fmaps` (BS, C, H, W).  Levels 1..L-1 (2x2 average
+ * pooling, stride 2, floor sizes) are written back to back into `pyr`:
+ * level l occupies BS*C*H_l*W_l floats starting at comet_pyramid_offset(l). */
+long long comet_pyramid_offset(int BS, int C, int H, int W, int level); /* elements; level>=1 */
+long long comet_pyramid_elems(int BS, int C, int H, int W, int L);      /* total for levels 1..L-1 */
+int comet_pyramid_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, comet_stream_t stream);
+
+/* ---- correlation volume: CorrBlock.corr, blocks.py:409-429 -------------
+ * vol[bs, n, hw] = (sum_c targets[bs, n, c] * fmap[bs, c, hw]) / sqrt(C) for ONE pyramid level.
+ * Provided for API completeness (CorrBlock.corrs_pyramid); the product path never materialises it. */
+int comet_corr_volume_f32(const float* targets, long long t_sbs, long long t_sn, const float* fmap_level, float* vol,
+                          int BS, int N, int C, int HW, int prec_mode, comet_stream_t stream);
+
+/* ---- fused correlation + window lookup: CorrBlock.corr + CorrBlock.sample
+ *      (blocks.py:376-429, padding zeros) and EfficientCorrBlock.sample
+ *      (blocks.py:446-484, padding border) ---------------------------------
+ * out[b,s,n, l*(2r+1)^2 + i*(2r+1) + j] = bilinear(V_l[b,s,n], x/2^l + (i-r), y/2^l + (j-r))
+ * (the x offset is the slow index, as in the reference).  The volume V_l is never written to memory.
+ * targets: (B,S,N,C) view with element strides t_sb,t_ss,t_sn (C contiguous); t_level_stride = 0, or C for
+ * `multiple_track_feats` (targets then hold L*C channels, level l uses channels [l*C,(l+1)*C)).
+ * coords: (B,S,N,2) view with strides c_sb,c_ss,c_sn.  out: element strides o_sb,o_ss,o_sn, innermost contiguous. */
+int comet_corr_lookup_f32(const float* fmaps, const float* pyr, const float* targets, long long t_sb, long long t_ss,
+                          long long t_sn, int t_level_stride, const float* coords, long long c_sb, long long c_ss,
+                          long long c_sn, float* out, long long o_sb, long long o_ss, long long o_sn, int B, int S,
+                          int N, int C, int H, int W, int L, int r, int pad_mode, int prec_mode,
+                          comet_stream_t stream);
+
+/* ---- fused track tokens: the token assembly of BaseTrackerPredictor.forward,
+ *      comet/models/track_modules/base_track_predictor.py:153-224 ----------
+ * tokens[b,n,s,:] = [ sin/cos(flow) (latent) | flow (2) | fcorrs (L*(2r+1)^2) | track_feats (latent) | 0 pad ]
+ *                   + pos_emb[b,n,:]
+ * with flow = coords[b,s,n] - coords[b,0,n] and fcorrs computed as in comet_corr_lookup_f32 (never stored
+ * separately).  pos_emb (B,N,D_tok) comes from comet_sampled_pos_emb_f32 and is iteration-invariant.
+ * latent == C.  tokens is (B,N,S,D_tok) contiguous. */
+int comet_track_tokens_f32(const float* fmaps, const float* pyr, const float* track_feats, long long t_sb,
+                           long long t_ss, long long t_sn, const float* coords, long long c_sb, long long c_ss,
+                           long long c_sn, const float* pos_emb, float* tokens, int B, int S, int N, int C, int H,
+                           int W, int L, int r, int pad_mode, int prec_mode, int D_tok, comet_stream_t stream);
+
+/* sampled_pos_emb = sample_features4d(get_2d_sincos_pos_embed(D,(H,W)), coords[:,0])
+ * (base_track_predictor.py:200-208; utils.py:724-755, :942-974): the float64 table is evaluated on the fly at
+ * the four integer taps, cast to float32 and blended -- no table is stored.  coords0: (B,N,2) view with strides
+ * c_sb, c_sn.  out (B,N,D) contiguous.  D % 4 == 0. */
+int comet_sampled_pos_emb_f32(const float* coords0, long long c_sb, long long c_sn, float* out, int B, int N, int D,
+                              int H, int W, comet_stream_t stream);
+
+/* ---- samplers: comet/models/utils.py:874-974 --------------------------- */
+/* bilinear_sampler, 4-D input (B,C,H,W), coords (B,Ho,Wo,2)=(x,y) in pixels -> out (B,C,Ho,Wo). */
+int comet_bilinear_sampler4d_f32(const float* input, const float* coords, float* out, int B, int C, int H, int W,
+                                 int Ho, int Wo, int align_corners, int pad_mode, comet_stream_t stream);
+/* bilinear_sampler, 5-D input (B,C,T,H,W), coords (B,Do,Ho,Wo,3)=(t,x,y) -> out (B,C,Do,Ho,Wo). */
+int comet_bilinear_sampler5d_f32(const float* input, const float* coords, float* out, int B, int C, int T, int H,
+                                 int W, int Do, int Ho, int Wo, int align_corners, int pad_mode,
+                                 comet_stream_t stream);
+/* sample_features4d: input (B,C,H,W) with batch stride in_sb (elements), coords (B,R,2) with strides c_sb,c_sr
+ * -> out (B,R,C) contiguous; border padding, align_corners=True. */
+int comet_sample_features4d_f32(const float* input, long long in_sb, const float* coords, long long c_sb,
+                                long long c_sr, float* out, int B, int C, int H, int W, int R,
+                                comet_stream_t stream);
+
+/* ---- sin/cos encodings: comet/models/utils.py:37-101, :724-832 ----------- */
+/* get_2d_embedding(xy, C, cat_coords): xy (M,2) contiguous -> out (M, 2*C [+2 in front if cat_coords]). */
+int comet_embed2d_f32(const float* xy, float* out, long long M, int C, int cat_coords, comet_stream_t stream);
+/* get_1d_sincos_pos_embed_from_grid(D, pos): pos (M) float32 -> out (M, D) = [sin | cos], float64 inside. */
+int comet_sincos1d_from_grid_f32(const float* pos, float* out, long long M, int D, comet_stream_t stream);
+/* get_2d_sincos_pos_embed(D, (H,W)) -> out (D, H, W); channel order [sin_x | cos_x | sin_y | cos_y]. */
+int comet_sincos2d_f32(float* out, int D, int H, int W, comet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COMET_B200_H */

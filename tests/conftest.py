@@ -1,0 +1,56 @@
+"""pytest configuration: the ``gpu`` marker and shared fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+class Golden:
+    """Lazy reader of tests/golden/*.npz."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def __call__(self, name):
+        if name not in self._cache:
+            self._cache[name] = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        return self._cache[name]
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return Golden()
+
+
+def rel_to_max(a, b):
+    """Parity metric of SURVEY.md 8(d): max|a-b| / max|b|."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))

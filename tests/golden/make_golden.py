@@ -1,0 +1,191 @@
+"""Generate the golden fixtures by EXECUTING THE UNMODIFIED REFERENCE.
+
+Run in the build container only (it needs /root/reference, which does not
+exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference hot-path modules are imported in place with the recipe of
+SURVEY.md section 8(c): sys.path = [ref/comet/models, ref, ref/comet] and one
+stub module (``train_eval_func``, imported by comet/models/utils.py:26 only
+for a class that the hot path never touches).  No reference source is copied;
+only tensors produced by running it are stored (``tests/golden/*.npz``).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("COMET_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+
+
+def import_reference():
+    sys.path[:0] = [REF + "/comet/models", REF, REF + "/comet"]
+    stub = types.ModuleType("train_eval_func")
+
+    class QuaternionCameras:  # placeholder, never instantiated on this path
+        pass
+
+    stub.QuaternionCameras = QuaternionCameras
+    sys.modules["train_eval_func"] = stub
+    import torch  # noqa: F401
+    from models.track_modules import blocks
+    from models.track_modules import base_track_predictor as btp
+    import utils as rutils
+
+    return blocks, btp, rutils
+
+
+def digest(*arrays) -> str:
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def main():
+    import torch
+
+    torch.manual_seed(0)
+    torch.set_grad_enabled(False)
+    blocks, btp, ru = import_reference()
+    t = torch.from_numpy
+
+    # ---- CorrBlock / EfficientCorrBlock ---------------------------------
+    out = {}
+    for name, (kw, L, r) in cases.CORR_CASES.items():
+        fmaps, targets, coords = cases.corr_case(**kw)
+        out[name + "/digest"] = np.frombuffer(digest(fmaps, targets, coords).encode(), dtype=np.uint8)
+        cb = blocks.CorrBlock(t(fmaps), num_levels=L, radius=r)
+        cb.corr(t(targets))
+        out[name + "/zeros"] = cb.sample(t(coords)).numpy()
+        if name in ("small_ragged", "tiny_odd"):
+            for l in range(L):
+                out[f"{name}/pyr{l}"] = cb.fmaps_pyramid[l].numpy()
+                out[f"{name}/vol{l}"] = cb.corrs_pyramid[l].numpy()
+        cbb = blocks.CorrBlock(t(fmaps), num_levels=L, radius=r, padding_mode="border")
+        cbb.corr(t(targets))
+        out[name + "/border"] = cbb.sample(t(coords)).numpy()
+        eb = blocks.EfficientCorrBlock(t(fmaps), num_levels=L, radius=r)
+        out[name + "/efficient"] = eb.sample(t(coords), t(targets)).numpy()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            ca = blocks.CorrBlock(t(fmaps), num_levels=L, radius=r)
+            ca.corr(t(targets))
+            assert ca.corrs_pyramid[0].dtype == torch.bfloat16
+            out[name + "/zeros_bf16"] = ca.sample(t(coords)).float().numpy()
+    save("corr_blocks", **out)
+
+    # ---- samplers / encodings ------------------------------------------
+    out = {}
+    inp, xy = cases.sampler_case(21, B=2, C=3, H=9, W=7, Ho=4, Wo=5)
+    for pm in ("zeros", "border"):
+        for ac in (True, False):
+            out[f"bs4/{pm}/{int(ac)}"] = ru.bilinear_sampler(t(inp), t(xy), align_corners=ac, padding_mode=pm).numpy()
+    inp5, txy = cases.sampler_case(22, B=2, C=3, H=6, W=8, Ho=3, Wo=4, T=3)
+    for pm in ("zeros", "border"):
+        out[f"bs5/{pm}"] = ru.bilinear_sampler(t(inp5), t(txy), padding_mode=pm).numpy()
+    inp1, txy1 = cases.sampler_case(23, B=2, C=4, H=6, W=8, Ho=3, Wo=4, T=1)
+    txy1[..., 0] = 0
+    out["bs5_t1/border"] = ru.bilinear_sampler(t(inp1), t(txy1)).numpy()
+    rng = np.random.default_rng(24)
+    pts = np.stack([rng.uniform(-1, 8, (2, 11)), rng.uniform(-1, 10, (2, 11))], -1).astype(np.float32)
+    out["sf4d/pts"] = pts
+    out["sf4d/out"] = ru.sample_features4d(t(inp), t(pts)).numpy()
+    for C, scale in ((64, 3.0), (16, 0.7), (64, 40.0)):
+        xyv = cases.embed_case(30 + C, 3, 5, scale)
+        out[f"emb2d/{C}/{scale}/xy"] = xyv
+        out[f"emb2d/{C}/{scale}/nocat"] = ru.get_2d_embedding(t(xyv), C, cat_coords=False).numpy()
+        out[f"emb2d/{C}/{scale}/cat"] = ru.get_2d_embedding(t(xyv), C, cat_coords=True).numpy()
+    out["sincos2d/216_31"] = ru.get_2d_sincos_pos_embed(216, (31, 31)).numpy()
+    full = ru.get_2d_sincos_pos_embed(664, (64, 64)).numpy()
+    out["sincos2d/664_64/rows"] = full[:, :, ::9, :]  # every 9th row, all columns/channels
+    out["sincos2d/664_64/sum"] = np.array([full.astype(np.float64).sum(), np.abs(full).astype(np.float64).sum()])
+    out["sincos2d/12_h3w5"] = ru.get_2d_sincos_pos_embed(12, (3, 5)).numpy()
+    pe, grid = ru.get_2d_sincos_pos_embed(8, 4, return_grid=True)
+    out["sincos2d/8_4"], out["sincos2d/8_4/grid"] = pe.numpy(), grid.numpy()
+    out["sincos1d/768_16"] = ru.get_1d_sincos_pos_embed(768, 16).numpy()
+    out["sincos1d/768_64"] = ru.get_1d_sincos_pos_embed(768, 64).numpy()
+    pe1, g1 = ru.get_1d_sincos_pos_embed(10, 7, return_grid=True)
+    out["sincos1d/10_7"], out["sincos1d/10_7/grid"] = pe1.numpy(), g1.numpy()
+    pos = np.array([0.0, 0.5, 3.25, 100.0, -2.0], dtype=np.float32)
+    out["sincos1dgrid/pos"] = pos
+    out["sincos1dgrid/14"] = ru.get_1d_sincos_pos_embed_from_grid(14, t(pos)).numpy()
+    save("samplers_encodings", **out)
+
+    # ---- BaseTrackerPredictor: tokens and refinement loop ---------------
+    from types import SimpleNamespace as NS
+
+    def cfg(eff=False, conf=False):
+        return NS(track_conf=conf, MODEL=NS(TRACK=NS(efficient_corr=eff)))
+
+    class Abort(Exception):
+        pass
+
+    out = {}
+    # (name, ctor kwargs, case kwargs, iters, down_ratio, eff, abort_after_first)
+    specs = [
+        ("coarse_tiny", dict(stride=4, corr_levels=5, corr_radius=2, latent_dim=16, hidden_size=32, depth=1,
+                             use_spaceatt=True, fine=False),
+         dict(seed=41, B=1, S=4, C=16, H=16, W=16, N=7, stride=4, down_ratio=2), 3, 2, False, False),
+        ("coarse_tiny_eff", dict(stride=4, corr_levels=2, corr_radius=3, latent_dim=16, hidden_size=32, depth=1,
+                                 use_spaceatt=True, fine=False),
+         dict(seed=42, B=1, S=4, C=16, H=16, W=16, N=7, stride=4, down_ratio=2), 2, 2, True, False),
+        ("fine_tiny", dict(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=32, depth=1,
+                           use_spaceatt=False, fine=True),
+         dict(seed=43, B=5, S=3, C=32, H=31, W=31, N=1, stride=1, down_ratio=1), 2, 1, False, False),
+        ("coarse_full_it0", dict(stride=4, corr_levels=5, corr_radius=4, latent_dim=128, hidden_size=16, depth=1,
+                                 use_spaceatt=True, fine=False),
+         dict(seed=44, B=1, S=3, C=128, H=64, W=64, N=16, stride=4, down_ratio=2), 1, 2, False, True),
+        ("fine_full_it0", dict(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=16, depth=1,
+                               use_spaceatt=False, fine=True),
+         dict(seed=45, B=8, S=3, C=32, H=31, W=31, N=1, stride=1, down_ratio=1), 1, 1, False, True),
+    ]
+    for name, ck, case_kw, iters, dr, eff, abort in specs:
+        torch.manual_seed(7)
+        m = btp.BaseTrackerPredictor(cfg=cfg(eff), **ck).eval()
+        fmaps, q = cases.tracker_case(**case_kw)
+        toks = []
+
+        def hook(mod, args):
+            toks.append(args[0].detach().clone().numpy())
+            if abort:
+                raise Abort()
+
+        h = m.updateformer.register_forward_pre_hook(hook)
+        try:
+            res = m(query_points=t(q), fmaps=t(fmaps), iters=iters, return_feat=True, down_ratio=dr,
+                    TRACKorPOSE=False)
+        except Abort:
+            res = None
+        h.remove()
+        out[name + "/digest"] = np.frombuffer(digest(fmaps, q).encode(), dtype=np.uint8)
+        for i, x in enumerate(toks):
+            out[f"{name}/tok{i}"] = x
+        if res is not None:
+            preds, vis, tf, qf, conf = res
+            for i, p in enumerate(preds):
+                out[f"{name}/pred{i}"] = p.numpy()
+            if vis is not None:
+                out[name + "/vis"] = vis.numpy()
+            out[name + "/track_feats"] = tf.numpy()
+            out[name + "/query_feat"] = qf.numpy()
+            for k, v in m.state_dict().items():
+                out[f"{name}/sd/{k}"] = v.numpy()
+    save("tracker", **out)
+
+
+if __name__ == "__main__":
+    main()
