@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the COMET tracking hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch Q] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "batched inference, seqlen=16, synthetic sequences on 1xB200"): one *step*
+is one pass of the hot path over a batch of Q synthetic 16-frame sequences per GPU.  Per sequence that is
+exactly what COMET.forward_all makes the tracker's correlation / lookup / token code do:
+
+  coarse tracker  fmaps (1,16,128,64,64), N=512 tracks, L=5, r=4:  pyramid + pos-emb once, then 4 iterations of
+                  [correlation -> 9x9x5 window lookup -> track tokens (1,512,16,664)]
+  fine tracker    patch features (512,16,32,31,31), 1 track/patch, L=3, r=3: pyramid + pos-emb once, then
+                  6 iterations of [correlation -> 7x7x3 lookup -> tokens (512,1,16,216)]
+
+The update transformer that runs between iterations is outside the path, so every iteration reads its
+own pre-generated coords / track_feats (seeded random walk around the query points) -- the bytes and flops of the
+path are exactly those of the real loop.  metric = sequences/s (whole job, all GPUs).
+
+  value  inputs already resident in HBM when the timed region starts
+  e2e    same pass through the public Python API with HOST (pinned) buffers: H2D of every input and D2H of the
+         last-iteration tokens inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+COARSE = dict(S=16, N=512, C=128, H=64, W=64, L=5, r=4, iters=4, fine=False)
+FINE = dict(S=16, P=512, C=32, H=31, W=31, L=3, r=3, iters=6, fine=True)
+METRIC = "sequences/sec (seqlen=16)"
+UNIT = "sequences/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tdim(L, r, latent, fine):
+    d = L * (2 * r + 1) ** 2 + 2 * latent
+    if fine:
+        d += 4 if d % 2 == 0 else 5
+    else:
+        d += (4 - d % 4) % 4
+    return d
+
+
+# --------------------------------------------------------------------------- synthetic inputs (host, seeded)
+def make_inputs(Q, seed, torch, pin):
+    """Host tensors for Q sequences.  SURVEY 8(d) item 5: fmaps ~ N(0,1); queries U over the map; per-iteration
+    coords = query + small random walk (frame 0 pinned); per-iteration track_feats ~ N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def alloc(*shape):
+        t = torch.empty(*shape, dtype=torch.float32)
+        return t.pin_memory() if pin else t
+
+    out = {}
+    for name, cfg, B, N in (("coarse", COARSE, Q, COARSE["N"]), ("fine", FINE, Q * FINE["P"], 1)):
+        S, C, H, W, it = cfg["S"], cfg["C"], cfg["H"], cfg["W"], cfg["iters"]
+        fm = alloc(B, S, C, H, W)
+        fm.normal_(generator=g)
+        q = torch.rand(B, 1, N, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
+        coords = alloc(it, B, S, N, 2)
+        feats = alloc(it, B, S, N, C)
+        feats.normal_(generator=g)
+        walk = torch.zeros(B, S, N, 2)
+        for i in range(it):
+            walk = walk + torch.randn(B, S, N, 2, generator=g) * 0.75
+            c = q + walk
+            c[:, 0] = q[:, 0]
+            coords[i].copy_(c)
+        out[name] = dict(fmaps=fm, coords=coords, feats=feats)
+    return out
+
+
+# --------------------------------------------------------------------------- our arm
+class HotPath:
+    """The hot path of one batch through the public API of comet_pose_estimation_b200."""
+
+    def __init__(self, cb, torch, Q, dev):
+        self.cb, self.torch, self.Q, self.dev = cb, torch, Q, dev
+        self.td_c = tdim(COARSE["L"], COARSE["r"], COARSE["C"], False)
+        self.td_f = tdim(FINE["L"], FINE["r"], FINE["C"], True)
+        self.tok_c = torch.empty(Q, COARSE["N"], COARSE["S"], self.td_c, device=dev)
+        self.tok_f = torch.empty(Q * FINE["P"], 1, FINE["S"], self.td_f, device=dev)
+        self.launches_per_step = (COARSE["L"] - 1) + 1 + COARSE["iters"] + (FINE["L"] - 1) + 1 + FINE["iters"]
+        self.events = None  # optional per-kernel timing
+
+    def _mark(self, tag):
+        if self.events is not None:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.events.append((tag, e))
+
+    def run(self, d):
+        cb = self.cb
+        for name, cfg, out in (("coarse", COARSE, self.tok_c), ("fine", FINE, self.tok_f)):
+            x = d[name]
+            self._mark(None)
+            blk = cb.CorrBlock(x["fmaps"], num_levels=cfg["L"], radius=cfg["r"])
+            self._mark(name + "_pyramid")
+            tk = cb.TrackTokenizer(blk, x["coords"][0][:, 0], out.shape[-1])
+            self._mark(name + "_posemb")
+            for i in range(cfg["iters"]):
+                tk.tokens(x["coords"][i], x["feats"][i], out=out)
+                self._mark(name + "_tokens")
+        return self.tok_c, self.tok_f
+
+
+def algorithmic_bytes(Q):
+    """DESIGN.md section 5.  Per launch of the fused token kernel."""
+    c, f = COARSE, FINE
+    tdc, tdf = tdim(c["L"], c["r"], c["C"], False), tdim(f["L"], f["r"], f["C"], True)
+    # coarse: SURVEY 8(d) compulsory traffic (whole level-0 map + targets + coords + tokens)
+    coarse = Q * (c["S"] * c["C"] * c["H"] * c["W"] * 4 + c["S"] * c["N"] * c["C"] * 4 + c["S"] * c["N"] * 8
+                  + c["N"] * c["S"] * tdc * 4)
+    # fine: window-neighbourhood definition (the 194 MB figure): the (2r+2)^2 taps of every level,
+    # clipped to the level size, + target + coords + token row (+ pos-emb row amortised over S)
+    G = 2 * f["r"] + 2
+    taps, h, w = 0, f["H"], f["W"]
+    for _ in range(f["L"]):
+        taps += min(G, h) * min(G, w)
+        h, w = h // 2, w // 2
+    per_q = taps * f["C"] * 4 + f["C"] * 4 + 8 + tdf * 4 + tdf * 4 / f["S"]
+    fine = Q * f["P"] * f["S"] * per_q
+    pyr_c = Q * c["S"] * c["C"] * 4 * (64 * 64 + 2 * (32 * 32 + 16 * 16 + 8 * 8) + 4 * 4)
+    pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (31 * 31 + 2 * 15 * 15 + 7 * 7)
+    return dict(coarse_tokens=coarse, fine_tokens=fine, coarse_pyramid=pyr_c, fine_pyramid=pyr_f)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            txt = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            txt = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in txt.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_seq_per_s(torch, reps):
+    """Times the CPU port of the same hot path (oracle/torch_port.py: the reference's own ATen calls) on the host
+    cores: ONE sequence per rep (coarse 4 iterations + fine 6 iterations, pyramids included)."""
+    from oracle import torch_port as P
+
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    d = make_inputs(1, 1234, torch, pin=False)
+    times = []
+    with torch.no_grad():
+        for rep in range(reps + 1):
+            t0 = time.perf_counter()
+            for name, cfg in (("coarse", COARSE), ("fine", FINE)):
+                x = d[name]
+                td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
+                lv = P.pyramid(x["fmaps"], cfg["L"])
+                for i in range(cfg["iters"]):
+                    P.hot_path_iteration(lv, x["coords"][i], x["feats"][i], cfg["r"], (cfg["H"], cfg["W"]), td)
+            dt = time.perf_counter() - t0
+            if rep > 0 or reps == 0:
+                times.append(dt)
+    return 1.0 / min(times), statistics.mean(times), ncores
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    t0 = time.perf_counter()
+    # warmup + K steps, each step = one sequence (bounded sample of the batch workload)
+    from oracle import torch_port as P  # noqa: F401
+
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    d = make_inputs(1, 1234, torch, pin=False)
+
+    def one():
+        with torch.no_grad():
+            for name, cfg in (("coarse", COARSE), ("fine", FINE)):
+                x = d[name]
+                td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
+                lv = P.pyramid(x["fmaps"], cfg["L"])
+                for i in range(cfg["iters"]):
+                    P.hot_path_iteration(lv, x["coords"][i], x["feats"][i], cfg["r"], (cfg["H"], cfg["W"]), td)
+
+    for _ in range(args.warmup):
+        one()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    el = time.perf_counter() - t1
+    v = args.steps / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(1), "note": "CPU: one sequence per step (bounded sample of the batch)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
+                         "sample": "1 sequence/step: coarse 4 it + fine 6 it, pyramids included; torch CPU fp32"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(Q):
+    return (f"COMET tracking hot path, batch of {Q} synthetic 16-frame sequences per GPU: coarse "
+            f"(S=16,N=512,C=128,64x64,L=5,r=4,4 it) + fine (512 patches,S=16,C=32,31x31,L=3,r=3,6 it); "
+            f"pyramid + pos-emb + fused corr/lookup/token kernels")
+
+
+# --------------------------------------------------------------------------- main (our arm)
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4, help="sequences per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    import comet_pose_estimation_b200 as cb
+
+    Q = args.batch
+    host = make_inputs(Q, 1000 + rank, torch, pin=True)
+    devin = {k: {n: t.to(dev, non_blocking=True) for n, t in v.items()} for k, v in host.items()}
+    torch.cuda.synchronize()
+    hp = HotPath(cb, torch, Q, dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        hp.run(devin)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    hp.events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        hp.run(devin)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    events, hp.events = hp.events, None
+    ms_step = ms_total / args.steps
+    value = Q * world / (ms_step * 1e-3)
+
+    # per-kernel-class device time from the events recorded inside the timed region
+    per = {}
+    for (t0, a), (t1, b) in zip(events[:-1], events[1:]):
+        if t1 is None:
+            continue
+        per.setdefault(t1, []).append(a.elapsed_time(b))
+    kern = {k: {"launch_groups": len(v), "ms_avg": sum(v) / len(v), "ms_per_step": sum(v) / args.steps}
+            for k, v in per.items()}
+    ab = algorithmic_bytes(Q)
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    peak, peak_src = peaks()
+    for k in kern:
+        if k in ab:
+            kern[k]["algorithmic_MB"] = ab[k] / 1e6
+            kern[k]["GBps"] = ab[k] / (kern[k]["ms_avg"] * 1e-3) / 1e9
+    ft = kern["fine_tokens"]
+    roof = {"bound": "hbm", "kernel": "corr_lookup_kernel<TOKENS> (fine tracker shape)", "achieved": ft["GBps"],
+            "peak": peak, "unit": "GB/s", "frac": ft["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab["fine_tokens"], "ms_per_launch": ft["ms_avg"],
+            "dominant_by_time": dom}
+
+    # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------
+    e2e = None
+    if not args.no_e2e:
+        td_c, td_f = hp.tok_c, hp.tok_f
+        out_c = torch.empty(td_c.shape, dtype=torch.float32).pin_memory()
+        out_f = torch.empty(td_f.shape, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * 4 for v in host.values() for t in v.values())
+        d2h = out_c.numel() * 4 + out_f.numel() * 4
+        stage = {k: {n: torch.empty_like(t, device=dev) for n, t in v.items()} for k, v in host.items()}
+
+        def e2e_step():
+            for k, v in host.items():
+                for n, t in v.items():
+                    stage[k][n].copy_(t, non_blocking=True)
+            a, b = hp.run(stage)
+            out_c.copy_(a, non_blocking=True)
+            out_f.copy_(b, non_blocking=True)
+
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        e2e = {"value": Q * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": n_e2e,
+               "api": "CorrBlock + TrackTokenizer (ctypes -> C ABI), pinned host tensors"}
+        del stage
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, mean_s, ncores = cpu_reference_seq_per_s(torch, args.cpu_reps)
+        cpu = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
+               "sample": f"1 sequence x {args.cpu_reps} reps (best), oracle/torch_port.py (reference's ATen calls), "
+                         f"fp32, {mean_s:.2f} s/sequence mean"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
+                       "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
+                       "l2": "inputs per step exceed L2 (fine patch features: %.1f GB)" % (Q * 1.008)},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": hp.launches_per_step * args.steps, "kernels": kern,
+            "tensor_path": bool(cb._lib.lib.comet_has_tensor_path()),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,84 @@
+"""The C-ABI shared library builds, loads, and exports exactly what include/comet_b200.h declares.
+No compute call is made here (no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from comet_pose_estimation_b200 import build
+
+    return build.build()
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "comet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(comet_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built):
+    names = _declared()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(built)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/comet_b200.h but not exported"
+
+
+def test_binding_table_matches_header(built):
+    from comet_pose_estimation_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == _declared()
+    assert _lib.lib.comet_version() >= 100
+
+
+def test_pyramid_geometry_helpers(built):
+    from comet_pose_estimation_b200 import _lib
+
+    lib = _lib.lib
+    # coarse: 64 -> 32 -> 16 -> 8 -> 4 ; fine: 31 -> 15 -> 7 (floor)
+    assert lib.comet_pyramid_elems(16, 128, 64, 64, 5) == 16 * 128 * (32 * 32 + 16 * 16 + 8 * 8 + 4 * 4)
+    assert lib.comet_pyramid_elems(2, 32, 31, 31, 3) == 2 * 32 * (15 * 15 + 7 * 7)
+    assert lib.comet_pyramid_offset(2, 32, 31, 31, 1) == 0
+    assert lib.comet_pyramid_offset(2, 32, 31, 31, 2) == 2 * 32 * 15 * 15
+    assert lib.comet_pyramid_elems(1, 1, 8, 8, 1) == 0
+
+
+def test_invalid_arguments_are_reported_without_a_gpu(built):
+    """Argument validation happens before any CUDA call and maps to AssertionError like the reference's asserts."""
+    from comet_pose_estimation_b200 import _lib
+
+    rc = _lib.lib.comet_pyramid_f32(None, None, 1, 4, 8, 8, 9, None)
+    assert rc == _lib.ERR_INVALID and "num_levels" in _lib.last_error()
+    with pytest.raises(AssertionError):
+        _lib.check(rc)
+    rc = _lib.lib.comet_corr_lookup_f32(None, None, None, 0, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0,
+                                        1, 1, 1, 4, 8, 8, 2, 9, 0, 0, None)
+    assert rc == _lib.ERR_INVALID and "radius" in _lib.last_error()
+    rc = _lib.lib.comet_sincos2d_f32(None, 10, 4, 4, None)
+    assert rc == _lib.ERR_INVALID
+
+
+def test_no_cpu_fallback(built):
+    import torch
+
+    import comet_pose_estimation_b200 as cb
+
+    with pytest.raises(cb._lib.CometB200Error):
+        cb.CorrBlock(torch.zeros(1, 1, 4, 8, 8))
+    with pytest.raises(cb._lib.CometB200Error):
+        cb.bilinear_sampler(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 1, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "comet_pose_estimation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f"{f} imports the oracle"

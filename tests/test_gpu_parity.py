@@ -1,0 +1,310 @@
+"""Parity of the CUDA path (through the Python mirror -> ctypes -> C ABI) against the reference goldens and the
+CPU oracle.  Bars: fp32 max|a-b|/max|b| <= 1e-4; bf16-autocast <= 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_to_max
+from oracle import comet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_BAR = 1e-4
+BF16_BAR = 2e-2
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import comet_pose_estimation_b200 as m
+
+    return m
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().float().cpu().numpy()
+
+
+# ------------------------------------------------------------------ CorrBlock
+@pytest.mark.parametrize("name", list(cases.CORR_CASES))
+def test_corrblock_vs_reference_golden(cb, golden, name):
+    g = golden("corr_blocks")
+    kw, L, r = cases.CORR_CASES[name]
+    fmaps, targets, coords = cases.corr_case(**kw)
+    blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r)
+    blk.corr(dev(targets))
+    out = blk.sample(dev(coords))
+    assert out.shape == g[name + "/zeros"].shape and out.is_contiguous() and out.dtype == torch.float32
+    assert rel_to_max(host(out), g[name + "/zeros"]) < FP32_BAR
+    blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r, padding_mode="border")
+    blk.corr(dev(targets))
+    assert rel_to_max(host(blk.sample(dev(coords))), g[name + "/border"]) < FP32_BAR
+    eff = cb.EfficientCorrBlock(dev(fmaps), num_levels=L, radius=r)
+    assert rel_to_max(host(eff.sample(dev(coords), dev(targets))), g[name + "/efficient"]) < FP32_BAR
+
+
+@pytest.mark.parametrize("name", ["small_ragged", "tiny_odd"])
+def test_pyramid_and_lazy_volumes(cb, golden, name):
+    g = golden("corr_blocks")
+    kw, L, r = cases.CORR_CASES[name]
+    fmaps, targets, _ = cases.corr_case(**kw)
+    blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r)
+    with pytest.raises(AttributeError):
+        blk.corrs_pyramid
+    blk.corr(dev(targets))
+    assert len(blk.fmaps_pyramid) == L and len(blk.corrs_pyramid) == L
+    for l in range(L):
+        assert tuple(blk.fmaps_pyramid[l].shape) == g[f"{name}/pyr{l}"].shape
+        assert rel_to_max(host(blk.fmaps_pyramid[l]), g[f"{name}/pyr{l}"]) < 1e-6
+        assert rel_to_max(host(blk.corrs_pyramid[l]), g[f"{name}/vol{l}"]) < FP32_BAR
+
+
+@pytest.mark.parametrize("name", list(cases.CORR_CASES))
+def test_bf16_autocast_mode(cb, golden, name):
+    g = golden("corr_blocks")
+    kw, L, r = cases.CORR_CASES[name]
+    fmaps, targets, coords = cases.corr_case(**kw)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r)
+        blk.corr(dev(targets))
+        out = blk.sample(dev(coords))
+    assert out.dtype == torch.float32
+    assert rel_to_max(host(out), g[name + "/zeros_bf16"]) < BF16_BAR
+    # and it really is the bf16 variant, not the fp32 one
+    assert rel_to_max(host(out), O.corr_lookup_bf16_autocast(fmaps, targets, coords, L, r)) < 4e-3
+
+
+def test_strided_views_and_multiple_track_feats(cb):
+    kw, L, r = cases.CORR_CASES["small_ragged"]
+    fmaps, targets, coords = cases.corr_case(**kw)
+    want = O.corr_lookup(fmaps, targets, coords, L, r)
+    # targets / coords handed over as permuted (B,N,S,.) storage, like track_feats in the tracker loop
+    t_perm = dev(targets.transpose(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    c_perm = dev(coords.transpose(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    assert not t_perm.is_contiguous()
+    blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r)
+    blk.corr(t_perm)
+    assert rel_to_max(host(blk.sample(c_perm)), want) < FP32_BAR
+    # multiple_track_feats: level l correlates channels [l*C, (l+1)*C) of the target (blocks.py:411-425)
+    rng = np.random.default_rng(5)
+    B, S, N, C = targets.shape
+    big = rng.standard_normal((B, S, N, C * L)).astype(np.float32)
+    pyr = O.build_pyramid(fmaps, L)
+    vols = [O.corr_volumes(big[..., l * C:(l + 1) * C], [pyr[l]])[0] for l in range(L)]
+    want = O.lookup_volumes(vols, coords, r, "zeros")
+    blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r, multiple_track_feats=True)
+    blk.corr(dev(big))
+    assert rel_to_max(host(blk.sample(dev(coords))), want) < FP32_BAR
+    for l in range(L):
+        assert rel_to_max(host(blk.corrs_pyramid[l]), vols[l]) < FP32_BAR
+
+
+def test_edge_cases(cb):
+    # empty track set
+    f = torch.randn(1, 2, 8, 8, 8, device="cuda")
+    blk = cb.CorrBlock(f, num_levels=2, radius=2)
+    blk.corr(torch.zeros(1, 2, 0, 8, device="cuda"))
+    out = blk.sample(torch.zeros(1, 2, 0, 2, device="cuda"))
+    assert out.shape == (1, 2, 0, 50)
+    # reference assertions (blocks.py:379, :415-416)
+    with pytest.raises(AssertionError):
+        blk.corr(torch.zeros(1, 2, 3, 7, device="cuda"))
+    with pytest.raises(AssertionError):
+        blk.corr(torch.zeros(1, 3, 3, 8, device="cuda"))
+    blk.corr(torch.zeros(1, 2, 3, 8, device="cuda"))
+    with pytest.raises(AssertionError):
+        blk.sample(torch.zeros(1, 2, 3, 3, device="cuda"))
+    with pytest.raises(AssertionError):  # pyramid deeper than the map
+        cb.CorrBlock(torch.randn(1, 1, 4, 4, 4, device="cuda"), num_levels=4)
+    # wild coordinates: far outside / huge -> zeros under zero padding, finite under border
+    kw, L, r = cases.CORR_CASES["deep_pyramid"]
+    fmaps, targets, coords = cases.corr_case(**kw)
+    coords[..., 0] = 1.0e9
+    coords[0, 0, 0] = (-1.0e9, 3.0)
+    blk = cb.CorrBlock(dev(fmaps), num_levels=L, radius=r)
+    blk.corr(dev(targets))
+    assert float(blk.sample(dev(coords)).abs().max()) == 0.0
+    eff = cb.EfficientCorrBlock(dev(fmaps), num_levels=L, radius=r)
+    assert bool(torch.isfinite(eff.sample(dev(coords), dev(targets))).all())
+    # maximum radius / level count the kernels accept
+    f = torch.randn(1, 1, 4, 128, 128, device="cuda")
+    t = torch.randn(1, 1, 3, 4, device="cuda")
+    c = torch.rand(1, 1, 3, 2, device="cuda") * 127
+    blk = cb.CorrBlock(f, num_levels=8, radius=7)
+    blk.corr(t)
+    want = O.corr_lookup(host(f), host(t), host(c), 8, 7)
+    assert rel_to_max(host(blk.sample(c)), want) < FP32_BAR
+
+
+# ------------------------------------------------------------------ samplers / encodings
+def test_samplers_vs_reference_golden(cb, golden):
+    g = golden("samplers_encodings")
+    inp, xy = cases.sampler_case(21, B=2, C=3, H=9, W=7, Ho=4, Wo=5)
+    for pm in ("zeros", "border"):
+        for ac in (True, False):
+            got = cb.bilinear_sampler(dev(inp), dev(xy), align_corners=ac, padding_mode=pm)
+            assert rel_to_max(host(got), g[f"bs4/{pm}/{int(ac)}"]) < FP32_BAR
+    inp5, txy = cases.sampler_case(22, B=2, C=3, H=6, W=8, Ho=3, Wo=4, T=3)
+    for pm in ("zeros", "border"):
+        assert rel_to_max(host(cb.bilinear_sampler(dev(inp5), dev(txy), padding_mode=pm)), g[f"bs5/{pm}"]) < FP32_BAR
+    inp1, txy1 = cases.sampler_case(23, B=2, C=4, H=6, W=8, Ho=3, Wo=4, T=1)
+    txy1[..., 0] = 0
+    assert rel_to_max(host(cb.bilinear_sampler(dev(inp1), dev(txy1))), g["bs5_t1/border"]) < FP32_BAR
+    assert rel_to_max(host(cb.sample_features4d(dev(inp), dev(g["sf4d/pts"]))), g["sf4d/out"]) < FP32_BAR
+    # batch-strided view (fmaps[:, 0]) and batch-expanded table
+    big = torch.randn(2, 3, 3, 9, 7, device="cuda")
+    pts = dev(g["sf4d/pts"])
+    assert rel_to_max(host(cb.sample_features4d(big[:, 1], pts)), O.sample_features4d(host(big[:, 1]), host(pts))) < FP32_BAR
+    tab = torch.randn(1, 3, 9, 7, device="cuda").expand(2, -1, -1, -1)
+    assert rel_to_max(host(cb.sample_features4d(tab, pts)), O.sample_features4d(host(tab), host(pts))) < FP32_BAR
+    with pytest.raises(AssertionError):
+        cb.bilinear_sampler(torch.zeros(1, 2, 3, device="cuda"), torch.zeros(1, 1, 1, 2, device="cuda"))
+
+
+def test_encodings_vs_reference_golden(cb, golden):
+    g = golden("samplers_encodings")
+    for C, scale in ((64, 3.0), (16, 0.7), (64, 40.0)):
+        xy = g[f"emb2d/{C}/{scale}/xy"]
+        # same float32 argument, accurate sinf/cosf: absolute error of a few ulp of 1.0
+        assert np.abs(host(cb.get_2d_embedding(dev(xy), C, cat_coords=False)) - g[f"emb2d/{C}/{scale}/nocat"]).max() < 2e-6
+        assert np.abs(host(cb.get_2d_embedding(dev(xy), C, cat_coords=True)) - g[f"emb2d/{C}/{scale}/cat"]).max() < 2e-6
+    assert np.abs(host(cb.get_2d_sincos_pos_embed(216, (31, 31))) - g["sincos2d/216_31"]).max() < 2e-7
+    full = host(cb.get_2d_sincos_pos_embed(664, (64, 64)))
+    assert full.shape == (1, 664, 64, 64)
+    assert np.abs(full[:, :, ::9, :] - g["sincos2d/664_64/rows"]).max() < 2e-7
+    assert abs(full.astype(np.float64).sum() - g["sincos2d/664_64/sum"][0]) < 1e-2
+    assert np.abs(host(cb.get_2d_sincos_pos_embed(12, (3, 5))) - g["sincos2d/12_h3w5"]).max() < 2e-7
+    pe, grid = cb.get_2d_sincos_pos_embed(8, 4, return_grid=True)
+    assert np.abs(host(pe) - g["sincos2d/8_4"]).max() < 2e-7 and np.array_equal(host(grid), g["sincos2d/8_4/grid"])
+    assert np.abs(host(cb.get_1d_sincos_pos_embed(768, 16)) - g["sincos1d/768_16"]).max() < 2e-7
+    assert np.abs(host(cb.get_1d_sincos_pos_embed(768, 64)) - g["sincos1d/768_64"]).max() < 2e-7
+    pe1, g1 = cb.get_1d_sincos_pos_embed(10, 7, return_grid=True)
+    assert np.abs(host(pe1) - g["sincos1d/10_7"]).max() < 2e-7 and np.array_equal(host(g1), g["sincos1d/10_7/grid"])
+    got = cb.get_1d_sincos_pos_embed_from_grid(14, dev(g["sincos1dgrid/pos"]))
+    assert np.abs(host(got) - g["sincos1dgrid/14"]).max() < 2e-7
+    grid = torch.stack([torch.arange(6.0), torch.arange(6.0) * 0.5]).cuda()
+    got = cb.get_2d_sincos_pos_embed_from_grid(12, grid)
+    want = O.get_2d_sincos_pos_embed_from_grid(12, host(grid))
+    assert got.shape == want.shape and np.abs(host(got) - want).max() < 2e-7
+
+
+# ------------------------------------------------------------------ fused track tokens
+TOKEN_CASES = {
+    "coarse_full_it0": (dict(seed=44, B=1, S=3, C=128, H=64, W=64, N=16, stride=4, down_ratio=2), 5, 4, 128, False, 8.0),
+    "fine_full_it0": (dict(seed=45, B=8, S=3, C=32, H=31, W=31, N=1, stride=1, down_ratio=1), 3, 3, 32, True, 1.0),
+}
+
+
+@pytest.mark.parametrize("name", list(TOKEN_CASES))
+def test_first_iteration_tokens_vs_reference_golden(cb, golden, name):
+    g = golden("tracker")
+    kw, L, r, latent, fine, qscale = TOKEN_CASES[name]
+    fmaps, q = cases.tracker_case(**kw)
+    B, S = fmaps.shape[:2]
+    N = q.shape[1]
+    q = dev(q) / qscale
+    coords = q.reshape(B, 1, N, 2).repeat(1, S, 1, 1)
+    f = dev(fmaps)
+    qfeat = cb.sample_features4d(f[:, 0], coords[:, 0])
+    feats = qfeat.unsqueeze(1).repeat(1, S, 1, 1)
+    tdim = cb.transformer_dim(L, r, latent, fine)
+    want = g[name + "/tok0"]
+    assert tdim == want.shape[-1]
+    tok = cb.TrackTokenizer(cb.CorrBlock(f, num_levels=L, radius=r), coords[:, 0], tdim)
+    x = tok.tokens(coords, feats)
+    assert tuple(x.shape) == want.shape
+    assert rel_to_max(host(x), want) < FP32_BAR
+
+
+def test_tokens_with_motion_vs_oracle(cb):
+    """Later iterations: coords differ per frame (non-zero flows with sin/cos arguments up to ~1e4), track_feats
+    arrive as a permuted (B,N,S,C) view, as in base_track_predictor.py:243-252."""
+    rng = np.random.default_rng(3)
+    B, S, N, C, H, W, L, r = 2, 5, 11, 32, 24, 20, 3, 3
+    fmaps = rng.standard_normal((B, S, C, H, W)).astype(np.float32)
+    feats = rng.standard_normal((B, S, N, C)).astype(np.float32)
+    c0 = np.stack([rng.uniform(0, W - 1, (B, N)), rng.uniform(0, H - 1, (B, N))], -1).astype(np.float32)
+    coords = c0[:, None] + (rng.standard_normal((B, S, N, 2)) * 3).astype(np.float32)
+    coords[:, 0] = c0
+    for fine in (False, True):
+        tdim = O.transformer_dim(L, r, C, fine)
+        want = O.track_tokens(O.corr_lookup(fmaps, feats, coords, L, r), coords, feats, (H, W), tdim)
+        f = dev(fmaps)
+        feats_view = dev(feats.transpose(0, 2, 1, 3)).permute(0, 2, 1, 3)
+        tok = cb.TrackTokenizer(f, dev(c0), tdim, num_levels=L, radius=r)
+        x = tok.tokens(dev(coords), feats_view)
+        assert rel_to_max(host(x), want) < FP32_BAR
+        # EfficientCorrBlock flavour (border padding)
+        want_b = O.track_tokens(O.efficient_corr_lookup(fmaps, feats, coords, L, r), coords, feats, (H, W), tdim)
+        tok_b = cb.TrackTokenizer(cb.EfficientCorrBlock(f, num_levels=L, radius=r), dev(c0), tdim)
+        assert rel_to_max(host(tok_b.tokens(dev(coords), dev(feats))), want_b) < FP32_BAR
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs)
+def _full_coarse(S, N, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    fmaps = torch.randn(1, S, 128, 64, 64, device="cuda", generator=g)
+    feats = torch.randn(1, S, N, 128, device="cuda", generator=g)
+    coords = torch.rand(1, S, N, 2, device="cuda", generator=g) * 63
+    wild = torch.rand(1, S, N, 1, device="cuda", generator=g) < 0.05
+    coords = torch.where(wild, torch.rand(1, S, N, 2, device="cuda", generator=g) * 76 - 6, coords)
+    return fmaps, feats, coords
+
+
+def test_full_size_coarse_config_subset_vs_oracle(cb):
+    """Config 1/2 shape (S=16, N=512, C=128, 64x64, L=5, r=4): queries are independent, so the oracle checks a
+    slice of them in seconds while the kernel runs the full problem."""
+    fmaps, feats, coords = _full_coarse(16, 512)
+    blk = cb.CorrBlock(fmaps, num_levels=5, radius=4)
+    blk.corr(feats)
+    out = blk.sample(coords)
+    assert out.shape == (1, 16, 512, 405)
+    sel = slice(0, 512, 37)
+    want = O.corr_lookup(host(fmaps), host(feats[:, :, sel]), host(coords[:, :, sel]), 5, 4)
+    assert rel_to_max(host(out[:, :, sel]), want) < FP32_BAR
+
+
+def test_full_size_properties(cb):
+    """Size-independent properties at full size: linearity in the target, pooling commutes with correlation
+    (level l of the output == level 0 of a CorrBlock built on the pooled map), and consistency between the
+    lookup-only and the token kernels."""
+    fmaps, feats, coords = _full_coarse(16, 512, seed=1)
+    L, r = 5, 4
+    blk = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+    blk.corr(feats)
+    a = blk.sample(coords)
+    blk.corr(feats * -2.5)
+    b = blk.sample(coords)
+    assert rel_to_max(host(b), host(a) * -2.5) < 1e-5
+    # level 1 of the pyramid == level 0 of a block built on the pooled maps, at halved coordinates
+    pooled = blk.fmaps_pyramid[1].contiguous()
+    blk1 = cb.CorrBlock(pooled, num_levels=1, radius=r)
+    blk1.corr(feats)
+    lvl1 = blk1.sample(coords / 2)
+    assert rel_to_max(host(lvl1), host(a[..., 81:162])) < 1e-5
+    # tokens carry the same correlation features, transposed to (B,N,S,.) and offset by the position embedding
+    tdim = cb.transformer_dim(L, r, 128, False)
+    tok = cb.TrackTokenizer(blk, coords[:, 0], tdim)
+    x = tok.tokens(coords, feats)
+    corr_part = x[..., 130:130 + 405] - tok.pos[:, :, None, 130:130 + 405]
+    assert rel_to_max(host(corr_part.permute(0, 2, 1, 3)), host(a)) < 1e-5
+    assert float((x[..., 663] - tok.pos[:, :, None, 663]).abs().max()) == 0.0  # zero pad channel
+
+
+def test_full_size_fine_config_subset_vs_oracle(cb):
+    """Fine tracker shape: B' = 512 patches, S=16, one query per 31x31 patch, C=32, L=3, r=3."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    fmaps = torch.randn(512, 16, 32, 31, 31, device="cuda", generator=g)
+    feats = torch.randn(512, 16, 1, 32, device="cuda", generator=g)
+    coords = torch.rand(512, 16, 1, 2, device="cuda", generator=g) * 30
+    blk = cb.CorrBlock(fmaps, num_levels=3, radius=3)
+    blk.corr(feats)
+    out = blk.sample(coords)
+    assert out.shape == (512, 16, 1, 147)
+    sel = slice(0, 512, 61)
+    want = O.corr_lookup(host(fmaps[sel]), host(feats[sel]), host(coords[sel]), 3, 3)
+    assert rel_to_max(host(out[sel]), want) < FP32_BAR

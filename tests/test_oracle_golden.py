@@ -139,3 +139,38 @@ def test_first_iteration_tokens_full_size(golden, name):
     assert toks[0].shape == want.shape
     assert O.transformer_dim(L, r, latent, fine) == want.shape[-1]
     assert rel_to_max(toks[0], want) < 1e-5
+
+
+# ---- the torch CPU port (what bench.py times as the CPU baseline) is pinned to the same goldens ----
+@pytest.mark.parametrize("name", list(cases.CORR_CASES))
+def test_torch_port_corr_lookup(golden, name):
+    import torch
+
+    from oracle import torch_port as P
+
+    g = golden("corr_blocks")
+    kw, L, r = cases.CORR_CASES[name]
+    fmaps, targets, coords = (torch.from_numpy(a) for a in cases.corr_case(**kw))
+    lv = P.pyramid(fmaps, L)
+    for pm in ("zeros", "border"):
+        got = P.lookup(P.volumes(lv, targets), coords, r, pm).numpy()
+        assert rel_to_max(got, g[f"{name}/{pm}"]) < TIGHT
+
+
+@pytest.mark.parametrize("name", list(TOKEN_CASES))
+def test_torch_port_tokens(golden, name):
+    import torch
+
+    from oracle import torch_port as P
+
+    g = golden("tracker")
+    kw, L, r, latent, fine, dr, stride = TOKEN_CASES[name]
+    fmaps, q = (torch.from_numpy(a) for a in cases.tracker_case(**kw))
+    if dr > 1:
+        q = q / float(dr) / float(stride)
+    B, S = fmaps.shape[:2]
+    coords = q[:, None].repeat(1, S, 1, 1)
+    feats = P.point_sample(fmaps[:, 0], coords[:, 0])[:, None].repeat(1, S, 1, 1)
+    tdim = O.transformer_dim(L, r, latent, fine)
+    x = P.hot_path_iteration(P.pyramid(fmaps, L), coords, feats, r, fmaps.shape[-2:], tdim)
+    assert rel_to_max(x.numpy(), g[name + "/tok0"]) < 1e-5
