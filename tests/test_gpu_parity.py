@@ -224,13 +224,14 @@ def test_tokens_with_motion_vs_oracle(cb):
     """Later iterations: coords differ per frame (non-zero flows with sin/cos arguments up to ~1e4), track_feats
     arrive as a permuted (B,N,S,C) view, as in base_track_predictor.py:243-252."""
     rng = np.random.default_rng(3)
-    B, S, N, C, H, W, L, r = 2, 5, 11, 32, 24, 20, 3, 3
-    fmaps = rng.standard_normal((B, S, C, H, W)).astype(np.float32)
-    feats = rng.standard_normal((B, S, N, C)).astype(np.float32)
-    c0 = np.stack([rng.uniform(0, W - 1, (B, N)), rng.uniform(0, H - 1, (B, N))], -1).astype(np.float32)
-    coords = c0[:, None] + (rng.standard_normal((B, S, N, 2)) * 3).astype(np.float32)
-    coords[:, 0] = c0
-    for fine in (False, True):
+    # (L, r, C, fine): token widths 216 (fine rule) and 132 (coarse rule, no padding needed)
+    for L, r, C, fine in ((3, 3, 32, True), (2, 3, 16, False), (5, 2, 16, False)):
+        B, S, N, H, W = 2, 5, 11, 24, 20
+        fmaps = rng.standard_normal((B, S, C, H, W)).astype(np.float32)
+        feats = rng.standard_normal((B, S, N, C)).astype(np.float32)
+        c0 = np.stack([rng.uniform(0, W - 1, (B, N)), rng.uniform(0, H - 1, (B, N))], -1).astype(np.float32)
+        coords = c0[:, None] + (rng.standard_normal((B, S, N, 2)) * 3).astype(np.float32)
+        coords[:, 0] = c0
         tdim = O.transformer_dim(L, r, C, fine)
         want = O.track_tokens(O.corr_lookup(fmaps, feats, coords, L, r), coords, feats, (H, W), tdim)
         f = dev(fmaps)
