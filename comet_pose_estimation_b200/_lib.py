@@ -40,6 +40,16 @@ SIGNATURES = {
     "comet_embed2d_f32": (_i, [_p, _p, _ll, _i, _i, _p]),
     "comet_sincos1d_from_grid_f32": (_i, [_p, _p, _ll, _i, _p]),
     "comet_sincos2d_f32": (_i, [_p, _i, _i, _i, _p]),
+    "comet_tc_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "comet_tc_split_elems": (_ll, [_i]),
+    "comet_tc_prepare_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "comet_tc_corr_lookup_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
+                                      _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_tc_track_tokens_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _p,
+                                       _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_tc_corr_volume_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_tc_status": (_i, []),
+    "comet_tc_debug_stamps": (None, [_p]),
 }
 
 

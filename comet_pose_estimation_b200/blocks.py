@@ -5,6 +5,8 @@ Differences a caller can observe: none in results (parity tests) -- but the corr
 materialised by ``corr()``/``sample()``; ``corrs_pyramid`` is produced lazily only if somebody reads it."""
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import List, Optional
 
 import torch
@@ -13,6 +15,11 @@ from . import _lib
 from ._dev import f32c, inner_contig, pad_mode, prec_mode, require_cuda, stream_ptr
 
 lib = _lib.lib
+
+
+def tensor_path_enabled() -> bool:
+    """The tcgen05 kernels serve the dense coarse shape; COMET_B200_DISABLE_TC=1 forces the SIMT kernels (A/B runs)."""
+    return os.environ.get("COMET_B200_DISABLE_TC", "0") != "1" and bool(lib.comet_has_tensor_path())
 
 
 class _Pyramid:
@@ -30,15 +37,28 @@ class _Pyramid:
         n = lib.comet_pyramid_elems(B * S, C, H, W, num_levels)
         assert n >= 0
         self.pyr = torch.empty(max(n, 1), dtype=torch.float32, device=fmaps.device)
+        self.split = None  # packed bf16 hi/lo pyramid of the tensor-core path
         with torch.cuda.device(fmaps.device):
-            _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W, num_levels,
-                                             stream_ptr(fmaps.device)))
+            if B * S > 0 and lib.comet_tc_supported(C, H, W, num_levels, 0, _lib.PAD_ZEROS) and tensor_path_enabled():
+                self.split = torch.empty(lib.comet_tc_split_elems(B * S), dtype=torch.bfloat16, device=fmaps.device)
+                _lib.check(lib.comet_tc_prepare_f32(self.fmaps0.data_ptr(), self.split.data_ptr(),
+                                                    self.pyr.data_ptr(), B * S, C, H, W, num_levels,
+                                                    stream_ptr(fmaps.device)))
+            else:
+                _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
+                                                 num_levels, stream_ptr(fmaps.device)))
         self.levels: List[torch.Tensor] = [fmaps]
+        self._tc_ok_cache = {}
         h, w = H, W
         for l in range(1, num_levels):
             h, w = h // 2, w // 2
             off = lib.comet_pyramid_offset(B * S, C, H, W, l)
             self.levels.append(self.pyr[off: off + B * S * C * h * w].view(B, S, C, h, w))
+
+
+def _use_tc(pyr: "_Pyramid", t: torch.Tensor, radius: int, padding: str, level_stride: int = 0) -> bool:
+    return (pyr.split is not None and level_stride == 0 and padding == "zeros" and radius <= 4
+            and t.data_ptr() % 16 == 0 and all(st % 4 == 0 for st in t.stride()[:3]))
 
 
 def _fused_lookup(pyr: _Pyramid, targets, coords, radius, padding, level_stride=0):
@@ -51,6 +71,14 @@ def _fused_lookup(pyr: _Pyramid, targets, coords, radius, padding, level_stride=
     Wr = 2 * radius + 1
     out = torch.empty((B, S, N, pyr.num_levels * Wr * Wr), dtype=torch.float32, device=coords.device)
     with torch.cuda.device(coords.device):
+        if B * S * N and _use_tc(pyr, t, radius, padding, level_stride):
+            _lib.check(lib.comet_tc_corr_lookup_f32(
+                pyr.split.data_ptr(), t.data_ptr(), t.stride(0), t.stride(1), t.stride(2),
+                c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
+                out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
+                B, S, N, pyr.C, pyr.H, pyr.W, pyr.num_levels, radius, pad_mode(padding), prec_mode(),
+                stream_ptr(coords.device)))
+            return out
         _lib.check(lib.comet_corr_lookup_f32(
             pyr.fmaps0.data_ptr(), pyr.pyr.data_ptr(),
             t.data_ptr(), t.stride(0), t.stride(1), t.stride(2), level_stride,
@@ -102,6 +130,19 @@ class CorrBlock:
             vols = []
             mode = prec_mode()
             with torch.cuda.device(t.device):
+                if B * S * N and not self.multiple_track_feats and _use_tc(p, t.view(B, S, N, -1), 0, "zeros"):
+                    for f in self.fmaps_pyramid:
+                        vols.append(torch.empty((B, S, N) + tuple(f.shape[-2:]), dtype=torch.float32,
+                                                device=t.device))
+                    ptrs = (ctypes.c_void_p * len(vols))(*[v.data_ptr() for v in vols])
+                    t4 = t.view(B, S, N, -1)
+                    _lib.check(lib.comet_tc_corr_volume_f32(
+                        p.split.data_ptr(), t4.data_ptr(), t4.stride(0), t4.stride(1), t4.stride(2), ptrs,
+                        B, S, N, p.C, p.H, p.W, p.num_levels, mode, stream_ptr(t.device)))
+                    if mode == _lib.PREC_BF16_AUTOCAST:
+                        vols = [v.to(torch.bfloat16) for v in vols]
+                    self._volumes = vols
+                    return self._volumes
                 for l, f in enumerate(self.fmaps_pyramid):
                     h, w = f.shape[-2:]
                     tl = t[..., l * self.C:(l + 1) * self.C] if self.multiple_track_feats else t

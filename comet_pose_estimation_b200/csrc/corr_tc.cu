@@ -1,0 +1,883 @@
+// Correlation on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) with the multi-level window lookup and the
+// track-token assembly as the epilogue -- the dense coarse-tracker shape of COMET (C=128, 64x64 maps, L<=5, r<=4,
+// zero padding: CorrBlock.corr + CorrBlock.sample, comet/models/track_modules/blocks.py:376-429, and the token
+// assembly of base_track_predictor.py:165-224).  The correlation volume lives only in TMEM.
+//
+// Arithmetic.  float32 parity (1e-4) on bf16 tensor cores: every operand is split x = hi + lo (two bf16) and the
+// product is accumulated in float32 as hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-18 relative), i.e. one
+// K=384 bf16 GEMM.  In COMET_PREC_BF16_AUTOCAST mode only hi*hi is issued and the accumulator is rounded to bf16
+// exactly where torch.autocast rounds the reference's volume.
+//
+// Data layout (HBM).  comet_tc_prepare_f32 (once per tracker call) pools the pyramid in float32 and writes, per
+// (frame, channel), ONE packed row of P=5504 positions  [L0 4096 | L1 1024 | L2 256 | L3 64 | L4 16 | 48 zeros]
+// as bf16 hi and bf16 lo:  split[2][BS][C][P].  A 64-position tile of any level is then one TMA box
+// [64 positions x 128 channels] = 16 KB that lands in shared memory in the MN-major SWIZZLE_128B UMMA layout.
+//
+// Work decomposition.  job = (frame bs, 128-query tile, chunk); chunks 0..3 = level-0 rows [16c, 16c+16] (one row
+// of overlap so that every window entry has both of its rows in one chunk), chunk 4 = levels 1..4 (22 tiles).
+// Persistent CTAs (one per SM) walk the job list; jobs of one frame are adjacent so concurrent CTAs share the
+// feature tiles through L2.
+//
+// CTA = 6 warps:  warp 0 TMA producer (B tiles, 3-stage ring) | warp 1 TMEM alloc + single-thread tcgen05.mma issue
+// (D 128x64 fp32 in TMEM, 4-stage accumulator ring) | warps 2-5 epilogue: load + hi/lo-split the 128x128 target
+// tile into the K-major SWIZZLE_128B layout at job start, then per tile tcgen05.ld the accumulator row of "their"
+// query (TMEM lane == query), park it in a private shared-memory row (dynamic column indexing), and stream the map
+// rows: horizontal lerp at the query's x window, vertical lerp with the previous row, store.
+#include "comet_common.cuh"
+
+#include <cuda.h>
+#include <cstdlib>
+
+namespace comet {
+namespace tc {
+
+constexpr int MAP = 64;        // level-0 map is MAP x MAP
+constexpr int KC = 128;        // channels == GEMM K per pass
+constexpr int TILE_M = 128;    // queries per CTA tile == TMEM lanes
+constexpr int TILE_N = 64;     // positions per accumulator tile
+constexpr int NSTAGE = 3;      // B-tile ring
+constexpr int NACC = 4;        // accumulator ring (4 x 64 TMEM columns)
+constexpr int P_TOTAL = 5504;  // packed positions per (frame, channel)
+constexpr int MAX_WR = 9;      // 2*4+1
+constexpr int THREADS = 320;   // 10 warps: TMA | MMA | 4 epilogue | 4 stager
+
+// tensor-memory map (all 512 columns of the SM are allocated, so the base address is 0)
+constexpr uint32_t TM_ACC = 0;      // accumulator ring: NACC x 64 columns
+constexpr uint32_t TM_A = 256;      // target tile: 2 buffers x [hi 64 cols | lo 64 cols] (two bf16 per column)
+
+constexpr int B_TILE_BYTES = TILE_N * KC * 2;   // 16 KB per hi / lo
+constexpr int STAGE_BYTES = 2 * B_TILE_BYTES;   // hi + lo
+constexpr int DUMP_STRIDE = 68;                 // floats per private accumulator row (64 + 4: conflict-free STS.128)
+constexpr int DUMP_BYTES = TILE_M * DUMP_STRIDE * 4;
+constexpr int WIN_STRIDE = 84;                  // floats per staged window row (81 + 3, 16-byte aligned rows)
+constexpr int WIN_BYTES = TILE_M * WIN_STRIDE * 4;
+constexpr int NWIN = 2;                         // window buffers (epilogue -> stager hand-off)
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + DUMP_BYTES + NWIN * WIN_BYTES + 512;
+
+__host__ __device__ inline int level_offset(int l) { return l == 0 ? 0 : l == 1 ? 4096 : l == 2 ? 5120 : l == 3 ? 5376 : 5440; }
+__host__ __device__ inline int num_tiles(int L) { return L == 1 ? 64 : L == 2 ? 80 : L == 3 ? 84 : L == 4 ? 85 : 86; }
+
+struct TileInfo {
+  int level, y_first, rows, W, H;
+};
+__device__ __forceinline__ TileInfo tile_info(int t) {
+  TileInfo ti;
+  if (t < 64) { ti.level = 0; ti.y_first = t; ti.rows = 1; ti.W = 64; }
+  else if (t < 80) { ti.level = 1; ti.y_first = (t - 64) * 2; ti.rows = 2; ti.W = 32; }
+  else if (t < 84) { ti.level = 2; ti.y_first = (t - 80) * 4; ti.rows = 4; ti.W = 16; }
+  else if (t < 85) { ti.level = 3; ti.y_first = 0; ti.rows = 8; ti.W = 8; }
+  else { ti.level = 4; ti.y_first = 0; ti.rows = 4; ti.W = 4; }
+  ti.H = ti.W;
+  return ti;
+}
+
+struct Params {
+  const float* targets; long long t_sb, t_ss, t_sn;
+  const float* coords;  long long c_sb, c_ss, c_sn;
+  float* out;           long long o_sb, o_ss, o_sn;   // lookup layout (B,S,N,L*Wr*Wr) when !tokens
+  const float* pos; int D_tok; int tokens;            // token layout (B,N,S,D_tok) when tokens
+  float* vol[5]; int volume_mode;                      // volume mode: per-level (BS,N,H_l,W_l)
+  int B, S, N, L, r, npass, bf16;
+  int BS, mtiles, nchunk, njobs, ntiles;
+  float inv_sqrt_c;
+  int* status;  // device int: set non-zero by the watchdog
+  int debug;    // COMET_TC_DEBUG bit mask (attribution experiments; 0 in production)
+  long long* stamps;  // optional clock64 trace of CTA 0 (debug aid): [4 roles][64][2]
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One elected lane of a fully converged warp (elect.sync): unlike `lane == 0`, ptxas knows exactly one thread is
+// active in the guarded region and emits the uniform-datapath UTCHMMA / UTMALDG without a per-instruction
+// ELECT + BRA.U.ANY loop (measured: ~70 clk per tcgen05.mma issue with `lane == 0`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (fast, visible failure) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* status, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      if (status) atomicExch(status, code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem], kind::f16 (bf16 in, f32 accumulate), one CTA.  A: row m in TMEM lane m, two
+// bf16 K-elements per 32-bit column (16 K-elements = 8 columns per instruction).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 64-bit shared-memory matrix descriptor (SWIZZLE_128B, version 1).  lbo/sbo in bytes.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D f32, A/B bf16, A K-major, B MN-major, M=128, N=64.
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                           ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_resid(float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ void job_decode(const Params& p, int job, int& bs, int& chunk, int& mt) {
+  mt = job % p.mtiles;
+  const int t = job / p.mtiles;
+  chunk = t % p.nchunk;
+  bs = t / p.nchunk;
+}
+__device__ __forceinline__ void chunk_tiles(const Params& p, int chunk, int& t0, int& t1) {
+  if (chunk < 4) { t0 = 16 * chunk; t1 = min(t0 + 17, 64); }
+  else { t0 = 64; t1 = p.ntiles; }
+}
+
+__device__ __forceinline__ void stamp(const Params& p, int role, int idx, int which) {
+  if (p.stamps && blockIdx.x == 0 && idx < 64) p.stamps[(role * 64 + idx) * 2 + which] = clock64();
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(THREADS, 1)
+corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+ // dynamic shared memory is the only shared allocation of this kernel, so it starts 1024-byte aligned (SWIZZLE_128B
+  // tiles need that); no integer round trip on the pointer, so that accesses stay LDS/STS rather than generic LD/ST
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;                                                   // NSTAGE x [hi 16 KB][lo 16 KB]
+  float* dump = reinterpret_cast<float*>(sB + NSTAGE * STAGE_BYTES);   // private accumulator rows
+  float* win = dump + TILE_M * DUMP_STRIDE;                            // staged window rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(win + NWIN * TILE_M * WIN_STRIDE);
+  uint64_t* full = bars;                  // [NSTAGE]  TMA -> MMA
+  uint64_t* empty = full + NSTAGE;        // [NSTAGE]  MMA -> TMA
+  uint64_t* acc_full = empty + NSTAGE;    // [NACC]    MMA -> epilogue
+  uint64_t* acc_empty = acc_full + NACC;  // [NACC]    epilogue -> MMA
+  uint64_t* a_full = acc_empty + NACC;    // [2]       stager -> MMA (target tile in TMEM)
+  uint64_t* a_empty = a_full + 2;         // [2]       MMA -> stager
+  uint64_t* win_full = a_empty + 2;       // [NWIN*4]  epilogue warp -> stager warp of the same lane quarter
+  uint64_t* win_empty = win_full + NWIN * 4;  // [NWIN*4]  stager warp -> epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(win_empty + NWIN * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NWIN * 4; ++i) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  // The whole tensor memory of the SM is ours (one CTA per SM), so the allocation starts at lane 0 / column 0 and
+  // every TMEM address below is a compile-time constant (keeps the MMA issue loop on the uniform datapath).
+  if (*tmem_slot != 0 || (smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0 && p.status) atomicExch(p.status, 9);
+    __trap();
+  }
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      int tcount = 0;
+      for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+        int bs, chunk, mt, t0, t1;
+        job_decode(p, job, bs, chunk, mt);
+        chunk_tiles(p, chunk, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
+          stamp(p, 0, tcount++, 0);
+          uint8_t* dst = sB + stage * STAGE_BYTES;
+          if (p.debug & 64) {
+            mbar_arrive(&full[stage]);
+          } else {
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(&tmap, &full[stage], dst, t * TILE_N, bs * KC);
+            tma_load_2d(&tmap, &full[stage], dst + B_TILE_BYTES, t * TILE_N, (p.BS + bs) * KC);
+          }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, ji = 0;
+    int tcount = 0;
+    const int npass = (p.debug & 8) ? 0 : p.npass;
+    const uint32_t idesc = (p.debug & 128) ? (IDESC + (8u << 17)) : IDESC;  // timing experiment: N=128
+    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
+      int bs, chunk, mt, t0, t1;
+      job_decode(p, job, bs, chunk, mt);
+      chunk_tiles(p, chunk, t0, t1);
+      const uint32_t abuf = ji & 1;
+      mbar_wait(&a_full[abuf], (ji >> 1) & 1, p.status, 2);
+      const uint32_t a_hi = TM_A + abuf * 128, a_lo = a_hi + 64;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1, p.status, 3);
+        mbar_wait(&full[stage], phase, p.status, 4);
+        tcgen05_fence_after();
+        if (lane == 0) stamp(p, 1, tcount, 0);
+        if (elect_one()) {
+          const uint32_t b_hi = smem_u32(sB + stage * STAGE_BYTES);
+          const uint32_t d = TM_ACC + acc * TILE_N;
+          uint32_t accum = 0;
+          for (int pass = 0; pass < npass; ++pass) {
+            const uint32_t a0 = (pass == 2) ? a_lo : a_hi;
+            // B: MN-major SW128, K row = 128 B, 8-row groups 1 KB apart; 16 K rows (2 KB) per step
+            const uint64_t bd0 = make_desc(b_hi + ((pass == 1) ? B_TILE_BYTES : 0), B_TILE_BYTES, 1024);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              umma_bf16_ts(d, a0 + k * 8, bd0 + (uint64_t)(k * (2048 >> 4)), idesc, accum);
+              accum = 1;
+            }
+          }
+          tcgen05_commit(&empty[stage]);    // B stage free once these MMAs retire
+          tcgen05_commit(&acc_full[acc]);   // accumulator ready
+          if (t + 1 == t1) tcgen05_commit(&a_empty[abuf]);  // target tile buffer free
+          stamp(p, 1, tcount, 1);
+        }
+        ++tcount;
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue warps (2..5) =====================
+    const int wq = warp & 3;                    // TMEM lane quarter this warp may access
+    const int q = 32 * wq + lane;               // TMEM lane == query slot in the tile
+    float* myrow = dump + q * DUMP_STRIDE;
+    const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
+    const int Wr = 2 * p.r + 1;
+    uint32_t acc = 0, acc_phase = 0, wu = 0;  // wu: window units handed to the stager so far
+    int tcount = 0;
+    float* mywin = win;
+
+    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+      int bs, chunk, mt, t0, t1;
+      job_decode(p, job, bs, chunk, mt);
+      chunk_tiles(p, chunk, t0, t1);
+      const int b = bs / p.S, s = bs - b * p.S;
+      const int m0 = mt * TILE_M;
+      const int n = m0 + q;
+      const bool valid = n < p.N;
+      float cx = 0.f, cy = 0.f;
+      if (valid && p.coords) {
+        const float* cp = p.coords + b * p.c_sb + s * p.c_ss + n * p.c_sn;
+        cx = __ldg(cp);
+        cy = __ldg(cp + 1);
+      }
+
+      int cur_level = -1;
+      int x0 = 0, y0 = 0, ta = 0, tb_ = 0, Hl = 0;
+      float fx = 0.f, fy = 0.f;
+      float hprev[MAX_WR];
+
+      for (int t = t0; t < t1; ++t) {
+        const TileInfo ti = tile_info(t);
+        // ---- accumulator -> registers ----
+        mbar_wait(&acc_full[acc], acc_phase, p.status, 5);
+        if (warp == 2 && lane == 0) stamp(p, 2, tcount, 0);
+        tcgen05_fence_after();
+        float v[64];
+        tmem_ld32(lane_addr + TM_ACC + acc * TILE_N, v);
+        tmem_ld32(lane_addr + TM_ACC + acc * TILE_N + 32, v + 32);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (warp == 2 && lane == 0) stamp(p, 2, tcount, 1);
+        ++tcount;
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+
+        if (p.bf16) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = round_bf16(round_bf16(v[i]) * p.inv_sqrt_c);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] *= p.inv_sqrt_c;
+        }
+
+        if (p.volume_mode) {
+          if (valid) {
+            const int cols = ti.level == 4 ? 16 : 64;
+            const int HW = ti.W * ti.W;
+            float* dst = p.vol[ti.level] + ((long long)bs * p.N + n) * HW + (t * TILE_N - level_offset(ti.level));
+#pragma unroll
+            for (int i = 0; i < 64; i += 4)
+              if (i < cols) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+          continue;
+        }
+        if (p.debug & 1) continue;
+
+        // private smem row: the window columns are indexed dynamically (x0 differs per query)
+#pragma unroll
+        for (int i = 0; i < 64; i += 4)
+          *reinterpret_cast<float4*>(myrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+
+        if (ti.level != cur_level) {
+          // ---- new pyramid level: window geometry; claim a window buffer and clear it (rows off the map stay 0) ----
+          cur_level = ti.level;
+          Hl = ti.H;
+          const float inv = 1.f / (float)(1 << ti.level);
+          const float px = fminf(fmaxf(cx * inv, -1.0e6f), 1.0e6f);
+          const float py = fminf(fmaxf(cy * inv, -1.0e6f), 1.0e6f);
+          const float flx = floorf(px), fly = floorf(py);
+          fx = px - flx; fy = py - fly;
+          x0 = (int)flx - p.r; y0 = (int)fly - p.r;
+          // tops handled while streaming: [ta, tb_]
+          ta = (ti.level == 0 && chunk > 0) ? 16 * chunk : -1;
+          tb_ = (ti.level == 0 && chunk < 3) ? 16 * chunk + 15 : Hl - 2;
+#pragma unroll
+          for (int i = 0; i < MAX_WR; ++i) hprev[i] = 0.f;
+          const uint32_t wbuf = wu % NWIN;
+          mbar_wait(&win_empty[wbuf * 4 + wq], ((wu / NWIN) & 1) ^ 1, p.status, 7);
+          mywin = win + (wbuf * TILE_M + q) * WIN_STRIDE;
+#pragma unroll
+          for (int i = 0; i < WIN_STRIDE; i += 4) *reinterpret_cast<float4*>(mywin + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+
+        // ---- stream the map rows of this tile ----
+        for (int rr = 0; rr < ti.rows; ++rr) {
+          const int y = ti.y_first + rr;
+          float h[MAX_WR];
+          const bool needed = valid && y >= y0 && y <= y0 + Wr;
+          if (needed) {
+            const float* row = myrow + rr * ti.W;
+            float vv[MAX_WR + 1];
+#pragma unroll
+            for (int i = 0; i <= MAX_WR; ++i) {
+              const int xi = x0 + i;
+              vv[i] = (i <= Wr && xi >= 0 && xi < ti.W) ? row[xi] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < MAX_WR; ++i) h[i] = (1.f - fx) * vv[i] + fx * vv[i + 1];
+          } else {
+#pragma unroll
+            for (int i = 0; i < MAX_WR; ++i) h[i] = 0.f;
+          }
+          const int top = y - 1, j = top - y0;
+          if (valid && j >= 0 && j < Wr && top >= ta && top <= tb_) {
+#pragma unroll
+            for (int i = 0; i < MAX_WR; ++i)
+              if (i < Wr) mywin[i * Wr + j] = (1.f - fy) * hprev[i] + fy * h[i];
+          }
+#pragma unroll
+          for (int i = 0; i < MAX_WR; ++i) hprev[i] = h[i];
+        }
+
+        // ---- end of a level inside this job: finish the window and hand it to the stager warp ----
+        const bool level_ends = (t + 1 == t1) || (tile_info(t + 1).level != ti.level);
+        if (level_ends) {
+          const bool last = ti.level > 0 || chunk == 3;
+          const bool first = ti.level > 0 || chunk == 0;
+          if (last && valid) {
+            const int jb = (Hl - 1) - y0;  // top = H-1: its bottom row is off the map
+            if (jb >= 0 && jb < Wr) {
+#pragma unroll
+              for (int i = 0; i < MAX_WR; ++i)
+                if (i < Wr) mywin[i * Wr + jb] = (1.f - fy) * hprev[i];
+            }
+          }
+          // window rows (index j) this job owns: tops in [lo_top, hi_top]
+          const int lo_top = first ? -(1 << 28) : 16 * chunk;
+          const int hi_top = last ? (1 << 28) : 16 * chunk + 15;
+          const int j_lo = valid ? max(0, lo_top - y0) : 1, j_hi = valid ? min(Wr - 1, hi_top - y0) : 0;
+          mywin[81] = __int_as_float(j_lo);
+          mywin[82] = __int_as_float(j_hi);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&win_full[(wu % NWIN) * 4 + wq]);  // release.cta: the STS above are visible
+          ++wu;
+        }
+      }
+    }
+  } else {
+    // ===================== stager warps (6..9): every global load/store except the TMA =====================
+    // per job:  (1) stage the NEXT job's 128 target rows into the free TMEM A buffer (hi/lo split, tcgen05.st);
+    //           (2) chunk-3 jobs own the (query, frame) pair: write the non-correlation part of the token;
+    //           (3) for every window unit the epilogue warp of the same lane quarter hands over: add the position
+    //               embedding and store the window rows this job owns, coalesced, with all loads of 16 queries in
+    //               flight before the first store.
+    const int wq = warp & 3;
+    const int q = 32 * wq + lane;
+    const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
+    const int Wr = 2 * p.r + 1, WW = Wr * Wr;
+    uint32_t wu = 0;
+
+    auto stage_targets = [&](int job, uint32_t ji) {
+      int bs, chunk, mt;
+      job_decode(p, job, bs, chunk, mt);
+      const int b = bs / p.S, s = bs - b * p.S;
+      const int m0 = mt * TILE_M;
+      const uint32_t abuf = ji & 1;
+      mbar_wait(&a_empty[abuf], ((ji >> 1) & 1) ^ 1, p.status, 6);
+      tcgen05_fence_after();
+      if (!(p.debug & 256)) {
+        const bool rv = m0 + q < p.N;
+        const float4* src = reinterpret_cast<const float4*>(p.targets + b * p.t_sb + s * p.t_ss +
+                                                            (long long)(m0 + q) * p.t_sn);
+        const uint32_t ta_hi = lane_addr + TM_A + abuf * 128, ta_lo = ta_hi + 64;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // 64 channels per step: 16 LDG.128 in flight
+          float4 f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = rv ? __ldg(src + half * 16 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 g = f[blk * 8 + i];
+              hi[2 * i] = pack_bf16(g.x, g.y);
+              hi[2 * i + 1] = pack_bf16(g.z, g.w);
+              lo[2 * i] = pack_bf16(bf16_resid(g.x), bf16_resid(g.y));
+              lo[2 * i + 1] = pack_bf16(bf16_resid(g.z), bf16_resid(g.w));
+            }
+            tmem_st16(ta_hi + half * 32 + blk * 16, hi);
+            tmem_st16(ta_lo + half * 32 + blk * 16, lo);
+          }
+        }
+        tmem_st_wait();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&a_full[abuf]);
+    };
+
+    if ((int)blockIdx.x < p.njobs) stage_targets(blockIdx.x, 0);
+    uint32_t ji = 0;
+    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
+      if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 0);
+      if (job + (int)gridDim.x < p.njobs) stage_targets(job + gridDim.x, ji + 1);
+      if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 1);
+      int bs, chunk, mt;
+      job_decode(p, job, bs, chunk, mt);
+      const int b = bs / p.S, s = bs - b * p.S;
+      const int m0 = mt * TILE_M;
+
+      if (p.tokens && !p.volume_mode && chunk == 3 && !(p.debug & 4)) {
+        // [ sin/cos(flow * div) (C) | flow (2) | .. fcorrs .. | track_feats (C) | zero pad ] + pos_emb
+        float fxq = 0.f, fyq = 0.f;
+        if (m0 + q < p.N) {
+          const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)(m0 + q) * p.c_sn;
+          const float* c0 = p.coords + b * p.c_sb + (long long)(m0 + q) * p.c_sn;  // frame 0
+          fxq = __ldg(cp) - __ldg(c0);
+          fyq = __ldg(cp + 1) - __ldg(c0 + 1);
+        }
+        const int Ce = KC >> 1;
+        const float step = 1000.0f / (float)Ce;
+        const int feat_off = KC + 2 + p.L * WW;
+        const int ntail = p.D_tok - feat_off;  // track_feats + pad
+        for (int q4 = 0; q4 < 32; q4 += 4) {
+          if (m0 + 32 * wq + q4 >= p.N) break;
+          float pe[4][4], pt[4][5], tf[4][4], pf[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // all loads of four queries first
+            const int nn = m0 + 32 * wq + q4 + u;
+            const bool qv = nn < p.N;
+            const float* pq = p.pos + ((long long)b * p.N + (qv ? nn : 0)) * p.D_tok;
+            const float* tq = p.targets + b * p.t_sb + s * p.t_ss + (long long)(qv ? nn : 0) * p.t_sn;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pe[u][k] = __ldg(pq + lane + 32 * k);
+            pf[u] = (lane < 2) ? __ldg(pq + KC + lane) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) pt[u][k] = (lane + 32 * k < ntail) ? __ldg(pq + feat_off + lane + 32 * k) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tf[u][k] = __ldg(tq + lane + 32 * k);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int nn = m0 + 32 * wq + q4 + u;
+            const float flx = __shfl_sync(0xffffffffu, fxq, q4 + u), fly = __shfl_sync(0xffffffffu, fyq, q4 + u);
+            if (nn >= p.N) continue;
+            float* o = p.out + (((long long)b * p.N + nn) * p.S + s) * p.D_tok;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = lane + 32 * k;
+              const int axis = e / Ce, w = e - axis * Ce;
+              const float arg = __fmul_rn(axis ? fly : flx, (float)(w & ~1) * step);
+              o[e] = ((w & 1) ? cosf(arg) : sinf(arg)) + pe[u][k];
+            }
+            if (lane < 2) o[KC + lane] = (lane ? fly : flx) + pf[u];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              const int c = lane + 32 * k;
+              if (c < ntail) o[feat_off + c] = (c < KC ? tf[u][k & 3] : 0.f) + pt[u][k];
+            }
+            const float* pq = p.pos + ((long long)b * p.N + nn) * p.D_tok;
+            for (int c = 160 + lane; c < ntail; c += 32) o[feat_off + c] = __ldg(pq + feat_off + c);  // wide pads
+          }
+        }
+      }
+
+      if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 1, 0);
+      if (p.volume_mode || (p.debug & 1)) continue;
+      // window units of this job: level 0 for the row chunks, levels 1..L-1 for the pyramid chunk
+      const int l0 = chunk < 4 ? 0 : 1, l1 = chunk < 4 ? 1 : p.L;
+      for (int lvl = l0; lvl < l1; ++lvl, ++wu) {
+        const uint32_t wbuf = wu % NWIN;
+        mbar_wait(&win_full[wbuf * 4 + wq], (wu / NWIN) & 1, p.status, 8);
+        if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 0);
+        const float* wrows = win + (wbuf * TILE_M + 32 * wq) * WIN_STRIDE;
+        const int lvl_off = (p.tokens ? KC + 2 : 0) + lvl * WW;
+        const int dcl[3] = {min(lane, WW - 1), min(lane + 32, WW - 1), min(lane + 64, WW - 1)};
+        const int jjs[3] = {lane % Wr, (lane + 32) % Wr, (lane + 64) % Wr};
+        const bool dok[3] = {lane < WW, lane + 32 < WW, lane + 64 < WW};
+#pragma unroll 1
+        for (int q16 = 0; q16 < 32; q16 += 16) {
+          if (m0 + 32 * wq + q16 >= p.N) break;
+          // branch-free, unconditional loads (clamped addresses) into their own registers: nothing consumes them
+          // until all 48 are in flight
+          float val[16][3];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int nn = min(m0 + 32 * wq + q16 + u, p.N - 1);
+            if (p.tokens) {
+              const float* pq = p.pos + ((long long)b * p.N + nn) * p.D_tok + lvl_off;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) val[u][k] = __ldg(pq + dcl[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) val[u][k] = 0.f;
+            }
+          }
+          const long long row_stride = p.tokens ? (long long)p.S * p.D_tok : p.o_sn;
+          float* dst = (p.tokens ? p.out + (((long long)b * p.N + m0 + 32 * wq + q16) * p.S + s) * p.D_tok
+                                 : p.out + b * p.o_sb + s * p.o_ss + (long long)(m0 + 32 * wq + q16) * p.o_sn) + lvl_off;
+          const float* wsrc = wrows + q16 * WIN_STRIDE;
+          const int nq = min(16, p.N - (m0 + 32 * wq + q16));
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            if (u < nq) {
+              const int jl = __float_as_int(wsrc[81]), jh = __float_as_int(wsrc[82]);
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                if (dok[k] && jjs[k] >= jl && jjs[k] <= jh) dst[lane + 32 * k] = wsrc[lane + 32 * k] + val[u][k];
+            }
+            dst += row_stride;
+            wsrc += WIN_STRIDE;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&win_empty[wbuf * 4 + wq]);
+        if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 1);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------ prepare: pooled pyramid + hi/lo split
+// One CTA per (frame, channel) plane.  Pools in float32 exactly like the reference chain (pool of pool), writes the
+// packed bf16 hi / lo rows and (optionally) the float32 pyramid levels used by the SIMT kernels.
+__global__ void __launch_bounds__(256) tc_prepare_kernel(const float* __restrict__ fmaps, __nv_bfloat16* __restrict__ split,
+                                                          float* __restrict__ pyr, int BS, int L, long long off1,
+                                                          long long off2, long long off3, long long off4) {
+  __shared__ float s[P_TOTAL];
+  const long long plane = blockIdx.x;  // bs * KC + c
+  const float4* src = reinterpret_cast<const float4*>(fmaps + plane * 4096);
+  for (int i = threadIdx.x; i < 1024; i += 256) reinterpret_cast<float4*>(s)[i] = __ldg(src + i);
+  __syncthreads();
+  int in_off = 0, W = 64;
+  for (int l = 1; l < 5; ++l) {
+    const int Wo = W / 2, out_off = level_offset(l);
+    for (int i = threadIdx.x; i < Wo * Wo; i += 256) {
+      const int y = i / Wo, x = i - y * Wo;
+      const float* a = s + in_off + (2 * y) * W + 2 * x;
+      s[out_off + i] = ((a[0] + a[1]) + (a[W] + a[W + 1])) * 0.25f;
+    }
+    __syncthreads();
+    in_off = out_off;
+    W = Wo;
+  }
+  for (int i = 5456 + threadIdx.x; i < P_TOTAL; i += 256) s[i] = 0.f;
+  __syncthreads();
+  __nv_bfloat162* hi = reinterpret_cast<__nv_bfloat162*>(split + plane * P_TOTAL);
+  __nv_bfloat162* lo = reinterpret_cast<__nv_bfloat162*>(split + ((long long)BS * KC + plane) * P_TOTAL);
+  for (int i = threadIdx.x; i < P_TOTAL / 2; i += 256) {
+    const float a = s[2 * i], b = s[2 * i + 1];
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi[i] = h;
+    lo[i] = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+  }
+  if (pyr) {
+    const long long offs[5] = {0, off1, off2, off3, off4};
+    int Wl = 32;
+    for (int l = 1; l < L; ++l) {
+      float* dst = pyr + offs[l] + plane * Wl * Wl;
+      const float* sl = s + level_offset(l);
+      for (int i = threadIdx.x; i < Wl * Wl; i += 256) dst[i] = sl[i];
+      Wl /= 2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int device_is_sm100() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached = (major == 10 && sms > 0 && encode_fn() != nullptr) ? sms : 0;
+  }
+  return cached;
+}
+
+static long long* g_stamps = nullptr;
+
+static int* status_word() {
+  static int* d = nullptr;
+  if (!d) {
+    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(d, 0, sizeof(int));
+  }
+  return d;
+}
+
+static int launch(Params& p, const void* split, cudaStream_t stream) {
+  const int sms = device_is_sm100();
+  if (!sms) return fail(COMET_ERR_UNSUPPORTED, "tensor path needs an sm_100 device and cuTensorMapEncodeTiled");
+  p.BS = p.B * p.S;
+  p.mtiles = (p.N + TILE_M - 1) / TILE_M;
+  p.nchunk = p.L > 1 ? 5 : 4;
+  p.ntiles = num_tiles(p.L);
+  const long long njobs = (long long)p.BS * p.nchunk * p.mtiles;
+  if (njobs == 0) return COMET_OK;
+  if (njobs > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many jobs");
+  p.njobs = (int)njobs;
+  p.inv_sqrt_c = 1.0f / sqrtf((float)KC);
+  p.status = status_word();
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("COMET_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+  p.stamps = g_stamps;
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)P_TOTAL, (cuuint64_t)2 * p.BS * KC};
+  const cuuint64_t gstride[1] = {(cuuint64_t)P_TOTAL * 2};
+  const cuuint32_t box[2] = {TILE_N, KC};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult cr = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(split), gdim, gstride, box,
+                            estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    COMET_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = (int)(njobs < sms ? njobs : sms);
+  corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);
+  return launch_status("corr_tc_kernel");
+}
+
+static int check_shape(int C, int H, int W, int L, int r, int pad_mode) {
+  COMET_REQUIRE(C == KC && H == MAP && W == MAP, "tensor path is specialised to C=128, 64x64 maps (got C=%d, %dx%d)", C, H, W);
+  COMET_REQUIRE(L >= 1 && L <= 5, "tensor path supports 1..5 levels (got %d)", L);
+  COMET_REQUIRE(r >= 0 && r <= 4, "tensor path supports radius <= 4 (got %d)", r);
+  COMET_REQUIRE(pad_mode == COMET_PAD_ZEROS, "tensor path implements zero padding only");
+  return COMET_OK;
+}
+
+}  // namespace tc
+}  // namespace comet
+
+using namespace comet;
+
+extern "C" int comet_has_tensor_path(void) { return tc::device_is_sm100() > 0; }
+
+extern "C" int comet_tc_supported(int C, int H, int W, int L, int r, int pad_mode) {
+  return C == tc::KC && H == tc::MAP && W == tc::MAP && L >= 1 && L <= 5 && r >= 0 && r <= 4 &&
+         pad_mode == COMET_PAD_ZEROS;
+}
+
+extern "C" long long comet_tc_split_elems(int BS) { return 2LL * BS * tc::KC * tc::P_TOTAL; }
+
+extern "C" int comet_tc_prepare_f32(const float* fmaps, void* split, float* pyr, int BS, int C, int H, int W, int L,
+                                    comet_stream_t stream) {
+  int rc = tc::check_shape(C, H, W, L, 0, COMET_PAD_ZEROS);
+  if (rc != COMET_OK) return rc;
+  if (BS == 0) return COMET_OK;
+  COMET_REQUIRE(fmaps && split, "null pointer");
+  Levels lv = make_levels(BS, C, H, W, 5);
+  tc::tc_prepare_kernel<<<BS * tc::KC, 256, 0, (cudaStream_t)stream>>>(
+      fmaps, reinterpret_cast<__nv_bfloat16*>(split), pyr, BS, L, lv.off[1], lv.off[2], lv.off[3], lv.off[4]);
+  return launch_status("tc_prepare_kernel");
+}
+
+static int tc_common(tc::Params& p, const float* targets, long long t_sb, long long t_ss, long long t_sn,
+                     const float* coords, long long c_sb, long long c_ss, long long c_sn, int B, int S, int N, int C,
+                     int H, int W, int L, int r, int pad_mode, int prec_mode) {
+  int rc = tc::check_shape(C, H, W, L, r, pad_mode);
+  if (rc != COMET_OK) return rc;
+  COMET_REQUIRE(B >= 0 && S >= 0 && N >= 0, "negative batch dimension");
+  COMET_REQUIRE(prec_mode == COMET_PREC_F32 || prec_mode == COMET_PREC_BF16_AUTOCAST, "bad prec_mode %d", prec_mode);
+  COMET_REQUIRE((t_sn % 4) == 0 && (t_ss % 4) == 0 && (t_sb % 4) == 0 && ((uintptr_t)targets % 16) == 0,
+                "targets must be 16-byte aligned rows for the tensor path");
+  p.targets = targets; p.t_sb = t_sb; p.t_ss = t_ss; p.t_sn = t_sn;
+  p.coords = coords; p.c_sb = c_sb; p.c_ss = c_ss; p.c_sn = c_sn;
+  p.B = B; p.S = S; p.N = N; p.L = L; p.r = r;
+  p.bf16 = prec_mode == COMET_PREC_BF16_AUTOCAST;
+  p.npass = p.bf16 ? 1 : 3;
+  return COMET_OK;
+}
+
+extern "C" int comet_tc_corr_lookup_f32(const void* split, const float* targets, long long t_sb, long long t_ss,
+                                        long long t_sn, const float* coords, long long c_sb, long long c_ss,
+                                        long long c_sn, float* out, long long o_sb, long long o_ss, long long o_sn,
+                                        int B, int S, int N, int C, int H, int W, int L, int r, int pad_mode,
+                                        int prec_mode, comet_stream_t stream) {
+  tc::Params p{};
+  int rc = tc_common(p, targets, t_sb, t_ss, t_sn, coords, c_sb, c_ss, c_sn, B, S, N, C, H, W, L, r, pad_mode, prec_mode);
+  if (rc != COMET_OK) return rc;
+  if ((long long)B * S * N == 0) return COMET_OK;
+  COMET_REQUIRE(split && targets && coords && out, "null pointer");
+  p.out = out; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sn = o_sn;
+  return tc::launch(p, split, (cudaStream_t)stream);
+}
+
+extern "C" int comet_tc_track_tokens_f32(const void* split, const float* track_feats, long long t_sb, long long t_ss,
+                                         long long t_sn, const float* coords, long long c_sb, long long c_ss,
+                                         long long c_sn, const float* pos_emb, float* tokens, int B, int S, int N,
+                                         int C, int H, int W, int L, int r, int pad_mode, int prec_mode, int D_tok,
+                                         comet_stream_t stream) {
+  tc::Params p{};
+  int rc = tc_common(p, track_feats, t_sb, t_ss, t_sn, coords, c_sb, c_ss, c_sn, B, S, N, C, H, W, L, r, pad_mode,
+                     prec_mode);
+  if (rc != COMET_OK) return rc;
+  const int need = 2 * C + 2 + L * (2 * r + 1) * (2 * r + 1);
+  COMET_REQUIRE(D_tok >= need, "D_tok=%d smaller than the %d token channels", D_tok, need);
+  if ((long long)B * S * N == 0) return COMET_OK;
+  COMET_REQUIRE(split && track_feats && coords && pos_emb && tokens, "null pointer");
+  p.out = tokens; p.pos = pos_emb; p.D_tok = D_tok; p.tokens = 1;
+  return tc::launch(p, split, (cudaStream_t)stream);
+}
+
+extern "C" int comet_tc_corr_volume_f32(const void* split, const float* targets, long long t_sb, long long t_ss,
+                                        long long t_sn, float* const* vols, int B, int S, int N, int C, int H, int W,
+                                        int L, int prec_mode, comet_stream_t stream) {
+  tc::Params p{};
+  int rc = tc_common(p, targets, t_sb, t_ss, t_sn, nullptr, 0, 0, 0, B, S, N, C, H, W, L, 0, COMET_PAD_ZEROS, prec_mode);
+  if (rc != COMET_OK) return rc;
+  if ((long long)B * S * N == 0) return COMET_OK;
+  COMET_REQUIRE(split && targets && vols, "null pointer");
+  for (int l = 0; l < L; ++l) {
+    COMET_REQUIRE(vols[l], "null volume pointer for level %d", l);
+    p.vol[l] = vols[l];
+  }
+  p.volume_mode = 1;
+  return tc::launch(p, split, (cudaStream_t)stream);
+}
+
+extern "C" void comet_tc_debug_stamps(long long* dev_buf) { comet::tc::g_stamps = dev_buf; }
+
+extern "C" int comet_tc_status(void) {
+  int* d = tc::status_word();
+  int h = 0;
+  if (!d || cudaMemcpy(&h, d, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return h;
+}

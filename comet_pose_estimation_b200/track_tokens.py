@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._dev import inner_contig, pad_mode, prec_mode, require_cuda, stream_ptr
-from .blocks import CorrBlock, EfficientCorrBlock, _Pyramid
+from .blocks import CorrBlock, EfficientCorrBlock, _Pyramid, _use_tc
 
 lib = _lib.lib
 
@@ -79,6 +79,14 @@ class TrackTokenizer:
         else:
             assert out.shape == (B, N, S, self.tdim) and out.is_contiguous() and out.dtype == torch.float32
         with torch.cuda.device(c.device):
+            if B * S * N and _use_tc(p, t, self.radius, self.padding_mode):
+                _lib.check(lib.comet_tc_track_tokens_f32(
+                    p.split.data_ptr(), t.data_ptr(), t.stride(0), t.stride(1), t.stride(2),
+                    c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
+                    self.pos.data_ptr(), out.data_ptr(),
+                    B, S, N, p.C, p.H, p.W, p.num_levels, self.radius, pad_mode(self.padding_mode), prec_mode(),
+                    self.tdim, stream_ptr(c.device)))
+                return out
             _lib.check(lib.comet_track_tokens_f32(
                 p.fmaps0.data_ptr(), p.pyr.data_ptr(),
                 t.data_ptr(), t.stride(0), t.stride(1), t.stride(2),

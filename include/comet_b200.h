@@ -123,6 +123,33 @@ int comet_sincos1d_from_grid_f32(const float* pos, float* out, long long M, int 
 /* get_2d_sincos_pos_embed(D, (H,W)) -> out (D, H, W); channel order [sin_x | cos_x | sin_y | cos_y]. */
 int comet_sincos2d_f32(float* out, int D, int H, int W, comet_stream_t stream);
 
+/* ---- tensor-core path (tcgen05 + TMEM + TMA), coarse-tracker shape only --------------------------------------
+ * Same results as comet_corr_lookup_f32 / comet_track_tokens_f32 / comet_corr_volume_f32 for
+ * C=128, H=W=64, L<=5, r<=4, zero padding; float32 parity through a bf16 hi/lo split (3 MMA passes), or the
+ * autocast rounding with one pass.  `split` is the packed bf16 pyramid written by comet_tc_prepare_f32
+ * (comet_tc_split_elems(BS) bf16 elements); `pyr` (optional, may be NULL) additionally receives the float32 levels
+ * 1..L-1 in the comet_pyramid_f32 layout. */
+int comet_tc_supported(int C, int H, int W, int L, int r, int pad_mode);
+long long comet_tc_split_elems(int BS);
+int comet_tc_prepare_f32(const float* fmaps, void* split, float* pyr, int BS, int C, int H, int W, int L,
+                         comet_stream_t stream);
+int comet_tc_corr_lookup_f32(const void* split, const float* targets, long long t_sb, long long t_ss, long long t_sn,
+                             const float* coords, long long c_sb, long long c_ss, long long c_sn, float* out,
+                             long long o_sb, long long o_ss, long long o_sn, int B, int S, int N, int C, int H, int W,
+                             int L, int r, int pad_mode, int prec_mode, comet_stream_t stream);
+int comet_tc_track_tokens_f32(const void* split, const float* track_feats, long long t_sb, long long t_ss,
+                              long long t_sn, const float* coords, long long c_sb, long long c_ss, long long c_sn,
+                              const float* pos_emb, float* tokens, int B, int S, int N, int C, int H, int W, int L,
+                              int r, int pad_mode, int prec_mode, int D_tok, comet_stream_t stream);
+/* vols: HOST array of L device pointers, level l = (B*S, N, H_l*W_l) float32. */
+int comet_tc_corr_volume_f32(const void* split, const float* targets, long long t_sb, long long t_ss, long long t_sn,
+                             float* const* vols, int B, int S, int N, int C, int H, int W, int L, int prec_mode,
+                             comet_stream_t stream);
+/* 0 = healthy; non-zero = a pipeline watchdog fired inside the tensor kernel (debug aid). Synchronises. */
+int comet_tc_status(void);
+/* debug aid: device buffer of 4*64*2 int64 receiving a clock64 trace of CTA 0 (NULL = off). */
+void comet_tc_debug_stamps(long long* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,3 +309,62 @@ def test_full_size_fine_config_subset_vs_oracle(cb):
     sel = slice(0, 512, 61)
     want = O.corr_lookup(host(fmaps[sel]), host(feats[sel]), host(coords[sel]), 3, 3)
     assert rel_to_max(host(out[sel]), want) < FP32_BAR
+
+
+# ------------------------------------------------------------------ tensor-core path (tcgen05) vs SIMT path
+def test_tensor_path_matches_simt_and_oracle(cb, monkeypatch):
+    """Coarse COMET shape (C=128, 64x64, L=5, r=4, zero padding) runs on the tcgen05 kernel; the same call with
+    COMET_B200_DISABLE_TC=1 runs the SIMT kernel.  Both must sit inside the fp32 bar against the oracle, for
+    N that is not a multiple of the 128-query tile, for strided targets, and for smaller L / r."""
+    if not cb._lib.lib.comet_has_tensor_path():
+        pytest.skip("no sm_100 tensor path on this device")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for (S, N, L, r) in ((3, 200, 5, 4), (2, 129, 3, 2), (1, 5, 1, 0), (2, 384, 4, 3)):
+        fmaps = torch.randn(2, S, 128, 64, 64, device="cuda", generator=g)
+        feats = torch.randn(2, N, S, 128, device="cuda", generator=g).permute(0, 2, 1, 3)  # strided view
+        coords = torch.rand(2, S, N, 2, device="cuda", generator=g) * 80 - 8
+        coords[0, 0, 0] = torch.tensor([63.0, 0.0], device="cuda")
+        coords[1, 0, 0] = torch.tensor([-30.0, 31.25], device="cuda")
+        monkeypatch.setenv("COMET_B200_DISABLE_TC", "0")
+        blk = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+        assert blk._pyr.split is not None
+        blk.corr(feats)
+        tc = blk.sample(coords)
+        tdim = cb.transformer_dim(L, r, 128, False)
+        if tdim >= 2 * 128 + 2 + L * (2 * r + 1) ** 2:
+            x_tc = cb.TrackTokenizer(blk, coords[:, 0], tdim).tokens(coords, feats)
+        else:
+            x_tc = None
+        vols_tc = [v.clone() for v in blk.corrs_pyramid]
+        monkeypatch.setenv("COMET_B200_DISABLE_TC", "1")
+        blk2 = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+        assert blk2._pyr.split is None
+        blk2.corr(feats)
+        simt = blk2.sample(coords)
+        assert rel_to_max(host(tc), host(simt)) < 2e-5
+        for a, b in zip(vols_tc, blk2.corrs_pyramid):
+            assert rel_to_max(host(a), host(b)) < 2e-5
+        if x_tc is not None:
+            x_simt = cb.TrackTokenizer(blk2, coords[:, 0], tdim).tokens(coords, feats)
+            assert rel_to_max(host(x_tc), host(x_simt)) < 2e-5
+        sel = slice(0, N, max(1, N // 9))
+        want = O.corr_lookup(host(fmaps), host(feats[:, :, sel]), host(coords[:, :, sel]), L, r)
+        assert rel_to_max(host(tc[:, :, sel]), want) < FP32_BAR
+        assert cb._lib.lib.comet_tc_status() == 0
+    monkeypatch.setenv("COMET_B200_DISABLE_TC", "0")
+
+
+def test_tensor_path_bf16_autocast(cb):
+    if not cb._lib.lib.comet_has_tensor_path():
+        pytest.skip("no sm_100 tensor path on this device")
+    g = torch.Generator(device="cuda").manual_seed(8)
+    fmaps = torch.randn(1, 2, 128, 64, 64, device="cuda", generator=g)
+    feats = torch.randn(1, 2, 150, 128, device="cuda", generator=g)
+    coords = torch.rand(1, 2, 150, 2, device="cuda", generator=g) * 70 - 3
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        blk = cb.CorrBlock(fmaps, num_levels=5, radius=4)
+        blk.corr(feats)
+        out = blk.sample(coords)
+    want = O.corr_lookup_bf16_autocast(host(fmaps), host(feats), host(coords), 5, 4)
+    assert rel_to_max(host(out), want) < 8e-3          # same rounding points (reciprocal multiply vs divide)
+    assert rel_to_max(host(out), O.corr_lookup(host(fmaps), host(feats), host(coords), 5, 4)) < BF16_BAR
