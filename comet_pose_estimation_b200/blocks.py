@@ -38,12 +38,18 @@ class _Pyramid:
         assert n >= 0
         self.pyr = torch.empty(max(n, 1), dtype=torch.float32, device=fmaps.device)
         self.split = None  # packed bf16 hi/lo pyramid of the tensor-core path
+        self.layout = _lib.PYR_NCHW
         with torch.cuda.device(fmaps.device):
             if B * S > 0 and lib.comet_tc_supported(C, H, W, num_levels, 0, _lib.PAD_ZEROS) and tensor_path_enabled():
                 self.split = torch.empty(lib.comet_tc_split_elems(B * S), dtype=torch.bfloat16, device=fmaps.device)
                 _lib.check(lib.comet_tc_prepare_f32(self.fmaps0.data_ptr(), self.split.data_ptr(),
                                                     self.pyr.data_ptr(), B * S, C, H, W, num_levels,
                                                     stream_ptr(fmaps.device)))
+            elif W <= 32 and H <= 33 and C % 4 == 0 and C <= 64 and num_levels > 1:
+                # small maps (fine tracker patches): levels >= 1 channel-last, one contiguous line per position
+                self.layout = _lib.PYR_CHANNEL_LAST
+                _lib.check(lib.comet_pyramid_cl_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
+                                                    num_levels, stream_ptr(fmaps.device)))
             else:
                 _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
                                                  num_levels, stream_ptr(fmaps.device)))
@@ -53,7 +59,11 @@ class _Pyramid:
         for l in range(1, num_levels):
             h, w = h // 2, w // 2
             off = lib.comet_pyramid_offset(B * S, C, H, W, l)
-            self.levels.append(self.pyr[off: off + B * S * C * h * w].view(B, S, C, h, w))
+            flat = self.pyr[off: off + B * S * C * h * w]
+            if self.layout == _lib.PYR_CHANNEL_LAST:
+                self.levels.append(flat.view(B, S, h, w, C).permute(0, 1, 4, 2, 3))  # same values, strided view
+            else:
+                self.levels.append(flat.view(B, S, C, h, w))
 
 
 def _use_tc(pyr: "_Pyramid", t: torch.Tensor, radius: int, padding: str, level_stride: int = 0) -> bool:
@@ -84,7 +94,7 @@ def _fused_lookup(pyr: _Pyramid, targets, coords, radius, padding, level_stride=
             t.data_ptr(), t.stride(0), t.stride(1), t.stride(2), level_stride,
             c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
             out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
-            B, S, N, pyr.C, pyr.H, pyr.W, pyr.num_levels, radius, pad_mode(padding), prec_mode(),
+            B, S, N, pyr.C, pyr.H, pyr.W, pyr.num_levels, radius, pad_mode(padding), prec_mode(), pyr.layout,
             stream_ptr(coords.device)))
     return out
 
@@ -146,7 +156,7 @@ class CorrBlock:
                 for l, f in enumerate(self.fmaps_pyramid):
                     h, w = f.shape[-2:]
                     tl = t[..., l * self.C:(l + 1) * self.C] if self.multiple_track_feats else t
-                    fl = p.fmaps0 if l == 0 else f
+                    fl = p.fmaps0 if l == 0 else f.contiguous()
                     v = torch.empty((B, S, N, h, w), dtype=torch.float32, device=t.device)
                     for b0 in range(0, B * S, 32768):  # gridDim.z limit
                         nb = min(32768, B * S - b0)

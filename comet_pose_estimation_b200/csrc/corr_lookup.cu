@@ -33,8 +33,15 @@ struct LookupParams {
   int pad_border, bf16;
   int lvlH[COMET_MAX_LEVELS], lvlW[COMET_MAX_LEVELS];
   long long lvlOff[COMET_MAX_LEVELS];
+  int channel_last;  // levels >= 1 stored (BS, H_l, W_l, C) instead of (BS, C, H_l, W_l); level 0 is always NCHW
   float sqrt_c;
 };
+
+// element strides of level l: channel, row, column
+__device__ __forceinline__ void level_strides(const LookupParams& p, int l, long long& sc, int& sy, int& sx) {
+  if (l > 0 && p.channel_last) { sc = 1; sy = p.lvlW[l] * p.C; sx = p.C; }
+  else { sc = (long long)p.lvlH[l] * p.lvlW[l]; sy = p.lvlW[l]; sx = 1; }
+}
 
 template <int KPL, bool TOKENS>
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) {
@@ -73,6 +80,8 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
     const int Hl = p.lvlH[l], Wl = p.lvlW[l];
     const long long HW = (long long)Hl * Wl;
     const float* F = (l == 0 ? p.fmaps : p.pyr + p.lvlOff[l]) + bs * p.C * HW;
+    long long sc; int sy, sx;
+    level_strides(p, l, sc, sy, sx);
 
     // stage the target vector (per level only when multiple_track_feats splits channels)
     if (l == 0 || p.t_level_stride != 0) {
@@ -105,14 +114,14 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
         v = vx && vy;
       }
       ok[k] = v;
-      offs[k] = v ? (long long)gy * Wl + gx : 0;
+      offs[k] = v ? (long long)gy * sy + (long long)gx * sx : 0;
       acc[k] = 0.f;
     }
     if (!p.bf16) {
 #pragma unroll 4
       for (int c = 0; c < p.C; ++c) {
         const float t = Ts[c];
-        const float* Fc = F + (long long)c * HW;
+        const float* Fc = F + (long long)c * sc;
 #pragma unroll
         for (int k = 0; k < KPL; ++k)
           if (ok[k]) acc[k] = fmaf(t, __ldg(Fc + offs[k]), acc[k]);
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
 #pragma unroll 4
       for (int c = 0; c < p.C; ++c) {
         const float t = Ts[c];
-        const float* Fc = F + (long long)c * HW;
+        const float* Fc = F + (long long)c * sc;
 #pragma unroll
         for (int k = 0; k < KPL; ++k)
           if (ok[k]) acc[k] = fmaf(t, round_bf16(__ldg(Fc + offs[k])), acc[k]);
@@ -180,6 +189,159 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const LookupParams p) 
   }
 }
 
+// ---- specialisation for the fine tracker: C == 32, compile-time radius R <= 3 (<= 64 grid positions) -----------
+// One warp per query, lanes <-> grid positions (2 per lane: rows a and a + G/2 of the same column), so all tap /
+// address arithmetic is done once per level and everything else is loads + FMAs (the first version of this kernel
+// was issue-bound: 6800 instructions per query, a quarter of them integer index math).
+//   level 0  (caller's NCHW map)     : per channel one uniform plane pointer, two scalar gathers per lane;
+//   level>=1 (channel-last pyramid)  : the 32 channels of a position are one 128-byte line -> 8 x LDG.128 at
+//                                      immediate offsets per position, target vector read as LDS.128 broadcasts.
+template <int R, bool TOKENS, bool BF16>
+__global__ void __launch_bounds__(256, 2) corr_lookup_c32_kernel(const LookupParams p) {
+  constexpr int G = 2 * R + 2, Wr = 2 * R + 1, GG = G * G, WW = Wr * Wr;
+  constexpr int ROWS0 = (GG + 31) / 32;  // grid positions per lane (2 for R=3, 1 for R=1)
+  __shared__ __align__(16) float Ts_all[8][32];
+  __shared__ float Vs_all[8][GG <= 32 ? 32 : 64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Ts = Ts_all[warp];
+  float* Vs = Vs_all[warp];
+
+  const long long q = (long long)blockIdx.x * 8 + warp;
+  const long long total = (long long)p.B * p.S * p.N;
+  if (q >= total) return;
+  const int n = (int)(q % p.N);
+  const int s = (int)((q / p.N) % p.S);
+  const int b = (int)(q / ((long long)p.N * p.S));
+  const long long bs = (long long)b * p.S + s;
+
+  const float* cp = p.coords + b * p.c_sb + s * p.c_ss + n * p.c_sn;
+  const float cx = __ldg(cp), cy = __ldg(cp + 1);
+  const float* tp = p.targets + b * p.t_sb + s * p.t_ss + n * p.t_sn;
+  {
+    const float t = __ldg(tp + lane);
+    Ts[lane] = BF16 ? round_bf16(t) : t;
+  }
+  __syncwarp();
+
+  float* op;
+  const float* pp = nullptr;
+  int corr_off = 0;
+  if (TOKENS) {
+    op = p.out + (((long long)b * p.N + n) * p.S + s) * p.D_tok;
+    pp = p.pos + ((long long)b * p.N + n) * p.D_tok;
+    corr_off = 32 + 2;
+  } else {
+    op = p.out + b * p.o_sb + s * p.o_ss + n * p.o_sn;
+  }
+  // (a one-warp-per-(query, level) variant was measured slower: the kernel sits at the DRAM transaction limit, so
+  //  what pays is memory-level parallelism per warp -- all 64 level-0 gathers of a lane are issued back to back)
+#pragma unroll 1
+  for (int l = 0; l < p.L; ++l) {
+    const int Hl = p.lvlH[l], Wl = p.lvlW[l];
+    const int HW = Hl * Wl;
+    const float* F = (l == 0 ? p.fmaps : p.pyr + p.lvlOff[l]) + bs * 32 * (long long)HW;
+    const float inv = 1.f / (float)(1 << l);
+    AxisWindow ax, ay;
+    ax.init(cx * inv, Wl, R, p.pad_border);
+    ay.init(cy * inv, Hl, R, p.pad_border);
+
+    int pos[ROWS0];
+    bool ok[ROWS0];
+    float acc[ROWS0];
+#pragma unroll
+    for (int k = 0; k < ROWS0; ++k) {
+      const int idx = lane + 32 * k;
+      int gx = 0, gy = 0;
+      const bool vx = ax.tap(idx % G, gx), vy = ay.tap(idx / G, gy);
+      ok[k] = idx < GG && vx && vy;
+      pos[k] = ok[k] ? gy * Wl + gx : 0;
+      acc[k] = 0.f;
+    }
+    if (l > 0 && p.channel_last) {
+#pragma unroll
+      for (int k = 0; k < ROWS0; ++k) {
+        const float4* v4 = reinterpret_cast<const float4*>(F) + (long long)pos[k] * 8;
+        float4 f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __ldg(v4 + i);  // pos = 0 (valid memory) when the tap is masked
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = *reinterpret_cast<const float4*>(Ts + 4 * i);
+          float4 g = f[i];
+          if (BF16) { g.x = round_bf16(g.x); g.y = round_bf16(g.y); g.z = round_bf16(g.z); g.w = round_bf16(g.w); }
+          acc[k] = fmaf(t.x, g.x, acc[k]);
+          acc[k] = fmaf(t.y, g.y, acc[k]);
+          acc[k] = fmaf(t.z, g.z, acc[k]);
+          acc[k] = fmaf(t.w, g.w, acc[k]);
+        }
+      }
+    } else {
+      float f[ROWS0][32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float* Fc = F + (long long)c * HW;  // warp-uniform plane pointer
+#pragma unroll
+        for (int k = 0; k < ROWS0; ++k) f[k][c] = __ldg(Fc + pos[k]);
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float t = Ts[c];
+#pragma unroll
+        for (int k = 0; k < ROWS0; ++k) acc[k] = fmaf(t, BF16 ? round_bf16(f[k][c]) : f[k][c], acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS0; ++k) {
+      const int idx = lane + 32 * k;
+      if (idx < GG) {
+        float v = acc[k];
+        if (BF16) v = round_bf16(v);
+        v = __fdiv_rn(v, p.sqrt_c);
+        if (BF16) v = round_bf16(v);
+        Vs[idx] = ok[k] ? v : 0.f;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < (WW + 31) / 32; ++k) {
+      const int o = lane + 32 * k;
+      if (o < WW) {
+        const int i = o / Wr, j = o - i * Wr;
+        float wx0, wx1, wy0, wy1;
+        ax.weights(i, wx0, wx1);
+        ay.weights(j, wy0, wy1);
+        const float* v = Vs + j * G + i;
+        float val = v[0] * (wx0 * wy0);
+        val += v[1] * (wx1 * wy0);
+        val += v[G] * (wx0 * wy1);
+        val += v[G + 1] * (wx1 * wy1);
+        const int d = corr_off + l * WW + o;
+        if (TOKENS) val += __ldg(pp + d);
+        op[d] = val;
+      }
+    }
+    __syncwarp();
+  }
+
+  if (TOKENS) {
+    const float* c0 = p.coords + b * p.c_sb + n * p.c_sn;  // frame 0
+    const float fx = cx - __ldg(c0), fy = cy - __ldg(c0 + 1);
+    const int w = lane & 15;                               // C_emb = 16: [pe_x (16) | pe_y (16)]
+    const float arg = __fmul_rn(lane >= 16 ? fy : fx, (float)(w & ~1) * (1000.0f / 16.f));
+    op[lane] = ((w & 1) ? cosf(arg) : sinf(arg)) + __ldg(pp + lane);
+    if (lane < 2) op[32 + lane] = (lane ? fy : fx) + __ldg(pp + 32 + lane);
+    const int feat_off = corr_off + p.L * WW;
+    op[feat_off + lane] = __ldg(tp + lane) + __ldg(pp + feat_off + lane);
+    for (int d = feat_off + 32 + lane; d < p.D_tok; d += 32) op[d] = __ldg(pp + d);
+  }
+}
+
+template <int R, bool TOKENS>
+static void launch_c32(const LookupParams& p, unsigned blocks, cudaStream_t stream) {
+  if (p.bf16) corr_lookup_c32_kernel<R, TOKENS, true><<<blocks, 256, 0, stream>>>(p);
+  else corr_lookup_c32_kernel<R, TOKENS, false><<<blocks, 256, 0, stream>>>(p);
+}
+
 template <bool TOKENS>
 static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
   const int G = 2 * p.r + 2;
@@ -190,6 +352,12 @@ static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
   if (total == 0) return COMET_OK;
   const long long blocks = (total + warps - 1) / warps;
   if (blocks > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many queries for one launch");
+  if (p.C == 32 && p.r >= 1 && p.r <= 3 && p.t_level_stride == 0 && ((uintptr_t)p.pyr % 16) == 0) {
+    if (p.r == 3) launch_c32<3, TOKENS>(p, (unsigned)blocks, stream);
+    else if (p.r == 2) launch_c32<2, TOKENS>(p, (unsigned)blocks, stream);
+    else launch_c32<1, TOKENS>(p, (unsigned)blocks, stream);
+    return launch_status("corr_lookup_c32_kernel");
+  }
   if (smem > 200 * 1024) return fail(COMET_ERR_UNSUPPORTED, "C=%d too large for the lookup kernel", p.C);
 #define COMET_LAUNCH(K)                                                                                   \
   do {                                                                                                    \
@@ -209,13 +377,14 @@ static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
 static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, const float* targets, long long t_sb,
                        long long t_ss, long long t_sn, int t_level_stride, const float* coords, long long c_sb,
                        long long c_ss, long long c_sn, int B, int S, int N, int C, int H, int W, int L, int r,
-                       int pad_mode, int prec_mode) {
+                       int pad_mode, int prec_mode, int pyr_layout) {
   COMET_REQUIRE(B >= 0 && S >= 0 && N >= 0, "negative batch dimension");
   COMET_REQUIRE(C >= 1 && H >= 1 && W >= 1, "C, H, W must be positive (got %d, %d, %d)", C, H, W);
   COMET_REQUIRE(L >= 1 && L <= COMET_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", COMET_MAX_LEVELS, L);
   COMET_REQUIRE(r >= 0 && r <= COMET_MAX_RADIUS, "radius must be in [0, %d] (got %d)", COMET_MAX_RADIUS, r);
   COMET_REQUIRE(pad_mode == COMET_PAD_ZEROS || pad_mode == COMET_PAD_BORDER, "bad pad_mode %d", pad_mode);
   COMET_REQUIRE(prec_mode == COMET_PREC_F32 || prec_mode == COMET_PREC_BF16_AUTOCAST, "bad prec_mode %d", prec_mode);
+  COMET_REQUIRE(pyr_layout == COMET_PYR_NCHW || pyr_layout == COMET_PYR_CHANNEL_LAST, "bad pyr_layout %d", pyr_layout);
   COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
   const long long total = (long long)B * S * N;
   COMET_REQUIRE(total == 0 || (fmaps && targets && coords), "null input pointer");
@@ -229,6 +398,7 @@ static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, co
   Levels lv = make_levels(B * S, C, H, W, L);
   for (int l = 0; l < L; ++l) { p.lvlH[l] = lv.H[l]; p.lvlW[l] = lv.W[l]; p.lvlOff[l] = lv.off[l]; }
   p.sqrt_c = sqrtf((float)C);
+  p.channel_last = pyr_layout == COMET_PYR_CHANNEL_LAST;
   p.pos = nullptr; p.D_tok = 0;
   return COMET_OK;
 }
@@ -241,10 +411,10 @@ extern "C" int comet_corr_lookup_f32(const float* fmaps, const float* pyr, const
                                      long long t_ss, long long t_sn, int t_level_stride, const float* coords,
                                      long long c_sb, long long c_ss, long long c_sn, float* out, long long o_sb,
                                      long long o_ss, long long o_sn, int B, int S, int N, int C, int H, int W, int L,
-                                     int r, int pad_mode, int prec_mode, comet_stream_t stream) {
+                                     int r, int pad_mode, int prec_mode, int pyr_layout, comet_stream_t stream) {
   LookupParams p{};
   int rc = fill_params(p, fmaps, pyr, targets, t_sb, t_ss, t_sn, t_level_stride, coords, c_sb, c_ss, c_sn, B, S, N,
-                       C, H, W, L, r, pad_mode, prec_mode);
+                       C, H, W, L, r, pad_mode, prec_mode, pyr_layout);
   if (rc != COMET_OK) return rc;
   COMET_REQUIRE(t_level_stride == 0 || t_level_stride == C, "t_level_stride must be 0 or C");
   COMET_REQUIRE((long long)B * S * N == 0 || out, "null output pointer");
@@ -256,10 +426,10 @@ extern "C" int comet_track_tokens_f32(const float* fmaps, const float* pyr, cons
                                       long long t_ss, long long t_sn, const float* coords, long long c_sb,
                                       long long c_ss, long long c_sn, const float* pos_emb, float* tokens, int B,
                                       int S, int N, int C, int H, int W, int L, int r, int pad_mode, int prec_mode,
-                                      int D_tok, comet_stream_t stream) {
+                                      int pyr_layout, int D_tok, comet_stream_t stream) {
   LookupParams p{};
   int rc = fill_params(p, fmaps, pyr, track_feats, t_sb, t_ss, t_sn, 0, coords, c_sb, c_ss, c_sn, B, S, N, C, H, W,
-                       L, r, pad_mode, prec_mode);
+                       L, r, pad_mode, prec_mode, pyr_layout);
   if (rc != COMET_OK) return rc;
   const int need = 2 * C + 2 + L * (2 * r + 1) * (2 * r + 1);
   COMET_REQUIRE(C % 4 == 0, "latent_dim must be a multiple of 4 for the flow embedding (got %d)", C);

@@ -21,6 +21,69 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const float* __restrict__
   }
 }
 
+// Channel-last pyramid for small maps (the fine tracker's 31x31 patches; W <= 32).  One CTA per (frame, map):
+// warp w streams the channel planes w, w+nw, ... from global memory (row pairs, fully coalesced, all loads of a
+// plane in flight), pools 2x2 with shuffles, and parks the results in a shared tile [level][pos][C+1] (the +1
+// keeps both the per-channel column accesses and the per-position row accesses bank-conflict free).  Deeper
+// levels are pooled from the tile.  After one barrier the CTA writes every level as ONE contiguous channel-last
+// block (BS, H_l, W_l, C) with coalesced stores.
+constexpr int CL_MAX_ROWS = 16;  // H/2 <= 16
+__global__ void __launch_bounds__(256, 4) pyramid_cl_kernel(const float* __restrict__ in, float* __restrict__ pyr,
+                                                          int C, int H, int W, int L, Levels lv) {
+  extern __shared__ float tile[];  // levels 1..L-1 back to back, each H_l*W_l rows of (C+1) floats
+  const long long map = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int CP = C + 1;
+  const int H1 = H / 2, W1 = W / 2;
+  for (int c = warp; c < C; c += nw) {
+    const float* plane = in + (map * C + c) * (long long)H * W;
+    // level 1 straight from global memory: lane <-> input column
+    float r0[CL_MAX_ROWS], r1[CL_MAX_ROWS];
+#pragma unroll
+    for (int y = 0; y < CL_MAX_ROWS; ++y) {
+      const bool on = y < H1 && lane < W;
+      r0[y] = on ? __ldg(plane + (2 * y) * W + lane) : 0.f;
+      r1[y] = on ? __ldg(plane + (2 * y + 1) * W + lane) : 0.f;
+    }
+#pragma unroll
+    for (int y = 0; y < CL_MAX_ROWS; ++y) {
+      if (y < H1) {
+        const int x2 = (2 * lane) & 31;
+        const float a = __shfl_sync(0xffffffffu, r0[y], x2), b = __shfl_sync(0xffffffffu, r0[y], x2 + 1);
+        const float cc = __shfl_sync(0xffffffffu, r1[y], x2), d = __shfl_sync(0xffffffffu, r1[y], x2 + 1);
+        if (lane < W1) tile[(y * W1 + lane) * CP + c] = ((a + b) + (cc + d)) * 0.25f;
+      }
+    }
+    __syncwarp();
+    // deeper levels from the tile (this warp's own channel column)
+    int Hi = H1, Wi = W1, in_off = 0;
+    for (int l = 2; l < L; ++l) {
+      const int Ho = Hi / 2, Wo = Wi / 2;
+      const int out_off = in_off + Hi * Wi * CP;
+      for (int i = lane; i < Ho * Wo; i += 32) {
+        const int yo = i / Wo, xo = i - yo * Wo;
+        const float* s4 = tile + in_off + ((2 * yo) * Wi + 2 * xo) * CP + c;
+        tile[out_off + i * CP + c] = ((s4[0] + s4[CP]) + (s4[Wi * CP] + s4[(Wi + 1) * CP])) * 0.25f;
+      }
+      __syncwarp();
+      in_off = out_off;
+      Hi = Ho; Wi = Wo;
+    }
+  }
+  __syncthreads();
+  int Hl = H1, Wl = W1, off = 0;
+  for (int l = 1; l < L; ++l) {
+    float* dst = pyr + lv.off[l] + map * (long long)C * Hl * Wl;
+    const int n = Hl * Wl * C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int pos = i / C, c = i - pos * C;
+      dst[i] = tile[off + pos * CP + c];
+    }
+    off += Hl * Wl * CP;
+    Hl /= 2; Wl /= 2;
+  }
+}
+
 }  // namespace comet
 
 using namespace comet;
@@ -57,4 +120,24 @@ extern "C" int comet_pyramid_f32(const float* fmaps, float* pyr, int BS, int C, 
     if (rc != COMET_OK) return rc;
   }
   return COMET_OK;
+}
+
+extern "C" int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L,
+                                    comet_stream_t stream) {
+  COMET_REQUIRE(BS >= 0 && C >= 1 && H >= 1 && W >= 1, "bad shape");
+  COMET_REQUIRE(L >= 1 && L <= COMET_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", COMET_MAX_LEVELS, L);
+  COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
+  COMET_REQUIRE(W <= 32 && H <= 2 * CL_MAX_ROWS + 1, "channel-last pyramid needs W <= 32 and H <= 33");
+  if (L == 1 || BS == 0) return COMET_OK;
+  COMET_REQUIRE(fmaps && pyr, "null pointer");
+  Levels lv = make_levels(BS, C, H, W, L);
+  size_t rows = 0;
+  for (int l = 1; l < L; ++l) rows += (size_t)lv.H[l] * lv.W[l];
+  const size_t smem = rows * (C + 1) * sizeof(float);
+  COMET_REQUIRE(smem <= 160 * 1024, "channel-last pyramid tile does not fit in shared memory (C=%d)", C);
+  if (smem > 48 * 1024)
+    COMET_CUDA(cudaFuncSetAttribute(pyramid_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = C >= 8 ? 256 : 32 * C;
+  pyramid_cl_kernel<<<BS, threads, smem, (cudaStream_t)stream>>>(fmaps, pyr, C, H, W, L, lv);
+  return launch_status("pyramid_cl_kernel");
 }

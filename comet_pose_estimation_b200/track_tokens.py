@@ -93,5 +93,5 @@ class TrackTokenizer:
                 c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
                 self.pos.data_ptr(), out.data_ptr(),
                 B, S, N, p.C, p.H, p.W, p.num_levels, self.radius, pad_mode(self.padding_mode), prec_mode(),
-                self.tdim, stream_ptr(c.device)))
+                p.layout, self.tdim, stream_ptr(c.device)))
         return out

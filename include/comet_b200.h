@@ -42,6 +42,9 @@ extern "C" {
 #define COMET_PREC_BF16_AUTOCAST 1 /* what torch.autocast(bf16) makes of CorrBlock.corr: bf16 operands,
                                       f32 accumulate, volume rounded to bf16, f32 lookup (bar 2e-2) */
 
+#define COMET_PYR_NCHW 0         /* pyramid levels 1..L-1 stored (BS, C, H_l, W_l), like the reference */
+#define COMET_PYR_CHANNEL_LAST 1 /* ... stored (BS, H_l, W_l, C): one contiguous line per position (fine tracker) */
+
 #define COMET_MAX_LEVELS 8
 #define COMET_MAX_RADIUS 7
 
@@ -61,6 +64,9 @@ int comet_has_tensor_path(void);
 long long comet_pyramid_offset(int BS, int C, int H, int W, int level); /* elements; level>=1 */
 long long comet_pyramid_elems(int BS, int C, int H, int W, int L);      /* total for levels 1..L-1 */
 int comet_pyramid_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, comet_stream_t stream);
+/* Same pooling, levels 1..L-1 written channel-last (COMET_PYR_CHANNEL_LAST) at the same offsets.
+ * Requires W <= 32, H <= 33 and a pooled tile that fits shared memory (small maps: the fine tracker's patches). */
+int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, comet_stream_t stream);
 
 /* ---- correlation volume: CorrBlock.corr, blocks.py:409-429 -------------
  * vol[bs, n, hw] = (sum_c targets[bs, n, c] * fmap[bs, c, hw]) / sqrt(C) for ONE pyramid level.
@@ -79,7 +85,7 @@ int comet_corr_volume_f32(const float* targets, long long t_sbs, long long t_sn,
 int comet_corr_lookup_f32(const float* fmaps, const float* pyr, const float* targets, long long t_sb, long long t_ss,
                           long long t_sn, int t_level_stride, const float* coords, long long c_sb, long long c_ss,
                           long long c_sn, float* out, long long o_sb, long long o_ss, long long o_sn, int B, int S,
-                          int N, int C, int H, int W, int L, int r, int pad_mode, int prec_mode,
+                          int N, int C, int H, int W, int L, int r, int pad_mode, int prec_mode, int pyr_layout,
                           comet_stream_t stream);
 
 /* ---- fused track tokens: the token assembly of BaseTrackerPredictor.forward,
@@ -92,7 +98,8 @@ int comet_corr_lookup_f32(const float* fmaps, const float* pyr, const float* tar
 int comet_track_tokens_f32(const float* fmaps, const float* pyr, const float* track_feats, long long t_sb,
                            long long t_ss, long long t_sn, const float* coords, long long c_sb, long long c_ss,
                            long long c_sn, const float* pos_emb, float* tokens, int B, int S, int N, int C, int H,
-                           int W, int L, int r, int pad_mode, int prec_mode, int D_tok, comet_stream_t stream);
+                           int W, int L, int r, int pad_mode, int prec_mode, int pyr_layout, int D_tok,
+                           comet_stream_t stream);
 
 /* sampled_pos_emb = sample_features4d(get_2d_sincos_pos_embed(D,(H,W)), coords[:,0])
  * (base_track_predictor.py:200-208; utils.py:724-755, :942-974): the float64 table is evaluated on the fly at

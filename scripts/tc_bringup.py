@@ -76,7 +76,7 @@ def simt_lookup():
     out = torch.empty(1, S_, N_, 405, device=dev)
     _lib.check(lib.comet_corr_lookup_f32(pyr.fmaps0.data_ptr(), pyr.pyr.data_ptr(), feats.data_ptr(), *feats.stride()[:3], 0,
                                          coords.data_ptr(), *coords.stride()[:3], out.data_ptr(), *out.stride()[:3],
-                                         1, S_, N_, 128, 64, 64, 5, 4, 0, 0, torch.cuda.current_stream().cuda_stream))
+                                         1, S_, N_, 128, 64, 64, 5, 4, 0, 0, pyr.layout, torch.cuda.current_stream().cuda_stream))
     return out
 
 

@@ -58,7 +58,7 @@ def test_invalid_arguments_are_reported_without_a_gpu(built):
     with pytest.raises(AssertionError):
         _lib.check(rc)
     rc = _lib.lib.comet_corr_lookup_f32(None, None, None, 0, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0,
-                                        1, 1, 1, 4, 8, 8, 2, 9, 0, 0, None)
+                                        1, 1, 1, 4, 8, 8, 2, 9, 0, 0, 0, None)
     assert rc == _lib.ERR_INVALID and "radius" in _lib.last_error()
     rc = _lib.lib.comet_sincos2d_f32(None, 10, 4, 4, None)
     assert rc == _lib.ERR_INVALID
