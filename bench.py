@@ -345,10 +345,37 @@ def main():
             kern[k]["algorithmic_MB"] = ab[k] / 1e6
             kern[k]["GBps"] = ab[k] / (kern[k]["ms_avg"] * 1e-3) / 1e9
     ft = kern["fine_tokens"]
-    roof = {"bound": "hbm", "kernel": "corr_lookup_kernel<TOKENS> (fine tracker shape)", "achieved": ft["GBps"],
-            "peak": peak, "unit": "GB/s", "frac": ft["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this batch size, from the
+    # committed ncu --set full capture (profiles/traffic.json, written by scripts/ncu_traffic.py)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)["fine_tokens"]
+        if tj.get("batch") == Q:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": "corr_lookup_c32_kernel<R=3,TOKENS> (fine tracker: fused corr + lookup + tokens)",
+            "achieved": ft["GBps"], "peak": peak, "unit": "GB/s", "frac": ft["GBps"] / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ab["fine_tokens"], "ms_per_launch": ft["ms_avg"],
-            "dominant_by_time": dom}
+            "dominant_by_time": dom,
+            "note": "algorithmic bytes = window neighbourhoods (SURVEY 8d, 194 MB/sequence definition); traffic above "
+                    "them is the 32-byte NCHW level-0 window rows fetched at DRAM granularity"}
+    # correlation on the tensor pipe (coarse tracker): FLOPs as the reference defines them (all pyramid levels,
+    # one pass) and as executed (3 bf16 passes for fp32 parity, 86 tiles of 64 positions incl. 48 padded columns)
+    ct = kern["coarse_tokens"]
+    flop_alg = 2.0 * Q * COARSE["S"] * COARSE["N"] * COARSE["C"] * 5456
+    flop_exec = 3 * 2.0 * Q * COARSE["S"] * COARSE["N"] * COARSE["C"] * 5504
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tpeak = float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        tpeak = 1400.0
+    tensor = {"bound": "tensor", "kernel": "corr_tc_kernel (coarse tracker: tcgen05 correlation + lookup + tokens)",
+              "achieved": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12, "executed_TFLOPs": flop_exec / (ct["ms_avg"] * 1e-3) / 1e12,
+              "peak": tpeak, "unit": "TFLOP/s", "frac": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12 / tpeak,
+              "frac_executed": flop_exec / (ct["ms_avg"] * 1e-3) / 1e12 / tpeak, "ms_per_launch": ct["ms_avg"]}
 
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------
     e2e = None
@@ -398,7 +425,7 @@ def main():
             "config": {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
                        "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
                        "l2": "inputs per step exceed L2 (fine patch features: %.1f GB)" % (Q * 1.008)},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roof, "roofline_tensor": tensor, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": hp.launches_per_step * args.steps, "kernels": kern,
             "tensor_path": bool(cb._lib.lib.comet_has_tensor_path()),
         }

@@ -8,6 +8,8 @@ Python mirror of the reference interface for the path:
   (comet/models/utils.py:37-101, :724-974)
 * :mod:`.track_tokens` -- the fused token assembly of ``BaseTrackerPredictor.forward``
   (comet/models/track_modules/base_track_predictor.py:153-224)
+* :mod:`.base_track_predictor` -- drop-in ``BaseTrackerPredictor`` (same signature / state-dict keys) whose loop
+  runs one fused kernel per iteration; :mod:`.update_former` is the torch plumbing it drives between iterations
 
 All arithmetic runs in hand-written CUDA kernels behind the C ABI of ``include/comet_b200.h``
 (``libcomet_b200.so``).  PyTorch is used for device memory, streams and ``torch.distributed`` only.
@@ -25,5 +27,7 @@ from .utils import (  # noqa: F401
     get_1d_sincos_pos_embed_from_grid,
 )
 from .track_tokens import TrackTokenizer, sampled_pos_emb, transformer_dim  # noqa: F401
+from .update_former import EfficientUpdateFormer  # noqa: F401
+from .base_track_predictor import BaseTrackerPredictor  # noqa: F401
 
 __version__ = "0.1.0"
