@@ -26,6 +26,8 @@ SIGNATURES = {
     "comet_version": (_i, []),
     "comet_last_error": (C.c_char_p, []),
     "comet_has_tensor_path": (_i, []),
+    "comet_launch_count": (_ll, []),
+    "comet_set_l2_fetch_granularity": (_i, [_i]),
     "comet_pyramid_offset": (_ll, [_i, _i, _i, _i, _i]),
     "comet_pyramid_elems": (_ll, [_i, _i, _i, _i, _i]),
     "comet_pyramid_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),

@@ -29,7 +29,9 @@ inline int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess)                                                                     \
       return ::comet::fail(COMET_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));    \
   } while (0)
+void count_launch();     // defined in cabi.cu: every kernel launch of the library goes through launch_status()
 inline int launch_status(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(COMET_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
   return COMET_OK;

@@ -55,6 +55,12 @@ int comet_version(void);
 const char* comet_last_error(void);
 /* 1 if the tcgen05/TMEM/TMA correlation kernels were compiled in and the current device is sm_100. */
 int comet_has_tensor_path(void);
+/* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */
+long long comet_launch_count(void);
+/* Device tuning hint: cudaLimitMaxL2FetchGranularity (32/64/128 bytes; 0 = only query).  The window gathers of the
+ * fine tracker touch 32-byte row segments, so a smaller fetch granularity cuts DRAM over-fetch.  Returns the value
+ * in effect, or -1 if there is no device. */
+int comet_set_l2_fetch_granularity(int bytes);
 
 /* ---- feature pyramid: CorrBlock.__init__ / EfficientCorrBlock.__init__,
  *      comet/models/track_modules/blocks.py:352-374 and :433-444 ------------

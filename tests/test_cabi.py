@@ -11,8 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def built():
-    from comet_pose_estimation_b200 import build
+    import importlib.util
 
+    spec = importlib.util.spec_from_file_location("_comet_b200_build",
+                                                  os.path.join(ROOT, "comet_pose_estimation_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)  # by path: the package import needs the library this fixture builds
     return build.build()
 
 
