@@ -27,7 +27,6 @@ SIGNATURES = {
     "comet_last_error": (C.c_char_p, []),
     "comet_has_tensor_path": (_i, []),
     "comet_launch_count": (_ll, []),
-    "comet_set_l2_fetch_granularity": (_i, [_i]),
     "comet_pyramid_offset": (_ll, [_i, _i, _i, _i, _i]),
     "comet_pyramid_elems": (_ll, [_i, _i, _i, _i, _i]),
     "comet_pyramid_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
@@ -46,12 +45,13 @@ SIGNATURES = {
     "comet_sincos2d_f32": (_i, [_p, _i, _i, _i, _p]),
     "comet_tc_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "comet_tc_split_elems": (_ll, [_i]),
+    "comet_tc_workspace_bytes": (_ll, [_i, _i]),
     "comet_tc_prepare_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "comet_tc_corr_lookup_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
-                                      _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+                                      _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "comet_tc_track_tokens_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _p,
-                                       _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "comet_tc_corr_volume_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+                                       _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "comet_tc_corr_volume_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "comet_tc_status": (_i, []),
     "comet_tc_debug_stamps": (None, [_p]),
 }

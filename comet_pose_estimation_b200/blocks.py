@@ -54,7 +54,7 @@ class _Pyramid:
                 _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
                                                  num_levels, stream_ptr(fmaps.device)))
         self.levels: List[torch.Tensor] = [fmaps]
-        self._tc_ok_cache = {}
+        self._ws = None  # scratch of the tensor path (sorted query order + job list), sized for the last N seen
         h, w = H, W
         for l in range(1, num_levels):
             h, w = h // 2, w // 2
@@ -64,6 +64,13 @@ class _Pyramid:
                 self.levels.append(flat.view(B, S, h, w, C).permute(0, 1, 4, 2, 3))  # same values, strided view
             else:
                 self.levels.append(flat.view(B, S, C, h, w))
+
+
+def _tc_workspace(pyr: "_Pyramid", N: int) -> torch.Tensor:
+    need = lib.comet_tc_workspace_bytes(pyr.B * pyr.S, N)
+    if pyr._ws is None or pyr._ws.numel() * 4 < need:
+        pyr._ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=pyr.fmaps0.device)
+    return pyr._ws
 
 
 def _use_tc(pyr: "_Pyramid", t: torch.Tensor, radius: int, padding: str, level_stride: int = 0) -> bool:
@@ -87,7 +94,7 @@ def _fused_lookup(pyr: _Pyramid, targets, coords, radius, padding, level_stride=
                 c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
                 out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
                 B, S, N, pyr.C, pyr.H, pyr.W, pyr.num_levels, radius, pad_mode(padding), prec_mode(),
-                stream_ptr(coords.device)))
+                _tc_workspace(pyr, N).data_ptr(), stream_ptr(coords.device)))
             return out
         _lib.check(lib.comet_corr_lookup_f32(
             pyr.fmaps0.data_ptr(), pyr.pyr.data_ptr(),
@@ -148,7 +155,8 @@ class CorrBlock:
                     t4 = t.view(B, S, N, -1)
                     _lib.check(lib.comet_tc_corr_volume_f32(
                         p.split.data_ptr(), t4.data_ptr(), t4.stride(0), t4.stride(1), t4.stride(2), ptrs,
-                        B, S, N, p.C, p.H, p.W, p.num_levels, mode, stream_ptr(t.device)))
+                        B, S, N, p.C, p.H, p.W, p.num_levels, mode, _tc_workspace(p, N).data_ptr(),
+                        stream_ptr(t.device)))
                     if mode == _lib.PREC_BF16_AUTOCAST:
                         vols = [v.to(torch.bfloat16) for v in vols]
                     self._volumes = vols

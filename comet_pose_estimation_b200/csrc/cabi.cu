@@ -17,19 +17,6 @@ extern "C" const char* comet_last_error(void) { return comet::last_error_buf(); 
 
 extern "C" long long comet_launch_count(void) { return comet::g_launches.load(std::memory_order_relaxed); }
 
-extern "C" int comet_set_l2_fetch_granularity(int bytes) {
-  size_t got = 0;
-  if (bytes > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes) != cudaSuccess) {
-    cudaGetLastError();
-    return -1;
-  }
-  if (cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity) != cudaSuccess) {
-    cudaGetLastError();
-    return -1;
-  }
-  return (int)got;
-}
-
 #ifndef COMET_HAVE_TC
 extern "C" int comet_has_tensor_path(void) { return 0; }
 #endif

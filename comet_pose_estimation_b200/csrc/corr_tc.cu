@@ -52,7 +52,8 @@ constexpr int DUMP_BYTES = TILE_M * DUMP_STRIDE * 4;
 constexpr int WIN_STRIDE = 84;                  // floats per staged window row (81 + 3, 16-byte aligned rows)
 constexpr int WIN_BYTES = TILE_M * WIN_STRIDE * 4;
 constexpr int NWIN = 2;                         // window buffers (epilogue -> stager hand-off)
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + DUMP_BYTES + NWIN * WIN_BYTES + 512;
+constexpr int ROWOFF_BYTES = 2 * TILE_M * 8;      // per query: element offset of its pos_emb row and of its output row
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + DUMP_BYTES + NWIN * WIN_BYTES + ROWOFF_BYTES + 512;
 
 __host__ __device__ inline int level_offset(int l) { return l == 0 ? 0 : l == 1 ? 4096 : l == 2 ? 5120 : l == 3 ? 5376 : 5440; }
 __host__ __device__ inline int num_tiles(int L) { return L == 1 ? 64 : L == 2 ? 80 : L == 3 ? 84 : L == 4 ? 85 : 86; }
@@ -71,6 +72,23 @@ __device__ __forceinline__ TileInfo tile_info(int t) {
   return ti;
 }
 
+// One unit of work of the persistent kernel: up to four runs of consecutive tiles (a run never spans two pyramid
+// levels) of one (frame, 128 sorted queries) pair.  Written by tc_plan_kernel, read by every warp role.
+struct __align__(16) JobRec {
+  int bs, mt, nseg, flags;
+  int t0[4];          // first tile of run i (global tile numbering of tile_info)
+  int t1[4];          // one past the last tile of run i
+  int own_lo, own_hi; // level-0 jobs: the window rows ("tops") whose output this job writes
+  int pad0, pad1;
+};
+constexpr int JF_FIRST0 = 1;  // first level-0 job of its (frame, query tile)
+constexpr int JF_LAST0 = 2;   // last level-0 job: also writes the non-correlation token channels
+constexpr int BIG = 1 << 28;
+constexpr int MAX_SPLIT = 4;  // level-0 row chunks per (frame, query tile)
+constexpr int MAX_CHUNK = MAX_SPLIT + 2;
+constexpr int PLAN_BINS = 96;      // sort key: floor(y) clamped to [-16, 79]
+constexpr int PLAN_MAX_MT = 256;   // query tiles per frame the plan kernel tracks row ranges for (N <= 32768)
+
 struct Params {
   const float* targets; long long t_sb, t_ss, t_sn;
   const float* coords;  long long c_sb, c_ss, c_sn;
@@ -78,7 +96,9 @@ struct Params {
   const float* pos; int D_tok; int tokens;            // token layout (B,N,S,D_tok) when tokens
   float* vol[5]; int volume_mode;                      // volume mode: per-level (BS,N,H_l,W_l)
   int B, S, N, L, r, npass, bf16;
-  int BS, mtiles, nchunk, njobs, ntiles;
+  int BS, mtiles, npad, nsplit, npyr, nchunk, njobs;
+  const int* perm;      // [BS][npad]: query index of sorted slot (or -1), written by tc_plan_kernel
+  const JobRec* jobs;   // [njobs]
   float inv_sqrt_c;
   int* status;  // device int: set non-zero by the watchdog
   int debug;    // COMET_TC_DEBUG bit mask (attribution experiments; 0 in production)
@@ -193,31 +213,189 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf16_resid(float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); }
 
-__device__ __forceinline__ void job_decode(const Params& p, int job, int& bs, int& chunk, int& mt) {
-  mt = job % p.mtiles;
-  const int t = job / p.mtiles;
-  chunk = t % p.nchunk;
-  bs = t / p.nchunk;
+__device__ __forceinline__ JobRec load_job(const JobRec* j) {
+  JobRec r;
+  const int4* s = reinterpret_cast<const int4*>(j);
+  int4* d = reinterpret_cast<int4*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d[i] = __ldg(s + i);
+  return r;
 }
-__device__ __forceinline__ void chunk_tiles(const Params& p, int chunk, int& t0, int& t1) {
-  if (chunk < 4) { t0 = 16 * chunk; t1 = min(t0 + 17, 64); }
-  else { t0 = 64; t1 = p.ntiles; }
+// Job sequence of this CTA: blockIdx.x, +gridDim.x, ... skipping empty records -- identical in every warp role.
+__device__ __forceinline__ int seek_job(const Params& p, int job) {
+  while (job < p.njobs && __ldg(&p.jobs[job].nseg) == 0) job += gridDim.x;
+  return job;
 }
 
 __device__ __forceinline__ void stamp(const Params& p, int role, int idx, int which) {
   if (p.stamps && blockIdx.x == 0 && idx < 64) p.stamps[(role * 64 + idx) * 2 + which] = clock64();
 }
 
+// Window geometry of one query along y at pyramid level l -- the ONE definition shared by the plan kernel (row
+// ranges, sort) and the epilogue (lookup), so both always agree on which map rows a query touches.
+__device__ __forceinline__ void level_y(float cy, int level, int r, int& y0, float& fy) {
+  const float inv = 1.f / (float)(1 << level);
+  const float py = fminf(fmaxf(cy * inv, -1.0e6f), 1.0e6f);
+  const float fl = floorf(py);
+  fy = py - fl;
+  y0 = (int)fl - r;
+}
+
+// ------------------------------------------------------------------ plan: sort queries by y, row ranges, job list
+// One CTA per frame.  Queries are counting-sorted by floor(y) so that the 128 queries of a tile (and the 32 of an
+// epilogue warp) share a narrow band of map rows; per (tile, level) the band [first, last needed row] is reduced
+// and turned into job records: `nsplit` level-0 jobs (row chunks with one row of overlap, so every window entry
+// finds both of its rows inside one chunk) and `npyr` jobs for levels 1..L-1.  `full` (volume mode): identity
+// order, every tile of every level.
+__device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ perm, JobRec* __restrict__ jobs, int full,
+                                           int bs) {
+  __shared__ int hist[PLAN_BINS];
+  __shared__ int rng[PLAN_MAX_MT][10];
+  const int b = bs / p.S, s = bs - b * p.S;
+  const int Wr = 2 * p.r + 1;
+  int* myperm = perm + (long long)bs * p.npad;
+  const bool track = p.mtiles <= PLAN_MAX_MT;  // else: sorted, but every job covers the full maps
+
+  for (int i = threadIdx.x; i < PLAN_BINS; i += blockDim.x) hist[i] = 0;
+  if (track)
+    for (int i = threadIdx.x; i < p.mtiles * 10; i += blockDim.x) (&rng[0][0])[i] = (i & 1) ? -BIG : BIG;
+  __syncthreads();
+
+  if (full) {
+    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) myperm[i] = i < p.N ? i : -1;
+  } else {
+    const float* cbase = p.coords + b * p.c_sb + s * p.c_ss + 1;
+    for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+      const float cy = __ldg(cbase + (long long)n * p.c_sn);
+      const int key = min(max((int)floorf(fminf(fmaxf(cy, -1.0e6f), 1.0e6f)), -16), PLAN_BINS - 17) + 16;
+      atomicAdd(&hist[key], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int i = 0; i < PLAN_BINS; ++i) { const int c = hist[i]; hist[i] = run; run += c; }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+      const float cy = __ldg(cbase + (long long)n * p.c_sn);
+      const int key = min(max((int)floorf(fminf(fmaxf(cy, -1.0e6f), 1.0e6f)), -16), PLAN_BINS - 17) + 16;
+      const int slot = atomicAdd(&hist[key], 1);
+      myperm[slot] = n;
+      if (track) {
+        const int mt = slot >> 7;
+        for (int l = 0; l < p.L; ++l) {
+          int y0; float fy;
+          level_y(cy, l, p.r, y0, fy);
+          const int rl = max(y0, 0), rh = min(y0 + Wr, (MAP >> l) - 1);
+          if (rl <= rh) { atomicMin(&rng[mt][2 * l], rl); atomicMax(&rng[mt][2 * l + 1], rh); }
+        }
+      }
+    }
+    for (int i = p.N + threadIdx.x; i < p.npad; i += blockDim.x) myperm[i] = -1;
+  }
+  __syncthreads();
+
+  for (int idx = threadIdx.x; idx < p.mtiles * p.nchunk; idx += blockDim.x) {
+    const int mt = idx / p.nchunk, c = idx - mt * p.nchunk;
+    JobRec jr;
+    jr.bs = bs; jr.mt = mt; jr.nseg = 0; jr.flags = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { jr.t0[i] = 0; jr.t1[i] = 0; }
+    jr.own_lo = -BIG; jr.own_hi = BIG; jr.pad0 = 0; jr.pad1 = 0;
+    auto rows_of = [&](int l, int& R0, int& R1) {
+      if (full || !track) { R0 = 0; R1 = (MAP >> l) - 1; }
+      else { R0 = rng[mt][2 * l]; R1 = rng[mt][2 * l + 1]; if (R0 > R1) { R0 = 0; R1 = 0; } }
+    };
+    if (c < p.nsplit) {
+      int R0, R1;
+      rows_of(0, R0, R1);
+      const int nr = R1 - R0 + 1, rpc = (nr + p.nsplit - 1) / p.nsplit;
+      const int a = R0 + c * rpc, bb = min(a + rpc, R1);
+      const bool real = (c == 0) || (a < R1);
+      if (real) {
+        const bool last = bb == R1;
+        jr.nseg = 1; jr.t0[0] = a; jr.t1[0] = bb + 1;
+        jr.flags = (c == 0 ? JF_FIRST0 : 0) | (last ? JF_LAST0 : 0);
+        jr.own_lo = (c == 0) ? -BIG : a;
+        jr.own_hi = last ? BIG : bb - 1;
+      }
+    } else {
+      const int k = c - p.nsplit;
+      const int l_lo = (p.npyr == 2 && k == 1) ? 2 : 1;
+      const int l_hi = (p.npyr == 2 && k == 0) ? 2 : p.L;   // exclusive
+      for (int l = l_lo; l < l_hi; ++l) {
+        int R0, R1;
+        rows_of(l, R0, R1);
+        const int sh = l == 1 ? 1 : l == 2 ? 2 : l == 3 ? 3 : 2;  // log2(map rows per tile): 2, 4, 8, 4
+        const int base = l == 1 ? 64 : l == 2 ? 80 : l == 3 ? 84 : 85;
+        jr.t0[jr.nseg] = base + (R0 >> sh);
+        jr.t1[jr.nseg] = base + (R1 >> sh) + 1;
+        ++jr.nseg;
+      }
+    }
+    jobs[((long long)bs * p.mtiles + mt) * p.nchunk + c] = jr;
+  }
+}
+
+// The token channels that do not depend on the correlation (base_track_predictor.py:170-196, :221):
+//   [ sin/cos(flow * div) (C) | flow (2) | .. fcorrs: written by corr_tc_kernel .. | track_feats (C) | zero pad ] + pos_emb
+// One warp per (b, n, s) token row, rows in output order (coalesced 128-byte stores).
+__device__ __forceinline__ void token_misc_rows(const Params& p, long long warp_id, long long nwarps, int lane) {
+  const int WW = (2 * p.r + 1) * (2 * p.r + 1);
+  const int Ce = KC >> 1;
+  const float step = 1000.0f / (float)Ce;
+  const int feat_off = KC + 2 + p.L * WW;
+  const int ntail = p.D_tok - feat_off;  // track_feats + pad
+  const long long rows = (long long)p.B * p.N * p.S;
+  for (long long row = warp_id; row < rows; row += nwarps) {
+    const int s = (int)(row % p.S);
+    const long long bn = row / p.S;
+    const int n = (int)(bn % p.N), b = (int)(bn / p.N);
+    const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)n * p.c_sn;
+    const float* c0 = p.coords + b * p.c_sb + (long long)n * p.c_sn;  // frame 0
+    const float flx = __ldg(cp) - __ldg(c0), fly = __ldg(cp + 1) - __ldg(c0 + 1);
+    const float* pq = p.pos + bn * p.D_tok;
+    const float* tq = p.targets + b * p.t_sb + s * p.t_ss + (long long)n * p.t_sn;
+    float* o = p.out + row * p.D_tok;
+    float pe[4], tf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { pe[k] = __ldg(pq + lane + 32 * k); tf[k] = __ldg(tq + lane + 32 * k); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = lane + 32 * k;
+      const int axis = e / Ce, w = e - axis * Ce;
+      const float arg = __fmul_rn(axis ? fly : flx, (float)(w & ~1) * step);
+      o[e] = ((w & 1) ? cosf(arg) : sinf(arg)) + pe[k];
+    }
+    if (lane < 2) o[KC + lane] = (lane ? fly : flx) + __ldg(pq + KC + lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[feat_off + lane + 32 * k] = tf[k] + __ldg(pq + feat_off + lane + 32 * k);
+    for (int c = KC + lane; c < ntail; c += 32) o[feat_off + c] = __ldg(pq + feat_off + c);   // zero pad + pos_emb
+  }
+}
+
+// Launch 1 of 2 per call: CTAs [0, BS) plan one frame each, the rest write the correlation-independent token channels.
+__global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __restrict__ perm, JobRec* __restrict__ jobs,
+                                                      int full) {
+  if ((int)blockIdx.x < p.BS) {
+    plan_frame(p, perm, jobs, full, blockIdx.x);
+  } else {
+    const long long nw = (long long)(gridDim.x - p.BS) * 8;
+    token_misc_rows(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
- // dynamic shared memory is the only shared allocation of this kernel, so it starts 1024-byte aligned (SWIZZLE_128B
+  // dynamic shared memory is the only shared allocation of this kernel, so it starts 1024-byte aligned (SWIZZLE_128B
   // tiles need that); no integer round trip on the pointer, so that accesses stay LDS/STS rather than generic LD/ST
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sB = smem;                                                   // NSTAGE x [hi 16 KB][lo 16 KB]
   float* dump = reinterpret_cast<float*>(sB + NSTAGE * STAGE_BYTES);   // private accumulator rows
   float* win = dump + TILE_M * DUMP_STRIDE;                            // staged window rows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(win + NWIN * TILE_M * WIN_STRIDE);
+  long long* rowoff = reinterpret_cast<long long*>(win + NWIN * TILE_M * WIN_STRIDE);  // [2][TILE_M]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowoff + 2 * TILE_M);
   uint64_t* full = bars;                  // [NSTAGE]  TMA -> MMA
   uint64_t* empty = full + NSTAGE;        // [NSTAGE]  MMA -> TMA
   uint64_t* acc_full = empty + NSTAGE;    // [NACC]    MMA -> epilogue
@@ -256,22 +434,22 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       int tcount = 0;
-      for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
-        int bs, chunk, mt, t0, t1;
-        job_decode(p, job, bs, chunk, mt);
-        chunk_tiles(p, chunk, t0, t1);
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
-          stamp(p, 0, tcount++, 0);
-          uint8_t* dst = sB + stage * STAGE_BYTES;
-          if (p.debug & 64) {
-            mbar_arrive(&full[stage]);
-          } else {
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(&tmap, &full[stage], dst, t * TILE_N, bs * KC);
-            tma_load_2d(&tmap, &full[stage], dst + B_TILE_BYTES, t * TILE_N, (p.BS + bs) * KC);
+      for (int job = seek_job(p, blockIdx.x); job < p.njobs; job = seek_job(p, job + gridDim.x)) {
+        const JobRec jr = load_job(p.jobs + job);
+        for (int sg = 0; sg < jr.nseg; ++sg) {
+          for (int t = jr.t0[sg]; t < jr.t1[sg]; ++t) {
+            mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
+            stamp(p, 0, tcount++, 0);
+            uint8_t* dst = sB + stage * STAGE_BYTES;
+            if (p.debug & 64) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_expect_tx(&full[stage], STAGE_BYTES);
+              tma_load_2d(&tmap, &full[stage], dst, t * TILE_N, jr.bs * KC);
+              tma_load_2d(&tmap, &full[stage], dst + B_TILE_BYTES, t * TILE_N, (p.BS + jr.bs) * KC);
+            }
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -280,48 +458,48 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, ji = 0;
     int tcount = 0;
     const int npass = (p.debug & 8) ? 0 : p.npass;
-    const uint32_t idesc = (p.debug & 128) ? (IDESC + (8u << 17)) : IDESC;  // timing experiment: N=128
-    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
-      int bs, chunk, mt, t0, t1;
-      job_decode(p, job, bs, chunk, mt);
-      chunk_tiles(p, chunk, t0, t1);
+    for (int job = seek_job(p, blockIdx.x); job < p.njobs; job = seek_job(p, job + gridDim.x), ++ji) {
+      const JobRec jr = load_job(p.jobs + job);
       const uint32_t abuf = ji & 1;
       mbar_wait(&a_full[abuf], (ji >> 1) & 1, p.status, 2);
       const uint32_t a_hi = TM_A + abuf * 128, a_lo = a_hi + 64;
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1, p.status, 3);
-        mbar_wait(&full[stage], phase, p.status, 4);
-        tcgen05_fence_after();
-        if (lane == 0) stamp(p, 1, tcount, 0);
-        if (elect_one()) {
-          const uint32_t b_hi = smem_u32(sB + stage * STAGE_BYTES);
-          const uint32_t d = TM_ACC + acc * TILE_N;
-          uint32_t accum = 0;
-          for (int pass = 0; pass < npass; ++pass) {
-            const uint32_t a0 = (pass == 2) ? a_lo : a_hi;
-            // B: MN-major SW128, K row = 128 B, 8-row groups 1 KB apart; 16 K rows (2 KB) per step
-            const uint64_t bd0 = make_desc(b_hi + ((pass == 1) ? B_TILE_BYTES : 0), B_TILE_BYTES, 1024);
+      for (int sg = 0; sg < jr.nseg; ++sg) {
+        for (int t = jr.t0[sg]; t < jr.t1[sg]; ++t) {
+          const bool job_ends = (sg + 1 == jr.nseg) && (t + 1 == jr.t1[sg]);
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1, p.status, 3);
+          mbar_wait(&full[stage], phase, p.status, 4);
+          tcgen05_fence_after();
+          if (lane == 0) stamp(p, 1, tcount, 0);
+          if (elect_one()) {
+            const uint32_t b_hi = smem_u32(sB + stage * STAGE_BYTES);
+            const uint32_t d = TM_ACC + acc * TILE_N;
+            uint32_t accum = 0;
+            for (int pass = 0; pass < npass; ++pass) {
+              const uint32_t a0 = (pass == 2) ? a_lo : a_hi;
+              // B: MN-major SW128, K row = 128 B, 8-row groups 1 KB apart; 16 K rows (2 KB) per step
+              const uint64_t bd0 = make_desc(b_hi + ((pass == 1) ? B_TILE_BYTES : 0), B_TILE_BYTES, 1024);
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              umma_bf16_ts(d, a0 + k * 8, bd0 + (uint64_t)(k * (2048 >> 4)), idesc, accum);
-              accum = 1;
+              for (int k = 0; k < KC / 16; ++k) {
+                umma_bf16_ts(d, a0 + k * 8, bd0 + (uint64_t)(k * (2048 >> 4)), IDESC, accum);
+                accum = 1;
+              }
             }
+            tcgen05_commit(&empty[stage]);    // B stage free once these MMAs retire
+            tcgen05_commit(&acc_full[acc]);   // accumulator ready
+            if (job_ends) tcgen05_commit(&a_empty[abuf]);  // target tile buffer free
+            stamp(p, 1, tcount, 1);
           }
-          tcgen05_commit(&empty[stage]);    // B stage free once these MMAs retire
-          tcgen05_commit(&acc_full[acc]);   // accumulator ready
-          if (t + 1 == t1) tcgen05_commit(&a_empty[abuf]);  // target tile buffer free
-          stamp(p, 1, tcount, 1);
+          ++tcount;
+          __syncwarp();
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
         }
-        ++tcount;
-        __syncwarp();
-        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < 6) {
     // ===================== epilogue warps (2..5) =====================
     const int wq = warp & 3;                    // TMEM lane quarter this warp may access
-    const int q = 32 * wq + lane;               // TMEM lane == query slot in the tile
+    const int q = 32 * wq + lane;               // TMEM lane == sorted query slot in the tile
     float* myrow = dump + q * DUMP_STRIDE;
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
     const int Wr = 2 * p.r + 1;
@@ -329,84 +507,46 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     int tcount = 0;
     float* mywin = win;
 
-    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
-      int bs, chunk, mt, t0, t1;
-      job_decode(p, job, bs, chunk, mt);
-      chunk_tiles(p, chunk, t0, t1);
+    for (int job = seek_job(p, blockIdx.x); job < p.njobs; job = seek_job(p, job + gridDim.x)) {
+      const JobRec jr = load_job(p.jobs + job);
+      const int bs = jr.bs;
       const int b = bs / p.S, s = bs - b * p.S;
-      const int m0 = mt * TILE_M;
-      const int n = m0 + q;
-      const bool valid = n < p.N;
+      const int n = __ldg(p.perm + (long long)bs * p.npad + jr.mt * TILE_M + q);
+      const bool valid = n >= 0;
       float cx = 0.f, cy = 0.f;
       if (valid && p.coords) {
-        const float* cp = p.coords + b * p.c_sb + s * p.c_ss + n * p.c_sn;
+        const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)n * p.c_sn;
         cx = __ldg(cp);
         cy = __ldg(cp + 1);
       }
 
-      int cur_level = -1;
-      int x0 = 0, y0 = 0, ta = 0, tb_ = 0, Hl = 0;
-      float fx = 0.f, fy = 0.f;
-      float hprev[MAX_WR];
-
-      for (int t = t0; t < t1; ++t) {
-        const TileInfo ti = tile_info(t);
-        // ---- accumulator -> registers ----
-        mbar_wait(&acc_full[acc], acc_phase, p.status, 5);
-        if (warp == 2 && lane == 0) stamp(p, 2, tcount, 0);
-        tcgen05_fence_after();
-        float v[64];
-        tmem_ld32(lane_addr + TM_ACC + acc * TILE_N, v);
-        tmem_ld32(lane_addr + TM_ACC + acc * TILE_N + 32, v + 32);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        if (warp == 2 && lane == 0) stamp(p, 2, tcount, 1);
-        ++tcount;
-        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
-
-        if (p.bf16) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = round_bf16(round_bf16(v[i]) * p.inv_sqrt_c);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] *= p.inv_sqrt_c;
-        }
-
-        if (p.volume_mode) {
-          if (valid) {
-            const int cols = ti.level == 4 ? 16 : 64;
-            const int HW = ti.W * ti.W;
-            float* dst = p.vol[ti.level] + ((long long)bs * p.N + n) * HW + (t * TILE_N - level_offset(ti.level));
-#pragma unroll
-            for (int i = 0; i < 64; i += 4)
-              if (i < cols) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          }
-          continue;
-        }
-        if (p.debug & 1) continue;
-
-        // private smem row: the window columns are indexed dynamically (x0 differs per query)
-#pragma unroll
-        for (int i = 0; i < 64; i += 4)
-          *reinterpret_cast<float4*>(myrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-
-        if (ti.level != cur_level) {
-          // ---- new pyramid level: window geometry; claim a window buffer and clear it (rows off the map stay 0) ----
-          cur_level = ti.level;
-          Hl = ti.H;
-          const float inv = 1.f / (float)(1 << ti.level);
+      for (int sg = 0; sg < jr.nseg; ++sg) {
+        const int tfirst = jr.t0[sg], tend = jr.t1[sg];
+        const TileInfo t0i = tile_info(tfirst);
+        const int level = t0i.level, Hl = t0i.H, Wl = t0i.W;
+        // ---- window geometry of this query at this level; row band of the whole warp ----
+        int x0, y0;
+        float fx, fy;
+        level_y(cy, level, p.r, y0, fy);
+        {
+          const float inv = 1.f / (float)(1 << level);
           const float px = fminf(fmaxf(cx * inv, -1.0e6f), 1.0e6f);
-          const float py = fminf(fmaxf(cy * inv, -1.0e6f), 1.0e6f);
-          const float flx = floorf(px), fly = floorf(py);
-          fx = px - flx; fy = py - fly;
-          x0 = (int)flx - p.r; y0 = (int)fly - p.r;
-          // tops handled while streaming: [ta, tb_]
-          ta = (ti.level == 0 && chunk > 0) ? 16 * chunk : -1;
-          tb_ = (ti.level == 0 && chunk < 3) ? 16 * chunk + 15 : Hl - 2;
+          const float flx = floorf(px);
+          fx = px - flx;
+          x0 = (int)flx - p.r;
+        }
+        int rl = max(y0, 0), rh = min(y0 + Wr, Hl - 1);   // map rows this query touches
+        if (!valid || rl > rh) { rl = BIG; rh = -BIG; }
+        const int wlo = __reduce_min_sync(0xffffffffu, rl), whi = __reduce_max_sync(0xffffffffu, rh);
+        const bool is0 = level == 0;
+        // window rows ("tops") written while streaming: [ta, tb_]; top = H-1 is finished at the end of the level
+        const int ta = is0 ? jr.own_lo : -BIG;
+        const int tb_ = is0 ? min(jr.own_hi, Hl - 2) : Hl - 2;
+        float hprev[MAX_WR];
 #pragma unroll
-          for (int i = 0; i < MAX_WR; ++i) hprev[i] = 0.f;
+        for (int i = 0; i < MAX_WR; ++i) hprev[i] = 0.f;
+        if (!p.volume_mode && !(p.debug & 1)) {
+          // claim a window buffer and clear it (entries whose rows are off the map stay 0)
           const uint32_t wbuf = wu % NWIN;
           mbar_wait(&win_empty[wbuf * 4 + wq], ((wu / NWIN) & 1) ^ 1, p.status, 7);
           mywin = win + (wbuf * TILE_M + q) * WIN_STRIDE;
@@ -414,42 +554,106 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           for (int i = 0; i < WIN_STRIDE; i += 4) *reinterpret_cast<float4*>(mywin + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
 
-        // ---- stream the map rows of this tile ----
-        for (int rr = 0; rr < ti.rows; ++rr) {
-          const int y = ti.y_first + rr;
-          float h[MAX_WR];
-          const bool needed = valid && y >= y0 && y <= y0 + Wr;
-          if (needed) {
-            const float* row = myrow + rr * ti.W;
-            float vv[MAX_WR + 1];
+        for (int t = tfirst; t < tend; ++t) {
+          const TileInfo ti = tile_info(t);
+          const int ylast = ti.y_first + ti.rows - 1;
+          // does any query of this warp touch the rows of this tile?  (warp-uniform)
+          const bool wneed = p.volume_mode || ((ti.y_first <= whi && ylast >= wlo) && !(p.debug & 32));
+          mbar_wait(&acc_full[acc], acc_phase, p.status, 5);
+          if (warp == 2 && lane == 0) stamp(p, 2, tcount, 0);
+          float v[64];
+          if (wneed) {
+            tcgen05_fence_after();
+            tmem_ld32(lane_addr + TM_ACC + acc * TILE_N, v);
+            tmem_ld32(lane_addr + TM_ACC + acc * TILE_N + 32, v + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          if (warp == 2 && lane == 0) stamp(p, 2, tcount, 1);
+          ++tcount;
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+
+          if (p.volume_mode) {
+            if (valid) {
+              const int cols = ti.level == 4 ? 16 : 64;
+              const int HW = ti.W * ti.W;
+              float* dst = p.vol[ti.level] + ((long long)bs * p.N + n) * HW + (t * TILE_N - level_offset(ti.level));
 #pragma unroll
-            for (int i = 0; i <= MAX_WR; ++i) {
-              const int xi = x0 + i;
-              vv[i] = (i <= Wr && xi >= 0 && xi < ti.W) ? row[xi] : 0.f;
+              for (int i = 0; i < 64; i += 4) {
+                if (i < cols) {
+                  float4 o;
+                  if (p.bf16) {
+                    o = make_float4(round_bf16(round_bf16(v[i]) * p.inv_sqrt_c), round_bf16(round_bf16(v[i + 1]) * p.inv_sqrt_c),
+                                    round_bf16(round_bf16(v[i + 2]) * p.inv_sqrt_c), round_bf16(round_bf16(v[i + 3]) * p.inv_sqrt_c));
+                  } else {
+                    o = make_float4(v[i] * p.inv_sqrt_c, v[i + 1] * p.inv_sqrt_c, v[i + 2] * p.inv_sqrt_c, v[i + 3] * p.inv_sqrt_c);
+                  }
+                  *reinterpret_cast<float4*>(dst + i) = o;
+                }
+              }
             }
-#pragma unroll
-            for (int i = 0; i < MAX_WR; ++i) h[i] = (1.f - fx) * vv[i] + fx * vv[i + 1];
-          } else {
-#pragma unroll
-            for (int i = 0; i < MAX_WR; ++i) h[i] = 0.f;
+            continue;
           }
-          const int top = y - 1, j = top - y0;
-          if (valid && j >= 0 && j < Wr && top >= ta && top <= tb_) {
+          if (p.debug & 1) continue;
+
+          if (wneed) {
+            // private smem row: the window columns are indexed dynamically (x0 differs per query); only the queries
+            // that touch this tile park their row, and at level 0 only the 16-byte groups under their x window
+            const bool lneed = ti.y_first <= rh && ylast >= rl;
+            if (lneed) {
+              if (is0) {
 #pragma unroll
-            for (int i = 0; i < MAX_WR; ++i)
-              if (i < Wr) mywin[i * Wr + j] = (1.f - fy) * hprev[i] + fy * h[i];
+                for (int i = 0; i < 64; i += 4)
+                  if (i + 3 >= x0 && i <= x0 + Wr)
+                    *reinterpret_cast<float4*>(myrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 64; i += 4)
+                  *reinterpret_cast<float4*>(myrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              }
+            }
+            // ---- stream the map rows of this tile ----
+            for (int rr = 0; rr < ti.rows; ++rr) {
+              const int y = ti.y_first + rr;
+              float h[MAX_WR];
+              const bool needed = y >= rl && y <= rh;
+              if (needed) {
+                const float* row = myrow + rr * Wl;
+                float vv[MAX_WR + 1];
+#pragma unroll
+                for (int i = 0; i <= MAX_WR; ++i) {
+                  const int xi = x0 + i;
+                  float c = (i <= Wr && xi >= 0 && xi < Wl) ? row[xi] : 0.f;
+                  // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
+                  vv[i] = p.bf16 ? round_bf16(round_bf16(c) * p.inv_sqrt_c) : c * p.inv_sqrt_c;
+                }
+#pragma unroll
+                for (int i = 0; i < MAX_WR; ++i) h[i] = (1.f - fx) * vv[i] + fx * vv[i + 1];
+              } else {
+#pragma unroll
+                for (int i = 0; i < MAX_WR; ++i) h[i] = 0.f;
+              }
+              const int top = y - 1, j = top - y0;
+              if (valid && j >= 0 && j < Wr && top >= ta && top <= tb_) {
+#pragma unroll
+                for (int i = 0; i < MAX_WR; ++i)
+                  if (i < Wr) mywin[i * Wr + j] = (1.f - fy) * hprev[i] + fy * h[i];
+              }
+#pragma unroll
+              for (int i = 0; i < MAX_WR; ++i) hprev[i] = h[i];
+            }
           }
-#pragma unroll
-          for (int i = 0; i < MAX_WR; ++i) hprev[i] = h[i];
         }
 
-        // ---- end of a level inside this job: finish the window and hand it to the stager warp ----
-        const bool level_ends = (t + 1 == t1) || (tile_info(t + 1).level != ti.level);
-        if (level_ends) {
-          const bool last = ti.level > 0 || chunk == 3;
-          const bool first = ti.level > 0 || chunk == 0;
+        if (p.volume_mode || (p.debug & 1)) continue;
+        // ---- end of the level inside this job: finish the window and hand it to the stager warp ----
+        {
+          const bool last = !is0 || (jr.flags & JF_LAST0);
           if (last && valid) {
-            const int jb = (Hl - 1) - y0;  // top = H-1: its bottom row is off the map
+            const int jb = (Hl - 1) - y0;  // top = H-1: its bottom row is off the map (hprev is row H-1: jb in range
+                                           // means this query touches row H-1, so its warp streamed up to it)
             if (jb >= 0 && jb < Wr) {
 #pragma unroll
               for (int i = 0; i < MAX_WR; ++i)
@@ -457,8 +661,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             }
           }
           // window rows (index j) this job owns: tops in [lo_top, hi_top]
-          const int lo_top = first ? -(1 << 28) : 16 * chunk;
-          const int hi_top = last ? (1 << 28) : 16 * chunk + 15;
+          const int lo_top = is0 ? jr.own_lo : -BIG;
+          const int hi_top = is0 ? jr.own_hi : BIG;
           const int j_lo = valid ? max(0, lo_top - y0) : 1, j_hi = valid ? min(Wr - 1, hi_top - y0) : 0;
           mywin[81] = __int_as_float(j_lo);
           mywin[82] = __int_as_float(j_hi);
@@ -471,7 +675,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   } else {
     // ===================== stager warps (6..9): every global load/store except the TMA =====================
     // per job:  (1) stage the NEXT job's 128 target rows into the free TMEM A buffer (hi/lo split, tcgen05.st);
-    //           (2) chunk-3 jobs own the (query, frame) pair: write the non-correlation part of the token;
+    //           (2) the last level-0 job of a (frame, query tile) writes the non-correlation part of the tokens;
     //           (3) for every window unit the epilogue warp of the same lane quarter hands over: add the position
     //               embedding and store the window rows this job owns, coalesced, with all loads of 16 queries in
     //               flight before the first store.
@@ -482,17 +686,16 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     uint32_t wu = 0;
 
     auto stage_targets = [&](int job, uint32_t ji) {
-      int bs, chunk, mt;
-      job_decode(p, job, bs, chunk, mt);
+      const int bs = __ldg(&p.jobs[job].bs), mt = __ldg(&p.jobs[job].mt);
       const int b = bs / p.S, s = bs - b * p.S;
-      const int m0 = mt * TILE_M;
       const uint32_t abuf = ji & 1;
       mbar_wait(&a_empty[abuf], ((ji >> 1) & 1) ^ 1, p.status, 6);
       tcgen05_fence_after();
       if (!(p.debug & 256)) {
-        const bool rv = m0 + q < p.N;
+        const int nq = __ldg(p.perm + (long long)bs * p.npad + mt * TILE_M + q);
+        const bool rv = nq >= 0;
         const float4* src = reinterpret_cast<const float4*>(p.targets + b * p.t_sb + s * p.t_ss +
-                                                            (long long)(m0 + q) * p.t_sn);
+                                                            (long long)(rv ? nq : 0) * p.t_sn);
         const uint32_t ta_hi = lane_addr + TM_A + abuf * 128, ta_lo = ta_hi + 64;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {  // 64 channels per step: 16 LDG.128 in flight
@@ -520,117 +723,72 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       mbar_arrive(&a_full[abuf]);
     };
 
-    if ((int)blockIdx.x < p.njobs) stage_targets(blockIdx.x, 0);
+    int job = seek_job(p, blockIdx.x);
+    if (job < p.njobs) stage_targets(job, 0);
     uint32_t ji = 0;
-    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
+    for (; job < p.njobs; ++ji) {
+      const int next = seek_job(p, job + gridDim.x);
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 0);
-      if (job + (int)gridDim.x < p.njobs) stage_targets(job + gridDim.x, ji + 1);
+      if (next < p.njobs) stage_targets(next, ji + 1);
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 1);
-      int bs, chunk, mt;
-      job_decode(p, job, bs, chunk, mt);
+      const JobRec jr = load_job(p.jobs + job);
+      job = next;
+      const int bs = jr.bs;
       const int b = bs / p.S, s = bs - b * p.S;
-      const int m0 = mt * TILE_M;
+      const int myn = __ldg(p.perm + (long long)bs * p.npad + jr.mt * TILE_M + q);  // query of sorted slot q
 
-      if (p.tokens && !p.volume_mode && chunk == 3 && !(p.debug & 4)) {
-        // [ sin/cos(flow * div) (C) | flow (2) | .. fcorrs .. | track_feats (C) | zero pad ] + pos_emb
-        float fxq = 0.f, fyq = 0.f;
-        if (m0 + q < p.N) {
-          const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)(m0 + q) * p.c_sn;
-          const float* c0 = p.coords + b * p.c_sb + (long long)(m0 + q) * p.c_sn;  // frame 0
-          fxq = __ldg(cp) - __ldg(c0);
-          fyq = __ldg(cp + 1) - __ldg(c0 + 1);
-        }
-        const int Ce = KC >> 1;
-        const float step = 1000.0f / (float)Ce;
-        const int feat_off = KC + 2 + p.L * WW;
-        const int ntail = p.D_tok - feat_off;  // track_feats + pad
-        for (int q4 = 0; q4 < 32; q4 += 4) {
-          if (m0 + 32 * wq + q4 >= p.N) break;
-          float pe[4][4], pt[4][5], tf[4][4], pf[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {  // all loads of four queries first
-            const int nn = m0 + 32 * wq + q4 + u;
-            const bool qv = nn < p.N;
-            const float* pq = p.pos + ((long long)b * p.N + (qv ? nn : 0)) * p.D_tok;
-            const float* tq = p.targets + b * p.t_sb + s * p.t_ss + (long long)(qv ? nn : 0) * p.t_sn;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) pe[u][k] = __ldg(pq + lane + 32 * k);
-            pf[u] = (lane < 2) ? __ldg(pq + KC + lane) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) pt[u][k] = (lane + 32 * k < ntail) ? __ldg(pq + feat_off + lane + 32 * k) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tf[u][k] = __ldg(tq + lane + 32 * k);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int nn = m0 + 32 * wq + q4 + u;
-            const float flx = __shfl_sync(0xffffffffu, fxq, q4 + u), fly = __shfl_sync(0xffffffffu, fyq, q4 + u);
-            if (nn >= p.N) continue;
-            float* o = p.out + (((long long)b * p.N + nn) * p.S + s) * p.D_tok;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int e = lane + 32 * k;
-              const int axis = e / Ce, w = e - axis * Ce;
-              const float arg = __fmul_rn(axis ? fly : flx, (float)(w & ~1) * step);
-              o[e] = ((w & 1) ? cosf(arg) : sinf(arg)) + pe[u][k];
-            }
-            if (lane < 2) o[KC + lane] = (lane ? fly : flx) + pf[u];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-              const int c = lane + 32 * k;
-              if (c < ntail) o[feat_off + c] = (c < KC ? tf[u][k & 3] : 0.f) + pt[u][k];
-            }
-            const float* pq = p.pos + ((long long)b * p.N + nn) * p.D_tok;
-            for (int c = 160 + lane; c < ntail; c += 32) o[feat_off + c] = __ldg(pq + feat_off + c);  // wide pads
-          }
-        }
+      // element offsets of this lane's query rows (pos_emb row, output row), shared with the warp through smem:
+      // the store loop below then needs one broadcast LDS.64 per row instead of shuffles + 64-bit index math.
+      // Padding slots point at row 0 and own no window rows (j_lo > j_hi), so they are never stored.
+      {
+        const long long nq = myn >= 0 ? myn : 0;
+        __syncwarp();
+        rowoff[q] = ((long long)b * p.N + nq) * p.D_tok;
+        rowoff[TILE_M + q] = p.tokens ? (((long long)b * p.N + nq) * p.S + s) * p.D_tok
+                                      : b * p.o_sb + s * p.o_ss + nq * p.o_sn;
+        __syncwarp();
       }
-
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 1, 0);
       if (p.volume_mode || (p.debug & 1)) continue;
-      // window units of this job: level 0 for the row chunks, levels 1..L-1 for the pyramid chunk
-      const int l0 = chunk < 4 ? 0 : 1, l1 = chunk < 4 ? 1 : p.L;
-      for (int lvl = l0; lvl < l1; ++lvl, ++wu) {
+      const int nvalid = min(32, p.N - (jr.mt * TILE_M + 32 * wq));   // sorted slots: valid first, padding last
+      // window units of this job: one per tile run (= one pyramid level)
+      for (int sg = 0; sg < jr.nseg; ++sg, ++wu) {
+        const int lvl = tile_info(jr.t0[sg]).level;
         const uint32_t wbuf = wu % NWIN;
         mbar_wait(&win_full[wbuf * 4 + wq], (wu / NWIN) & 1, p.status, 8);
         if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 0);
         const float* wrows = win + (wbuf * TILE_M + 32 * wq) * WIN_STRIDE;
         const int lvl_off = (p.tokens ? KC + 2 : 0) + lvl * WW;
-        const int dcl[3] = {min(lane, WW - 1), min(lane + 32, WW - 1), min(lane + 64, WW - 1)};
-        const int jjs[3] = {lane % Wr, (lane + 32) % Wr, (lane + 64) % Wr};
-        const bool dok[3] = {lane < WW, lane + 32 < WW, lane + 64 < WW};
+        const int jj0 = lane % Wr, jj1 = (lane + 32) % Wr, jj2 = (lane + 64) % Wr;
+        const bool ok1 = lane + 32 < WW, ok2 = lane + 64 < WW;   // lane < WW always (WW >= 1 ... 81; lane 0..31 may exceed for r=0..2)
+        const bool ok0 = lane < WW;
+        const float* pbase = p.pos + lvl_off + min(lane, WW - 1);
+        const int d1 = min(lane + 32, WW - 1) - min(lane, WW - 1), d2 = min(lane + 64, WW - 1) - min(lane, WW - 1);
+        float* obase = p.out + lvl_off + lane;
 #pragma unroll 1
         for (int q16 = 0; q16 < 32; q16 += 16) {
-          if (m0 + 32 * wq + q16 >= p.N) break;
-          // branch-free, unconditional loads (clamped addresses) into their own registers: nothing consumes them
-          // until all 48 are in flight
+          if (q16 >= nvalid || (p.debug & 2)) break;
+          // unconditional loads (clamped addresses) into their own registers: all 48 in flight before the first store
           float val[16][3];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int nn = min(m0 + 32 * wq + q16 + u, p.N - 1);
-            if (p.tokens) {
-              const float* pq = p.pos + ((long long)b * p.N + nn) * p.D_tok + lvl_off;
-#pragma unroll
-              for (int k = 0; k < 3; ++k) val[u][k] = __ldg(pq + dcl[k]);
+            if (p.tokens && !(p.debug & 16)) {
+              const float* pq = pbase + rowoff[32 * wq + q16 + u];
+              val[u][0] = __ldg(pq);
+              val[u][1] = __ldg(pq + d1);
+              val[u][2] = __ldg(pq + d2);
             } else {
-#pragma unroll
-              for (int k = 0; k < 3; ++k) val[u][k] = 0.f;
+              val[u][0] = 0.f; val[u][1] = 0.f; val[u][2] = 0.f;
             }
           }
-          const long long row_stride = p.tokens ? (long long)p.S * p.D_tok : p.o_sn;
-          float* dst = (p.tokens ? p.out + (((long long)b * p.N + m0 + 32 * wq + q16) * p.S + s) * p.D_tok
-                                 : p.out + b * p.o_sb + s * p.o_ss + (long long)(m0 + 32 * wq + q16) * p.o_sn) + lvl_off;
           const float* wsrc = wrows + q16 * WIN_STRIDE;
-          const int nq = min(16, p.N - (m0 + 32 * wq + q16));
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            if (u < nq) {
-              const int jl = __float_as_int(wsrc[81]), jh = __float_as_int(wsrc[82]);
-#pragma unroll
-              for (int k = 0; k < 3; ++k)
-                if (dok[k] && jjs[k] >= jl && jjs[k] <= jh) dst[lane + 32 * k] = wsrc[lane + 32 * k] + val[u][k];
-            }
-            dst += row_stride;
+            float* dst = obase + rowoff[TILE_M + 32 * wq + q16 + u];
+            const int jl = __float_as_int(wsrc[81]), jh = __float_as_int(wsrc[82]);
+            if (ok0 && jj0 >= jl && jj0 <= jh) dst[0] = wsrc[lane] + val[u][0];
+            if (ok1 && jj1 >= jl && jj1 <= jh) dst[32] = wsrc[lane + 32] + val[u][1];
+            if (ok2 && jj2 >= jl && jj2 <= jh) dst[64] = wsrc[lane + 64] + val[u][2];
             wsrc += WIN_STRIDE;
           }
         }
@@ -735,13 +893,34 @@ static int* status_word() {
   return d;
 }
 
-static int launch(Params& p, const void* split, cudaStream_t stream) {
+// Work decomposition chosen on the host: `nsplit` level-0 row chunks + `npyr` pyramid jobs per (frame, query tile),
+// enough jobs for ~4 per SM (COMET_TC_NSPLIT / COMET_TC_NPYR override, for experiments).
+static void choose_split(int BS, int mtiles, int L, int sms, int& nsplit, int& npyr) {
+  const long long base = (long long)BS * mtiles;
+  npyr = L == 1 ? 0 : (L >= 3 && base * 3 < 4LL * sms) ? 2 : 1;
+  long long want = (4LL * sms + base - 1) / (base > 0 ? base : 1) - npyr;
+  nsplit = (int)(want < 1 ? 1 : want > MAX_SPLIT ? MAX_SPLIT : want);
+  static int env_split = -1, env_pyr = -1;
+  if (env_split < 0) { const char* e = getenv("COMET_TC_NSPLIT"); env_split = e ? atoi(e) : 0; }
+  if (env_pyr < 0) { const char* e = getenv("COMET_TC_NPYR"); env_pyr = e ? atoi(e) : 0; }
+  if (env_split >= 1 && env_split <= MAX_SPLIT) nsplit = env_split;
+  if (env_pyr >= 1 && env_pyr <= 2 && L > 1) npyr = (env_pyr == 2 && L < 3) ? 1 : env_pyr;
+}
+
+static long long workspace_bytes(int BS, int N) {
+  const long long mtiles = (N + TILE_M - 1) / TILE_M;
+  return (long long)BS * mtiles * TILE_M * 4 + (long long)BS * mtiles * MAX_CHUNK * (long long)sizeof(JobRec) + 64;
+}
+
+static int launch(Params& p, const void* split, void* workspace, cudaStream_t stream) {
   const int sms = device_is_sm100();
   if (!sms) return fail(COMET_ERR_UNSUPPORTED, "tensor path needs an sm_100 device and cuTensorMapEncodeTiled");
+  COMET_REQUIRE(workspace && ((uintptr_t)workspace % 16) == 0, "workspace must be a 16-byte aligned device buffer");
   p.BS = p.B * p.S;
   p.mtiles = (p.N + TILE_M - 1) / TILE_M;
-  p.nchunk = p.L > 1 ? 5 : 4;
-  p.ntiles = num_tiles(p.L);
+  p.npad = p.mtiles * TILE_M;
+  choose_split(p.BS, p.mtiles, p.L, sms, p.nsplit, p.npyr);
+  p.nchunk = p.nsplit + p.npyr;
   const long long njobs = (long long)p.BS * p.nchunk * p.mtiles;
   if (njobs == 0) return COMET_OK;
   if (njobs > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many jobs");
@@ -754,6 +933,11 @@ static int launch(Params& p, const void* split, cudaStream_t stream) {
     p.debug = dbg;
   }
   p.stamps = g_stamps;
+  // workspace: [jobs: BS*mtiles*MAX_CHUNK records][perm: BS*npad ints]
+  JobRec* jobs = reinterpret_cast<JobRec*>(workspace);
+  int* perm = reinterpret_cast<int*>(jobs + (long long)p.BS * p.mtiles * MAX_CHUNK);
+  p.jobs = jobs;
+  p.perm = perm;
 
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)P_TOTAL, (cuuint64_t)2 * p.BS * KC};
@@ -770,6 +954,16 @@ static int launch(Params& p, const void* split, cudaStream_t stream) {
     COMET_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
+  const int full = (p.volume_mode || (p.debug & 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
+  // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
+  long long misc = 0;
+  if (p.tokens) {
+    misc = ((long long)p.B * p.N * p.S + 7) / 8;
+    if (misc > 64LL * sms) misc = 64LL * sms;
+  }
+  tc_pre_kernel<<<(unsigned)(p.BS + misc), 256, 0, stream>>>(p, perm, jobs, full);
+  int rc = launch_status("tc_pre_kernel");
+  if (rc != COMET_OK) return rc;
   const int grid = (int)(njobs < sms ? njobs : sms);
   corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);
   return launch_status("corr_tc_kernel");
@@ -796,6 +990,11 @@ extern "C" int comet_tc_supported(int C, int H, int W, int L, int r, int pad_mod
 }
 
 extern "C" long long comet_tc_split_elems(int BS) { return 2LL * BS * tc::KC * tc::P_TOTAL; }
+
+extern "C" long long comet_tc_workspace_bytes(int BS, int N) {
+  if (BS < 0 || N < 0) return -1;
+  return tc::workspace_bytes(BS, N);
+}
 
 extern "C" int comet_tc_prepare_f32(const float* fmaps, void* split, float* pyr, int BS, int C, int H, int W, int L,
                                     comet_stream_t stream) {
@@ -830,21 +1029,21 @@ extern "C" int comet_tc_corr_lookup_f32(const void* split, const float* targets,
                                         long long t_sn, const float* coords, long long c_sb, long long c_ss,
                                         long long c_sn, float* out, long long o_sb, long long o_ss, long long o_sn,
                                         int B, int S, int N, int C, int H, int W, int L, int r, int pad_mode,
-                                        int prec_mode, comet_stream_t stream) {
+                                        int prec_mode, void* workspace, comet_stream_t stream) {
   tc::Params p{};
   int rc = tc_common(p, targets, t_sb, t_ss, t_sn, coords, c_sb, c_ss, c_sn, B, S, N, C, H, W, L, r, pad_mode, prec_mode);
   if (rc != COMET_OK) return rc;
   if ((long long)B * S * N == 0) return COMET_OK;
   COMET_REQUIRE(split && targets && coords && out, "null pointer");
   p.out = out; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sn = o_sn;
-  return tc::launch(p, split, (cudaStream_t)stream);
+  return tc::launch(p, split, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int comet_tc_track_tokens_f32(const void* split, const float* track_feats, long long t_sb, long long t_ss,
                                          long long t_sn, const float* coords, long long c_sb, long long c_ss,
                                          long long c_sn, const float* pos_emb, float* tokens, int B, int S, int N,
                                          int C, int H, int W, int L, int r, int pad_mode, int prec_mode, int D_tok,
-                                         comet_stream_t stream) {
+                                         void* workspace, comet_stream_t stream) {
   tc::Params p{};
   int rc = tc_common(p, track_feats, t_sb, t_ss, t_sn, coords, c_sb, c_ss, c_sn, B, S, N, C, H, W, L, r, pad_mode,
                      prec_mode);
@@ -854,12 +1053,12 @@ extern "C" int comet_tc_track_tokens_f32(const void* split, const float* track_f
   if ((long long)B * S * N == 0) return COMET_OK;
   COMET_REQUIRE(split && track_feats && coords && pos_emb && tokens, "null pointer");
   p.out = tokens; p.pos = pos_emb; p.D_tok = D_tok; p.tokens = 1;
-  return tc::launch(p, split, (cudaStream_t)stream);
+  return tc::launch(p, split, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int comet_tc_corr_volume_f32(const void* split, const float* targets, long long t_sb, long long t_ss,
                                         long long t_sn, float* const* vols, int B, int S, int N, int C, int H, int W,
-                                        int L, int prec_mode, comet_stream_t stream) {
+                                        int L, int prec_mode, void* workspace, comet_stream_t stream) {
   tc::Params p{};
   int rc = tc_common(p, targets, t_sb, t_ss, t_sn, nullptr, 0, 0, 0, B, S, N, C, H, W, L, 0, COMET_PAD_ZEROS, prec_mode);
   if (rc != COMET_OK) return rc;
@@ -870,7 +1069,7 @@ extern "C" int comet_tc_corr_volume_f32(const void* split, const float* targets,
     p.vol[l] = vols[l];
   }
   p.volume_mode = 1;
-  return tc::launch(p, split, (cudaStream_t)stream);
+  return tc::launch(p, split, workspace, (cudaStream_t)stream);
 }
 
 extern "C" void comet_tc_debug_stamps(long long* dev_buf) { comet::tc::g_stamps = dev_buf; }

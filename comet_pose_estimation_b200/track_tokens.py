@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._dev import inner_contig, pad_mode, prec_mode, require_cuda, stream_ptr
-from .blocks import CorrBlock, EfficientCorrBlock, _Pyramid, _use_tc
+from .blocks import CorrBlock, EfficientCorrBlock, _Pyramid, _tc_workspace, _use_tc
 
 lib = _lib.lib
 
@@ -85,7 +85,7 @@ class TrackTokenizer:
                     c.data_ptr(), c.stride(0), c.stride(1), c.stride(2),
                     self.pos.data_ptr(), out.data_ptr(),
                     B, S, N, p.C, p.H, p.W, p.num_levels, self.radius, pad_mode(self.padding_mode), prec_mode(),
-                    self.tdim, stream_ptr(c.device)))
+                    self.tdim, _tc_workspace(p, N).data_ptr(), stream_ptr(c.device)))
                 return out
             _lib.check(lib.comet_track_tokens_f32(
                 p.fmaps0.data_ptr(), p.pyr.data_ptr(),

@@ -57,10 +57,6 @@ const char* comet_last_error(void);
 int comet_has_tensor_path(void);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */
 long long comet_launch_count(void);
-/* Device tuning hint: cudaLimitMaxL2FetchGranularity (32/64/128 bytes; 0 = only query).  The window gathers of the
- * fine tracker touch 32-byte row segments, so a smaller fetch granularity cuts DRAM over-fetch.  Returns the value
- * in effect, or -1 if there is no device. */
-int comet_set_l2_fetch_granularity(int bytes);
 
 /* ---- feature pyramid: CorrBlock.__init__ / EfficientCorrBlock.__init__,
  *      comet/models/track_modules/blocks.py:352-374 and :433-444 ------------
@@ -141,23 +137,28 @@ int comet_sincos2d_f32(float* out, int D, int H, int W, comet_stream_t stream);
  * C=128, H=W=64, L<=5, r<=4, zero padding; float32 parity through a bf16 hi/lo split (3 MMA passes), or the
  * autocast rounding with one pass.  `split` is the packed bf16 pyramid written by comet_tc_prepare_f32
  * (comet_tc_split_elems(BS) bf16 elements); `pyr` (optional, may be NULL) additionally receives the float32 levels
- * 1..L-1 in the comet_pyramid_f32 layout. */
+ * 1..L-1 in the comet_pyramid_f32 layout.
+ * `workspace`: comet_tc_workspace_bytes(B*S, N) bytes of 16-byte aligned device scratch, rewritten by every call: the
+ * queries of each frame are counting-sorted by floor(y) so that the 128 queries of an MMA tile share a narrow band
+ * of map rows, and the per-tile job list (which feature tiles each band needs) lives there too.  Results do not
+ * depend on the order (every query writes its own output row). */
 int comet_tc_supported(int C, int H, int W, int L, int r, int pad_mode);
 long long comet_tc_split_elems(int BS);
+long long comet_tc_workspace_bytes(int BS, int N);
 int comet_tc_prepare_f32(const float* fmaps, void* split, float* pyr, int BS, int C, int H, int W, int L,
                          comet_stream_t stream);
 int comet_tc_corr_lookup_f32(const void* split, const float* targets, long long t_sb, long long t_ss, long long t_sn,
                              const float* coords, long long c_sb, long long c_ss, long long c_sn, float* out,
                              long long o_sb, long long o_ss, long long o_sn, int B, int S, int N, int C, int H, int W,
-                             int L, int r, int pad_mode, int prec_mode, comet_stream_t stream);
+                             int L, int r, int pad_mode, int prec_mode, void* workspace, comet_stream_t stream);
 int comet_tc_track_tokens_f32(const void* split, const float* track_feats, long long t_sb, long long t_ss,
                               long long t_sn, const float* coords, long long c_sb, long long c_ss, long long c_sn,
                               const float* pos_emb, float* tokens, int B, int S, int N, int C, int H, int W, int L,
-                              int r, int pad_mode, int prec_mode, int D_tok, comet_stream_t stream);
+                              int r, int pad_mode, int prec_mode, int D_tok, void* workspace, comet_stream_t stream);
 /* vols: HOST array of L device pointers, level l = (B*S, N, H_l*W_l) float32. */
 int comet_tc_corr_volume_f32(const void* split, const float* targets, long long t_sb, long long t_ss, long long t_sn,
                              float* const* vols, int B, int S, int N, int C, int H, int W, int L, int prec_mode,
-                             comet_stream_t stream);
+                             void* workspace, comet_stream_t stream);
 /* 0 = healthy; non-zero = a pipeline watchdog fired inside the tensor kernel (debug aid). Synchronises. */
 int comet_tc_status(void);
 /* debug aid: device buffer of 4*64*2 int64 receiving a clock64 trace of CTA 0 (NULL = off). */

@@ -11,8 +11,24 @@ for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
         sys.path.insert(0, p)
 
 
+def _build_library():
+    """Build (or refresh) libcomet_b200.so before any test imports the package -- a fresh clone has no .so, and the
+    package refuses to import without it.  build.py is loaded by path for the same reason."""
+    import importlib.util
+    import shutil
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        return  # GPU box without a toolchain: the prebuilt in-tree .so is used as is
+    spec = importlib.util.spec_from_file_location("_comet_b200_build",
+                                                  os.path.join(ROOT, "comet_pose_estimation_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    _build_library()
 
 
 def pytest_collection_modifyitems(config, items):
