@@ -75,11 +75,16 @@ __device__ __forceinline__ TileInfo tile_info(int t) {
 // One unit of work of the persistent kernel: up to four runs of consecutive tiles (a run never spans two pyramid
 // levels) of one (frame, 128 sorted queries) pair.  Written by tc_plan_kernel, read by every warp role.
 struct __align__(16) JobRec {
-  int bs, mt, nseg, flags;
-  int t0[4];          // first tile of run i (global tile numbering of tile_info)
-  int t1[4];          // one past the last tile of run i
+  int bs;
+  int mnf;            // query tile (bits 0-15) | number of runs (16-23) | flags (24-31)
+  uint32_t t0p, t1p;  // run i: first tile / one past the last tile in byte i (global tile numbering of tile_info, < 256)
   int own_lo, own_hi; // level-0 jobs: the window rows ("tops") whose output this job writes
   int pad0, pad1;
+  __host__ __device__ int mt() const { return mnf & 0xffff; }
+  __host__ __device__ int nseg() const { return (mnf >> 16) & 0xff; }
+  __host__ __device__ int flags() const { return (mnf >> 24) & 0xff; }
+  __host__ __device__ int t0(int i) const { return (t0p >> (8 * i)) & 0xff; }
+  __host__ __device__ int t1(int i) const { return (t1p >> (8 * i)) & 0xff; }
 };
 constexpr int JF_FIRST0 = 1;  // first level-0 job of its (frame, query tile)
 constexpr int JF_LAST0 = 2;   // last level-0 job: also writes the non-correlation token channels
@@ -213,18 +218,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf16_resid(float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); }
 
-__device__ __forceinline__ JobRec load_job(const JobRec* j) {
+__device__ __forceinline__ JobRec load_job(const Params& p, int job) {
   JobRec r;
-  const int4* s = reinterpret_cast<const int4*>(j);
-  int4* d = reinterpret_cast<int4*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d[i] = __ldg(s + i);
+  if (job < p.njobs) {
+    const int4* s = reinterpret_cast<const int4*>(p.jobs + job);
+    int4* d = reinterpret_cast<int4*>(&r);
+    d[0] = __ldg(s);
+    d[1] = __ldg(s + 1);
+  } else {
+    r.bs = 0; r.mnf = 0; r.t0p = 0; r.t1p = 0; r.own_lo = 0; r.own_hi = 0; r.pad0 = 0; r.pad1 = 0;
+  }
   return r;
-}
-// Job sequence of this CTA: blockIdx.x, +gridDim.x, ... skipping empty records -- identical in every warp role.
-__device__ __forceinline__ int seek_job(const Params& p, int job) {
-  while (job < p.njobs && __ldg(&p.jobs[job].nseg) == 0) job += gridDim.x;
-  return job;
 }
 
 __device__ __forceinline__ void stamp(const Params& p, int role, int idx, int which) {
@@ -298,10 +302,9 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
   for (int idx = threadIdx.x; idx < p.mtiles * p.nchunk; idx += blockDim.x) {
     const int mt = idx / p.nchunk, c = idx - mt * p.nchunk;
     JobRec jr;
-    jr.bs = bs; jr.mt = mt; jr.nseg = 0; jr.flags = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { jr.t0[i] = 0; jr.t1[i] = 0; }
+    jr.bs = bs; jr.t0p = 0; jr.t1p = 0;
     jr.own_lo = -BIG; jr.own_hi = BIG; jr.pad0 = 0; jr.pad1 = 0;
+    int nseg = 0, flags = 0;
     auto rows_of = [&](int l, int& R0, int& R1) {
       if (full || !track) { R0 = 0; R1 = (MAP >> l) - 1; }
       else { R0 = rng[mt][2 * l]; R1 = rng[mt][2 * l + 1]; if (R0 > R1) { R0 = 0; R1 = 0; } }
@@ -312,12 +315,17 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
       const int nr = R1 - R0 + 1, rpc = (nr + p.nsplit - 1) / p.nsplit;
       const int a = R0 + c * rpc, bb = min(a + rpc, R1);
       const bool real = (c == 0) || (a < R1);
+      nseg = 1;
       if (real) {
         const bool last = bb == R1;
-        jr.nseg = 1; jr.t0[0] = a; jr.t1[0] = bb + 1;
-        jr.flags = (c == 0 ? JF_FIRST0 : 0) | (last ? JF_LAST0 : 0);
+        jr.t0p = a; jr.t1p = bb + 1;
+        flags = (c == 0 ? JF_FIRST0 : 0) | (last ? JF_LAST0 : 0);
         jr.own_lo = (c == 0) ? -BIG : a;
         jr.own_hi = last ? BIG : bb - 1;
+      } else {
+        // band narrower than the split: a one-tile job that owns no window rows (keeps the job sequence static)
+        jr.t0p = R1; jr.t1p = R1 + 1;
+        jr.own_lo = BIG; jr.own_hi = -BIG;
       }
     } else {
       const int k = c - p.nsplit;
@@ -328,11 +336,12 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
         rows_of(l, R0, R1);
         const int sh = l == 1 ? 1 : l == 2 ? 2 : l == 3 ? 3 : 2;  // log2(map rows per tile): 2, 4, 8, 4
         const int base = l == 1 ? 64 : l == 2 ? 80 : l == 3 ? 84 : 85;
-        jr.t0[jr.nseg] = base + (R0 >> sh);
-        jr.t1[jr.nseg] = base + (R1 >> sh) + 1;
-        ++jr.nseg;
+        jr.t0p |= (uint32_t)(base + (R0 >> sh)) << (8 * nseg);
+        jr.t1p |= (uint32_t)(base + (R1 >> sh) + 1) << (8 * nseg);
+        ++nseg;
       }
     }
+    jr.mnf = mt | (nseg << 16) | (flags << 24);
     jobs[((long long)bs * p.mtiles + mt) * p.nchunk + c] = jr;
   }
 }
@@ -434,10 +443,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       int tcount = 0;
-      for (int job = seek_job(p, blockIdx.x); job < p.njobs; job = seek_job(p, job + gridDim.x)) {
-        const JobRec jr = load_job(p.jobs + job);
-        for (int sg = 0; sg < jr.nseg; ++sg) {
-          for (int t = jr.t0[sg]; t < jr.t1[sg]; ++t) {
+      JobRec nxt = load_job(p, blockIdx.x);
+      for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+        const JobRec jr = nxt;
+        nxt = load_job(p, job + gridDim.x);   // record of the next job: in flight while this one streams
+        const int nseg = jr.nseg();
+        for (int sg = 0; sg < nseg; ++sg) {
+          for (int t = jr.t0(sg), te = jr.t1(sg); t < te; ++t) {
             mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
             stamp(p, 0, tcount++, 0);
             uint8_t* dst = sB + stage * STAGE_BYTES;
@@ -458,14 +470,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, ji = 0;
     int tcount = 0;
     const int npass = (p.debug & 8) ? 0 : p.npass;
-    for (int job = seek_job(p, blockIdx.x); job < p.njobs; job = seek_job(p, job + gridDim.x), ++ji) {
-      const JobRec jr = load_job(p.jobs + job);
+    JobRec nxt = load_job(p, blockIdx.x);
+    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
+      const JobRec jr = nxt;
+      nxt = load_job(p, job + gridDim.x);
+      const int nseg = jr.nseg();
       const uint32_t abuf = ji & 1;
       mbar_wait(&a_full[abuf], (ji >> 1) & 1, p.status, 2);
       const uint32_t a_hi = TM_A + abuf * 128, a_lo = a_hi + 64;
-      for (int sg = 0; sg < jr.nseg; ++sg) {
-        for (int t = jr.t0[sg]; t < jr.t1[sg]; ++t) {
-          const bool job_ends = (sg + 1 == jr.nseg) && (t + 1 == jr.t1[sg]);
+      for (int sg = 0; sg < nseg; ++sg) {
+        for (int t = jr.t0(sg), te = jr.t1(sg); t < te; ++t) {
+          const bool job_ends = (sg + 1 == nseg) && (t + 1 == te);
           mbar_wait(&acc_empty[acc], acc_phase ^ 1, p.status, 3);
           mbar_wait(&full[stage], phase, p.status, 4);
           tcgen05_fence_after();
@@ -507,21 +522,34 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     int tcount = 0;
     float* mywin = win;
 
-    for (int job = seek_job(p, blockIdx.x); job < p.njobs; job = seek_job(p, job + gridDim.x)) {
-      const JobRec jr = load_job(p.jobs + job);
-      const int bs = jr.bs;
-      const int b = bs / p.S, s = bs - b * p.S;
-      const int n = __ldg(p.perm + (long long)bs * p.npad + jr.mt * TILE_M + q);
-      const bool valid = n >= 0;
-      float cx = 0.f, cy = 0.f;
-      if (valid && p.coords) {
-        const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)n * p.c_sn;
-        cx = __ldg(cp);
-        cy = __ldg(cp + 1);
+    // software pipeline over jobs: the record of job i+2 and the query (slot -> index -> coordinates) of job i+1 are
+    // fetched while job i is processed, so no dependent global load sits between two jobs
+    auto fetch_query = [&](const JobRec& r, bool in_range, int& n_, float& cx_, float& cy_) {
+      n_ = -1; cx_ = 0.f; cy_ = 0.f;
+      if (in_range) {
+        n_ = __ldg(p.perm + (long long)r.bs * p.npad + r.mt() * TILE_M + q);
+        if (n_ >= 0 && p.coords) {
+          const int b_ = r.bs / p.S, s_ = r.bs - b_ * p.S;
+          const float* cp = p.coords + b_ * p.c_sb + s_ * p.c_ss + (long long)n_ * p.c_sn;
+          cx_ = __ldg(cp);
+          cy_ = __ldg(cp + 1);
+        }
       }
+    };
+    JobRec jr = load_job(p, blockIdx.x);
+    JobRec jr1 = load_job(p, blockIdx.x + gridDim.x);
+    int n, n1;
+    float cx, cy, cx1, cy1;
+    fetch_query(jr, (int)blockIdx.x < p.njobs, n, cx, cy);
+    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
+      const JobRec jr2 = load_job(p, job + 2 * gridDim.x);
+      fetch_query(jr1, job + (int)gridDim.x < p.njobs, n1, cx1, cy1);
+      const int bs = jr.bs;
+      const bool valid = n >= 0;
+      const int nseg = jr.nseg();
 
-      for (int sg = 0; sg < jr.nseg; ++sg) {
-        const int tfirst = jr.t0[sg], tend = jr.t1[sg];
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int tfirst = jr.t0(sg), tend = jr.t1(sg);
         const TileInfo t0i = tile_info(tfirst);
         const int level = t0i.level, Hl = t0i.H, Wl = t0i.W;
         // ---- window geometry of this query at this level; row band of the whole warp ----
@@ -650,7 +678,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         if (p.volume_mode || (p.debug & 1)) continue;
         // ---- end of the level inside this job: finish the window and hand it to the stager warp ----
         {
-          const bool last = !is0 || (jr.flags & JF_LAST0);
+          const bool last = !is0 || (jr.flags() & JF_LAST0);
           if (last && valid) {
             const int jb = (Hl - 1) - y0;  // top = H-1: its bottom row is off the map (hprev is row H-1: jb in range
                                            // means this query touches row H-1, so its warp streamed up to it)
@@ -671,6 +699,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           ++wu;
         }
       }
+      jr = jr1; jr1 = jr2;
+      n = n1; cx = cx1; cy = cy1;
     }
   } else {
     // ===================== stager warps (6..9): every global load/store except the TMA =====================
@@ -685,14 +715,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const int Wr = 2 * p.r + 1, WW = Wr * Wr;
     uint32_t wu = 0;
 
-    auto stage_targets = [&](int job, uint32_t ji) {
-      const int bs = __ldg(&p.jobs[job].bs), mt = __ldg(&p.jobs[job].mt);
-      const int b = bs / p.S, s = bs - b * p.S;
+    // stage the 128 target rows of job record `r` (hi/lo split) into TMEM A buffer (ji & 1); `nq` = this lane's query
+    auto stage_targets = [&](const JobRec& r, int nq, uint32_t ji) {
+      const int b = r.bs / p.S, s = r.bs - b * p.S;
       const uint32_t abuf = ji & 1;
       mbar_wait(&a_empty[abuf], ((ji >> 1) & 1) ^ 1, p.status, 6);
       tcgen05_fence_after();
       if (!(p.debug & 256)) {
-        const int nq = __ldg(p.perm + (long long)bs * p.npad + mt * TILE_M + q);
         const bool rv = nq >= 0;
         const float4* src = reinterpret_cast<const float4*>(p.targets + b * p.t_sb + s * p.t_ss +
                                                             (long long)(rv ? nq : 0) * p.t_sn);
@@ -722,20 +751,26 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       tcgen05_fence_before();
       mbar_arrive(&a_full[abuf]);
     };
+    auto slot_query = [&](const JobRec& r, bool in_range) {
+      return in_range ? __ldg(p.perm + (long long)r.bs * p.npad + r.mt() * TILE_M + q) : -1;
+    };
 
-    int job = seek_job(p, blockIdx.x);
-    if (job < p.njobs) stage_targets(job, 0);
+    // software pipeline: record of job i+2 and query index of job i+1 are in flight while job i is served
+    JobRec jr = load_job(p, blockIdx.x);
+    JobRec jr1 = load_job(p, blockIdx.x + gridDim.x);
+    int myn = slot_query(jr, (int)blockIdx.x < p.njobs);
+    int myn1 = slot_query(jr1, (int)(blockIdx.x + gridDim.x) < p.njobs);
+    if ((int)blockIdx.x < p.njobs) stage_targets(jr, myn, 0);
     uint32_t ji = 0;
-    for (; job < p.njobs; ++ji) {
-      const int next = seek_job(p, job + gridDim.x);
+    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
+      const JobRec jr2 = load_job(p, job + 2 * gridDim.x);
+      const int myn2 = slot_query(jr2, job + 2 * (int)gridDim.x < p.njobs);   // needs jr2: consumed two jobs later
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 0);
-      if (next < p.njobs) stage_targets(next, ji + 1);
+      if (job + (int)gridDim.x < p.njobs) stage_targets(jr1, myn1, ji + 1);
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 1);
-      const JobRec jr = load_job(p.jobs + job);
-      job = next;
       const int bs = jr.bs;
       const int b = bs / p.S, s = bs - b * p.S;
-      const int myn = __ldg(p.perm + (long long)bs * p.npad + jr.mt * TILE_M + q);  // query of sorted slot q
+      const int nseg = jr.nseg();
 
       // element offsets of this lane's query rows (pos_emb row, output row), shared with the warp through smem:
       // the store loop below then needs one broadcast LDS.64 per row instead of shuffles + 64-bit index math.
@@ -749,18 +784,18 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         __syncwarp();
       }
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 1, 0);
-      if (p.volume_mode || (p.debug & 1)) continue;
-      const int nvalid = min(32, p.N - (jr.mt * TILE_M + 32 * wq));   // sorted slots: valid first, padding last
+      const bool do_windows = !(p.volume_mode || (p.debug & 1));
+      const int nvalid = min(32, p.N - (jr.mt() * TILE_M + 32 * wq));   // sorted slots: valid first, padding last
       // window units of this job: one per tile run (= one pyramid level)
-      for (int sg = 0; sg < jr.nseg; ++sg, ++wu) {
-        const int lvl = tile_info(jr.t0[sg]).level;
+      for (int sg = 0; do_windows && sg < nseg; ++sg, ++wu) {
+        const int lvl = tile_info(jr.t0(sg)).level;
         const uint32_t wbuf = wu % NWIN;
         mbar_wait(&win_full[wbuf * 4 + wq], (wu / NWIN) & 1, p.status, 8);
         if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 0);
         const float* wrows = win + (wbuf * TILE_M + 32 * wq) * WIN_STRIDE;
         const int lvl_off = (p.tokens ? KC + 2 : 0) + lvl * WW;
         const int jj0 = lane % Wr, jj1 = (lane + 32) % Wr, jj2 = (lane + 64) % Wr;
-        const bool ok1 = lane + 32 < WW, ok2 = lane + 64 < WW;   // lane < WW always (WW >= 1 ... 81; lane 0..31 may exceed for r=0..2)
+        const bool ok1 = lane + 32 < WW, ok2 = lane + 64 < WW;
         const bool ok0 = lane < WW;
         const float* pbase = p.pos + lvl_off + min(lane, WW - 1);
         const int d1 = min(lane + 32, WW - 1) - min(lane, WW - 1), d2 = min(lane + 64, WW - 1) - min(lane, WW - 1);
@@ -796,6 +831,8 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         if (lane == 0) mbar_arrive(&win_empty[wbuf * 4 + wq]);
         if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 1);
       }
+      jr = jr1; jr1 = jr2;
+      myn = myn1; myn1 = myn2;
     }
   }
 

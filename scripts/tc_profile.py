@@ -26,7 +26,21 @@ for i in range(iters):
     ev[i + 1].record()
 torch.cuda.synchronize()
 ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(iters)]
-print(f"Q={Q} debug={os.environ.get('COMET_TC_DEBUG','0')} tokens: min {min(ts):.1f} us, median {sorted(ts)[len(ts)//2]:.1f} us")
+print(f"Q={Q} debug={os.environ.get('COMET_TC_DEBUG','0')} tokens: min {min(ts):.1f} us, median {sorted(ts)[len(ts)//2]:.1f} us", end="")
+# GPU-only time: the same call captured in a CUDA graph (no Python / launch overhead between kernels)
+g = torch.cuda.CUDAGraph()
+st = torch.cuda.Stream()
+st.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(st):
+    t3.tokens(co, ft, out=out)
+    with torch.cuda.graph(g, stream=st):
+        for _ in range(iters):
+            t3.tokens(co, ft, out=out)
+torch.cuda.synchronize()
+g.replay(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+print(f"  | graph: {e0.elapsed_time(e1)*1e3/iters:.1f} us/iter")
 b3.corr(ft)
 for _ in range(2): b3.sample(co)
 torch.cuda.synchronize()
