@@ -58,7 +58,7 @@ def tdim(L, r, latent, fine):
 
 
 # --------------------------------------------------------------------------- synthetic inputs (host, seeded)
-def make_inputs(Q, seed, torch, pin):
+def make_inputs(Q, seed, torch, pin, fine_layout="nchw"):
     """Host tensors for Q sequences.  SURVEY 8(d) item 5: fmaps ~ N(0,1); queries U over the map; per-iteration
     coords = query + small random walk (frame 0 pinned); per-iteration track_feats ~ N(0,1)."""
     g = torch.Generator().manual_seed(seed)
@@ -70,7 +70,12 @@ def make_inputs(Q, seed, torch, pin):
     out = {}
     for name, cfg, B, N in (("coarse", COARSE, Q, COARSE["N"]), ("fine", FINE, Q * FINE["P"], 1)):
         S, C, H, W, it = cfg["S"], cfg["C"], cfg["H"], cfg["W"], cfg["iters"]
-        fm = alloc(B, S, C, H, W)
+        if name == "fine" and fine_layout == "cl":
+            # same (B,S,C,H,W) tensor, memory laid out (B,S,H,W,C): the native output layout of a channels-last
+            # patch encoder; the kernels use it zero-copy
+            fm = alloc(B, S, H, W, C).permute(0, 1, 4, 2, 3)
+        else:
+            fm = alloc(B, S, C, H, W)
         fm.normal_(generator=g)
         q = torch.rand(B, 1, N, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
         coords = alloc(it, B, S, N, 2)
@@ -136,7 +141,7 @@ def algorithmic_bytes(Q):
     per_q = taps * f["C"] * 4 + f["C"] * 4 + 8 + tdf * 4 + tdf * 4 / f["S"]
     fine = Q * f["P"] * f["S"] * per_q
     pyr_c = Q * c["S"] * c["C"] * 4 * (64 * 64 + 2 * (32 * 32 + 16 * 16 + 8 * 8) + 4 * 4)
-    pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (31 * 31 + 2 * 15 * 15 + 7 * 7)
+    pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (31 * 31 + 15 * 15 + 7 * 7)   # read level 0 once, write levels 1-2
     return dict(coarse_tokens=coarse, fine_tokens=fine, coarse_pyramid=pyr_c, fine_pyramid=pyr_f)
 
 
@@ -268,6 +273,9 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fine-layout", default="nchw", choices=["nchw", "cl"],
+                    help="memory layout of the fine tracker's patch features: nchw = contiguous (B,S,C,H,W) as the "
+                         "reference's encoder returns them; cl = channels-last view (a torch.channels_last encoder)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -292,8 +300,10 @@ def main():
     import comet_pose_estimation_b200 as cb
 
     Q = args.batch
-    host = make_inputs(Q, 1000 + rank, torch, pin=True)
-    devin = {k: {n: t.to(dev, non_blocking=True) for n, t in v.items()} for k, v in host.items()}
+    host = make_inputs(Q, 1000 + rank, torch, pin=True, fine_layout=args.fine_layout)
+    # empty_like + copy_ keep the strides (a channels-last view stays a channels-last view on the device)
+    devin = {k: {n: torch.empty_like(t, device=dev).copy_(t, non_blocking=True) for n, t in v.items()}
+             for k, v in host.items()}
     torch.cuda.synchronize()
     hp = HotPath(cb, torch, Q, dev)
 
@@ -425,6 +435,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
                        "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
+                       "fine_layout": args.fine_layout,
                        "l2": "inputs per step exceed L2 (fine patch features: %.1f GB)" % (Q * 1.008)},
             "roofline": roof, "roofline_tensor": tensor, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "kernels": kern,

@@ -33,7 +33,12 @@ class _Pyramid:
         assert 1 <= num_levels <= _lib.MAX_LEVELS, f"num_levels must be in [1, {_lib.MAX_LEVELS}]"
         self.B, self.S, self.C, self.H, self.W = B, S, C, H, W
         self.num_levels = num_levels
-        self.fmaps0 = f32c(fmaps)
+        # A dense channels-last view (B,S,C,H,W) with strides (S*H*W*C, H*W*C, 1, W*C, C) -- what a
+        # torch.channels_last encoder hands over after a reshape -- is used zero-copy when the fused kernels of the
+        # small-map path can read it (one 128-byte line per position); anything else becomes NCHW-contiguous.
+        self.cl_input = (fmaps.dtype == torch.float32 and C % 4 == 0 and C <= 64 and B * S > 0 and not fmaps.is_contiguous()
+                         and fmaps.permute(0, 1, 3, 4, 2).is_contiguous() and fmaps.data_ptr() % 16 == 0)
+        self.fmaps0 = fmaps if self.cl_input else f32c(fmaps)
         n = lib.comet_pyramid_elems(B * S, C, H, W, num_levels)
         assert n >= 0
         self.pyr = torch.empty(max(n, 1), dtype=torch.float32, device=fmaps.device)
@@ -45,11 +50,16 @@ class _Pyramid:
                 _lib.check(lib.comet_tc_prepare_f32(self.fmaps0.data_ptr(), self.split.data_ptr(),
                                                     self.pyr.data_ptr(), B * S, C, H, W, num_levels,
                                                     stream_ptr(fmaps.device)))
+            elif self.cl_input:
+                self.layout = _lib.PYR_ALL_CHANNEL_LAST
+                if num_levels > 1:
+                    _lib.check(lib.comet_pyramid_cl_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
+                                                        num_levels, _lib.FMAPS_CHANNEL_LAST, stream_ptr(fmaps.device)))
             elif W <= 32 and H <= 33 and C % 4 == 0 and C <= 64 and num_levels > 1:
                 # small maps (fine tracker patches): levels >= 1 channel-last, one contiguous line per position
                 self.layout = _lib.PYR_CHANNEL_LAST
                 _lib.check(lib.comet_pyramid_cl_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
-                                                    num_levels, stream_ptr(fmaps.device)))
+                                                    num_levels, _lib.FMAPS_NCHW, stream_ptr(fmaps.device)))
             else:
                 _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
                                                  num_levels, stream_ptr(fmaps.device)))
@@ -60,7 +70,7 @@ class _Pyramid:
             h, w = h // 2, w // 2
             off = lib.comet_pyramid_offset(B * S, C, H, W, l)
             flat = self.pyr[off: off + B * S * C * h * w]
-            if self.layout == _lib.PYR_CHANNEL_LAST:
+            if self.layout != _lib.PYR_NCHW:
                 self.levels.append(flat.view(B, S, h, w, C).permute(0, 1, 4, 2, 3))  # same values, strided view
             else:
                 self.levels.append(flat.view(B, S, C, h, w))
@@ -164,7 +174,7 @@ class CorrBlock:
                 for l, f in enumerate(self.fmaps_pyramid):
                     h, w = f.shape[-2:]
                     tl = t[..., l * self.C:(l + 1) * self.C] if self.multiple_track_feats else t
-                    fl = p.fmaps0 if l == 0 else f.contiguous()
+                    fl = p.fmaps0 if (l == 0 and not p.cl_input) else f.contiguous()
                     v = torch.empty((B, S, N, h, w), dtype=torch.float32, device=t.device)
                     for b0 in range(0, B * S, 32768):  # gridDim.z limit
                         nb = min(32768, B * S - b0)

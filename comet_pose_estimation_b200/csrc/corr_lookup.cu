@@ -33,13 +33,14 @@ struct LookupParams {
   int pad_border, bf16;
   int lvlH[COMET_MAX_LEVELS], lvlW[COMET_MAX_LEVELS];
   long long lvlOff[COMET_MAX_LEVELS];
-  int channel_last;  // levels >= 1 stored (BS, H_l, W_l, C) instead of (BS, C, H_l, W_l); level 0 is always NCHW
+  int channel_last;  // levels >= 1 stored (BS, H_l, W_l, C) instead of (BS, C, H_l, W_l)
+  int cl0;           // level 0 (the caller's fmaps) is channel-last too
   float sqrt_c;
 };
 
 // element strides of level l: channel, row, column
 __device__ __forceinline__ void level_strides(const LookupParams& p, int l, long long& sc, int& sy, int& sx) {
-  if (l > 0 && p.channel_last) { sc = 1; sy = p.lvlW[l] * p.C; sx = p.C; }
+  if (p.channel_last && (l > 0 || p.cl0)) { sc = 1; sy = p.lvlW[l] * p.C; sx = p.C; }
   else { sc = (long long)p.lvlH[l] * p.lvlW[l]; sy = p.lvlW[l]; sx = 1; }
 }
 
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(256, 2) corr_lookup_c32_kernel(const LookupPar
       pos[k] = ok[k] ? gy * Wl + gx : 0;
       acc[k] = 0.f;
     }
-    if (l > 0 && p.channel_last) {
+    if (p.channel_last && (l > 0 || p.cl0)) {
 #pragma unroll
       for (int k = 0; k < ROWS0; ++k) {
         const float4* v4 = reinterpret_cast<const float4*>(F) + (long long)pos[k] * 8;
@@ -352,7 +353,8 @@ static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
   if (total == 0) return COMET_OK;
   const long long blocks = (total + warps - 1) / warps;
   if (blocks > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many queries for one launch");
-  if (p.C == 32 && p.r >= 1 && p.r <= 3 && p.t_level_stride == 0 && ((uintptr_t)p.pyr % 16) == 0) {
+  if (p.C == 32 && p.r >= 1 && p.r <= 3 && p.t_level_stride == 0 && ((uintptr_t)p.pyr % 16) == 0 &&
+      (!p.cl0 || ((uintptr_t)p.fmaps % 16) == 0)) {
     if (p.r == 3) launch_c32<3, TOKENS>(p, (unsigned)blocks, stream);
     else if (p.r == 2) launch_c32<2, TOKENS>(p, (unsigned)blocks, stream);
     else launch_c32<1, TOKENS>(p, (unsigned)blocks, stream);
@@ -384,7 +386,8 @@ static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, co
   COMET_REQUIRE(r >= 0 && r <= COMET_MAX_RADIUS, "radius must be in [0, %d] (got %d)", COMET_MAX_RADIUS, r);
   COMET_REQUIRE(pad_mode == COMET_PAD_ZEROS || pad_mode == COMET_PAD_BORDER, "bad pad_mode %d", pad_mode);
   COMET_REQUIRE(prec_mode == COMET_PREC_F32 || prec_mode == COMET_PREC_BF16_AUTOCAST, "bad prec_mode %d", prec_mode);
-  COMET_REQUIRE(pyr_layout == COMET_PYR_NCHW || pyr_layout == COMET_PYR_CHANNEL_LAST, "bad pyr_layout %d", pyr_layout);
+  COMET_REQUIRE(pyr_layout == COMET_PYR_NCHW || pyr_layout == COMET_PYR_CHANNEL_LAST ||
+                    pyr_layout == COMET_PYR_ALL_CHANNEL_LAST, "bad pyr_layout %d", pyr_layout);
   COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
   const long long total = (long long)B * S * N;
   COMET_REQUIRE(total == 0 || (fmaps && targets && coords), "null input pointer");
@@ -398,7 +401,8 @@ static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, co
   Levels lv = make_levels(B * S, C, H, W, L);
   for (int l = 0; l < L; ++l) { p.lvlH[l] = lv.H[l]; p.lvlW[l] = lv.W[l]; p.lvlOff[l] = lv.off[l]; }
   p.sqrt_c = sqrtf((float)C);
-  p.channel_last = pyr_layout == COMET_PYR_CHANNEL_LAST;
+  p.channel_last = pyr_layout != COMET_PYR_NCHW;
+  p.cl0 = pyr_layout == COMET_PYR_ALL_CHANNEL_LAST;
   p.pos = nullptr; p.D_tok = 0;
   return COMET_OK;
 }

@@ -132,6 +132,57 @@ __global__ void __launch_bounds__(256, 4) pyramid_cl_fine_kernel(const float* __
   }
 }
 
+// Channel-last INPUT (the producer's native layout, e.g. a cuDNN encoder run in torch.channels_last): level 0 is
+// (BS, H, W, C) and never copied; levels 1..L-1 are written channel-last.  One CTA per map, thread <-> (output
+// position, 4 channels): four 128-bit loads (one per 2x2 tap, lanes of a position read one contiguous line), one
+// 128-bit store; the level stays in shared memory for the next one.  Row / column H-1 of an odd map is never read.
+__global__ void __launch_bounds__(256, 4) pyramid_cl_in_kernel(const float4* __restrict__ in, float* __restrict__ pyr,
+                                                               int C4, int H, int W, int L, Levels lv) {
+  extern __shared__ float4 tile4[];  // levels 1..L-1 back to back, dense (pos, C4)
+  const long long map = blockIdx.x;
+  const float4* src = in + map * (long long)H * W * C4;
+  int Hi = H, Wi = W, in_off = 0, out_off = 0;
+  for (int l = 1; l < L; ++l) {
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    const int items = Ho * Wo * C4;
+    float4* dst = reinterpret_cast<float4*>(pyr + lv.off[l]) + map * (long long)items;
+    for (int i0 = threadIdx.x; i0 < items; i0 += 4 * blockDim.x) {
+      float4 t[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(i0 + u * (int)blockDim.x, items - 1);
+        const int pos = i / C4, c4 = i - pos * C4;
+        const int yo = pos / Wo, xo = pos - yo * Wo;
+        const int base = ((2 * yo) * Wi + 2 * xo) * C4 + c4;
+        if (l == 1) {
+          t[u][0] = __ldg(src + base); t[u][1] = __ldg(src + base + C4);
+          t[u][2] = __ldg(src + base + Wi * C4); t[u][3] = __ldg(src + base + (Wi + 1) * C4);
+        } else {
+          t[u][0] = tile4[in_off + base]; t[u][1] = tile4[in_off + base + C4];
+          t[u][2] = tile4[in_off + base + Wi * C4]; t[u][3] = tile4[in_off + base + (Wi + 1) * C4];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * (int)blockDim.x;
+        if (i < items) {
+          float4 v;
+          v.x = ((t[u][0].x + t[u][1].x) + (t[u][2].x + t[u][3].x)) * 0.25f;
+          v.y = ((t[u][0].y + t[u][1].y) + (t[u][2].y + t[u][3].y)) * 0.25f;
+          v.z = ((t[u][0].z + t[u][1].z) + (t[u][2].z + t[u][3].z)) * 0.25f;
+          v.w = ((t[u][0].w + t[u][1].w) + (t[u][2].w + t[u][3].w)) * 0.25f;
+          tile4[out_off + i] = v;
+          dst[i] = v;
+        }
+      }
+    }
+    __syncthreads();
+    in_off = out_off;
+    out_off += items;
+    Hi = Ho; Wi = Wo;
+  }
+}
+
 }  // namespace comet
 
 using namespace comet;
@@ -171,8 +222,28 @@ extern "C" int comet_pyramid_f32(const float* fmaps, float* pyr, int BS, int C, 
 }
 
 extern "C" int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L,
-                                    comet_stream_t stream) {
+                                    int fmaps_layout, comet_stream_t stream) {
   COMET_REQUIRE(BS >= 0 && C >= 1 && H >= 1 && W >= 1, "bad shape");
+  COMET_REQUIRE(fmaps_layout == COMET_FMAPS_NCHW || fmaps_layout == COMET_FMAPS_CHANNEL_LAST, "bad fmaps_layout %d",
+                fmaps_layout);
+  if (fmaps_layout == COMET_FMAPS_CHANNEL_LAST) {
+    COMET_REQUIRE(L >= 1 && L <= COMET_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", COMET_MAX_LEVELS, L);
+    COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
+    COMET_REQUIRE(C % 4 == 0, "channel-last input needs C %% 4 == 0 (got %d)", C);
+    if (L == 1 || BS == 0) return COMET_OK;
+    COMET_REQUIRE(fmaps && pyr, "null pointer");
+    COMET_REQUIRE(((uintptr_t)fmaps % 16) == 0 && ((uintptr_t)pyr % 16) == 0, "channel-last pyramid needs 16-byte aligned buffers");
+    Levels lv = make_levels(BS, C, H, W, L);
+    size_t items = 0;
+    for (int l = 1; l < L; ++l) items += (size_t)lv.H[l] * lv.W[l];
+    const size_t smem = items * C * sizeof(float);
+    COMET_REQUIRE(smem <= 200 * 1024, "pooled levels of one map (%zu bytes) do not fit shared memory", smem);
+    if (smem > 48 * 1024)
+      COMET_CUDA(cudaFuncSetAttribute(pyramid_cl_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pyramid_cl_in_kernel<<<BS, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(fmaps), pyr, C / 4, H, W,
+                                                                   L, lv);
+    return launch_status("pyramid_cl_in_kernel");
+  }
   COMET_REQUIRE(L >= 1 && L <= COMET_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", COMET_MAX_LEVELS, L);
   COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
   COMET_REQUIRE(W <= 32 && H <= 2 * CL_MAX_ROWS + 1, "channel-last pyramid needs W <= 32 and H <= 33");

@@ -44,6 +44,10 @@ extern "C" {
 
 #define COMET_PYR_NCHW 0         /* pyramid levels 1..L-1 stored (BS, C, H_l, W_l), like the reference */
 #define COMET_PYR_CHANNEL_LAST 1 /* ... stored (BS, H_l, W_l, C): one contiguous line per position (fine tracker) */
+#define COMET_PYR_ALL_CHANNEL_LAST 2 /* as 1, and level 0 (the caller's fmaps) is channel-last (BS, H, W, C) too */
+
+#define COMET_FMAPS_NCHW 0         /* fmaps (BS, C, H, W) contiguous, as the reference's encoders return them */
+#define COMET_FMAPS_CHANNEL_LAST 1 /* fmaps (BS, H, W, C) dense: a torch.channels_last encoder output, used zero-copy */
 
 #define COMET_MAX_LEVELS 8
 #define COMET_MAX_RADIUS 7
@@ -67,8 +71,10 @@ long long comet_pyramid_offset(int BS, int C, int H, int W, int level); /* eleme
 long long comet_pyramid_elems(int BS, int C, int H, int W, int L);      /* total for levels 1..L-1 */
 int comet_pyramid_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, comet_stream_t stream);
 /* Same pooling, levels 1..L-1 written channel-last (COMET_PYR_CHANNEL_LAST) at the same offsets.
- * Requires W <= 32, H <= 33 and a pooled tile that fits shared memory (small maps: the fine tracker's patches). */
-int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, comet_stream_t stream);
+ * COMET_FMAPS_NCHW input requires W <= 32, H <= 33 and a pooled tile that fits shared memory (small maps: the fine
+ * tracker's patches); COMET_FMAPS_CHANNEL_LAST input requires C % 4 == 0 and 16-byte aligned buffers. */
+int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, int fmaps_layout,
+                         comet_stream_t stream);
 
 /* ---- correlation volume: CorrBlock.corr, blocks.py:409-429 -------------
  * vol[bs, n, hw] = (sum_c targets[bs, n, c] * fmap[bs, c, hw]) / sqrt(C) for ONE pyramid level.

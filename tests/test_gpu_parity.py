@@ -311,7 +311,107 @@ def test_full_size_fine_config_subset_vs_oracle(cb):
     assert rel_to_max(host(out[sel]), want) < FP32_BAR
 
 
+def _channels_last_view(fmaps):
+    """Same values, (B,S,C,H,W) shape, memory laid out (B,S,H,W,C): what a torch.channels_last encoder returns."""
+    return fmaps.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+
+
+@pytest.mark.parametrize("shape", [(24, 4, 32, 31, 31, 3, 3), (3, 2, 32, 31, 31, 2, 2), (2, 3, 16, 20, 13, 3, 3),
+                                   (2, 2, 32, 31, 31, 1, 3), (5, 2, 8, 9, 9, 4, 1)])
+def test_channels_last_fmaps_are_used_zero_copy(cb, shape):
+    """A channels-last fmaps view (the producer's native layout) goes through the same kernels without a copy and
+    gives the reference's numbers: pyramid, lookup (both paddings), tokens, lazily materialised volumes."""
+    B, S, C, H, W, L, r = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    fmaps = torch.randn(B, S, C, H, W, device="cuda", generator=g)
+    feats = torch.randn(B, S, 2, C, device="cuda", generator=g)
+    coords = torch.rand(B, S, 2, 2, device="cuda", generator=g) * torch.tensor([W + 6.0, H + 6.0], device="cuda") - 3
+    fcl = _channels_last_view(fmaps)
+    assert not fcl.is_contiguous() and torch.equal(fcl, fmaps)
+    blk = cb.CorrBlock(fcl, num_levels=L, radius=r)
+    assert blk._pyr.cl_input and blk._pyr.fmaps0.data_ptr() == fcl.data_ptr()
+    want_levels = O.build_pyramid(host(fmaps), L)
+    for l in range(L):
+        assert rel_to_max(host(blk.fmaps_pyramid[l]), want_levels[l]) < 1e-6
+    blk.corr(feats)
+    want = O.corr_lookup(host(fmaps), host(feats), host(coords), L, r, "zeros")
+    assert rel_to_max(host(blk.sample(coords)), want) < FP32_BAR
+    eff = cb.EfficientCorrBlock(fcl, num_levels=L, radius=r)
+    want_b = O.corr_lookup(host(fmaps), host(feats), host(coords), L, r, "border")
+    assert rel_to_max(host(eff.sample(coords, feats)), want_b) < FP32_BAR
+    ref = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+    ref.corr(feats)
+    for a, b in zip(blk.corrs_pyramid, ref.corrs_pyramid):
+        assert rel_to_max(host(a), host(b)) < 1e-5
+    tdim = (2 * C + 2 + L * (2 * r + 1) ** 2 + 3) // 4 * 4 + 4   # any multiple of 4 that holds the channels
+    x = cb.TrackTokenizer(blk, coords[:, 0], tdim).tokens(coords, feats)
+    x_ref = cb.TrackTokenizer(ref, coords[:, 0], tdim).tokens(coords, feats)
+    assert rel_to_max(host(x), host(x_ref)) < 1e-5
+
+
+def test_full_size_fine_config_channels_last(cb):
+    """Fine tracker at full size with channels-last patch features == the NCHW result (same oracle slice)."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    fmaps = torch.randn(512, 16, 32, 31, 31, device="cuda", generator=g)
+    feats = torch.randn(512, 16, 1, 32, device="cuda", generator=g)
+    coords = torch.rand(512, 16, 1, 2, device="cuda", generator=g) * 30
+    blk = cb.CorrBlock(_channels_last_view(fmaps), num_levels=3, radius=3)
+    assert blk._pyr.cl_input
+    blk.corr(feats)
+    out = blk.sample(coords)
+    sel = slice(0, 512, 61)
+    want = O.corr_lookup(host(fmaps[sel]), host(feats[sel]), host(coords[sel]), 3, 3)
+    assert rel_to_max(host(out[sel]), want) < FP32_BAR
+
+
 # ------------------------------------------------------------------ tensor-core path (tcgen05) vs SIMT path
+def test_tensor_path_degenerate_query_sets(cb):
+    """The tensor path sorts the queries of a frame by row and only streams the band of map rows a tile of 128
+    queries needs.  Degenerate bands: every query on one row, every query off the map (wild / non-finite
+    coordinates), a single query, bands narrower than the row split, many query tiles per frame."""
+    if not cb._lib.lib.comet_has_tensor_path():
+        pytest.skip("no sm_100 tensor path on this device")
+    g = torch.Generator(device="cuda").manual_seed(21)
+    S, L, r = 2, 5, 4
+    fmaps = torch.randn(1, S, 128, 64, 64, device="cuda", generator=g)
+    sets = {}
+    c = torch.rand(1, S, 300, 2, device="cuda", generator=g) * 63
+    c[..., 1] = 17.25
+    sets["one_row"] = c
+    c = torch.rand(1, S, 140, 2, device="cuda", generator=g) * 63
+    c[:, :, ::2] = 1.0e7
+    c[:, :, 1::4] = -3.0e5
+    c[0, 0, 5, 0] = float("inf")
+    c[0, 1, 7, 1] = float("-inf")
+    sets["mostly_off_map"] = c
+    sets["all_off_map"] = torch.full((1, S, 130, 2), -500.0, device="cuda")
+    sets["single"] = torch.tensor([[[[63.0, 63.0]], [[0.0, 0.0]]]], device="cuda")
+    c = torch.rand(1, S, 1500, 2, device="cuda", generator=g) * 70 - 3
+    sets["many_tiles"] = c
+    c = torch.rand(1, S, 257, 2, device="cuda", generator=g) * 63
+    c[..., 1] = c[..., 1] * 0.02 + 62.5   # band hugging the bottom border
+    sets["bottom_band"] = c
+    for name, coords in sets.items():
+        N = coords.shape[2]
+        feats = torch.randn(1, S, N, 128, device="cuda", generator=g)
+        blk = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+        assert blk._pyr.split is not None
+        blk.corr(feats)
+        got = blk.sample(coords)
+        tdim = cb.transformer_dim(L, r, 128, False)
+        x = cb.TrackTokenizer(blk, coords[:, 0], tdim).tokens(coords, feats)
+        assert cb._lib.lib.comet_tc_status() == 0, name
+        finite = torch.isfinite(coords).all(-1)
+        sel = torch.arange(0, N, max(1, N // 40), device="cuda")
+        want = O.corr_lookup(host(fmaps), host(feats[:, :, sel]), host(torch.nan_to_num(coords[:, :, sel], posinf=1e7, neginf=-1e7)),
+                             L, r)
+        err = np.abs(host(got[:, :, sel]) - want)[host(finite[:, :, sel]).astype(bool)]
+        assert err.size == 0 or err.max() / max(np.abs(want).max(), 1.0) < FP32_BAR, name
+        corr_part = x[..., 130:130 + 405] - cb.TrackTokenizer(blk, coords[:, 0], tdim).pos[:, :, None, 130:535]
+        ok = finite.permute(0, 2, 1)
+        assert rel_to_max(host(corr_part[ok]), host(got.permute(0, 2, 1, 3)[ok])) < 1e-5, name
+
+
 def test_tensor_path_matches_simt_and_oracle(cb, monkeypatch):
     """Coarse COMET shape (C=128, 64x64, L=5, r=4, zero padding) runs on the tcgen05 kernel; the same call with
     COMET_B200_DISABLE_TC=1 runs the SIMT kernel.  Both must sit inside the fp32 bar against the oracle, for
