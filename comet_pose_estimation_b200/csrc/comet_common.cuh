@@ -1,5 +1,6 @@
 // Shared host/device helpers for the COMET B200 kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdarg>
@@ -35,6 +36,38 @@ inline int launch_status(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(COMET_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
   return COMET_OK;
+}
+
+// ---- TMA descriptors (host): cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeFn>(ptr);
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// SM count of the current device if it is compute capability 10.x, else 0 (no device: 0).
+inline int device_sm_count_if_sm100() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached = (major == 10 && sms > 0) ? sms : 0;
+  }
+  return cached;
 }
 
 // ---- pyramid geometry (host) -------------------------------------------

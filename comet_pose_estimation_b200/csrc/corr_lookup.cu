@@ -15,6 +15,10 @@
 // the dense coarse shapes go through the tcgen05 kernel in corr_tc.cu when available.
 #include "comet_common.cuh"
 
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+
 namespace comet {
 
 struct LookupParams {
@@ -337,6 +341,308 @@ __global__ void __launch_bounds__(256, 2) corr_lookup_c32_kernel(const LookupPar
   }
 }
 
+
+// ---- TMA-staged variant of the C == 32 kernel (the fine tracker's hot kernel) -------------------------------------
+// The register version above walks the levels one after the other: three dependent DRAM round trips per query, so it
+// is latency-bound (62 % of the HBM rate even with every sector fully used).  Here one elected lane per warp issues
+// ONE 4-D TMA box load per channel-last level -- box = [32 channels x G x G positions] around the query, out-of-map
+// positions zero-filled by the TMA unit (= the reference's zero padding), landing in shared memory with the 128-byte
+// swizzle -- so all levels of a query are in flight at once and no address arithmetic or predicate is spent on them.
+// A level-0 map in the caller's NCHW layout (CL0 == false) is gathered through registers while the boxes fly.
+// Then lanes <-> grid positions read "their" 128-byte line (swizzle makes the 8 lanes of a quarter-warp hit 8 different
+// bank groups), dot it with the target vector held in registers, and the blend / token epilogue is the one above.
+// Persistent: 8 warps per SM, each owns 3 box buffers (24 KB at r = 3) and loops over queries.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();  // a protocol bug must fail fast, not hang the device
+  }
+}
+__device__ __forceinline__ void load_box_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+}  // namespace tma
+
+struct TmaMaps { CUtensorMap m[3]; };
+
+template <int R, bool TOKENS, bool BF16, bool CL0>
+__global__ void __launch_bounds__(256, 1) corr_lookup_c32_tma_kernel(const __grid_constant__ TmaMaps maps, const LookupParams p) {
+  constexpr int G = 2 * R + 2, Wr = 2 * R + 1, GG = G * G, WW = Wr * Wr;
+  constexpr int ROWS0 = (GG + 31) / 32;
+  constexpr int BOX = GG * 128;                      // bytes landed per level
+  constexpr int BOXP = (BOX + 1023) & ~1023;         // swizzle atoms are 1 KB
+  extern __shared__ __align__(1024) uint8_t smem_tma[];
+  uint8_t* const smem = smem_tma;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* mybox = smem + warp * 3 * BOXP;
+  float* Ts = reinterpret_cast<float*>(smem + 8 * 3 * BOXP) + warp * 32;
+  float* Vs = reinterpret_cast<float*>(smem + 8 * 3 * BOXP + 8 * 32 * 4) + warp * 64;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * 3 * BOXP + 8 * 32 * 4 + 8 * 64 * 4) + warp;
+  if (lane == 0) {
+    tma::mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+  const long long total = (long long)p.B * p.S * p.N;
+  const long long nwarps = (long long)gridDim.x * 8;
+  const int l_first = CL0 ? 0 : 1;   // first level that arrives by TMA
+
+  // software pipeline over queries: coordinates / target of query i+1 are fetched while query i is processed, so the
+  // only global latency a warp waits for is its own TMA boxes
+  auto fetch = [&](long long q_, float& cx_, float& cy_, float& fx0_, float& fy0_, float& tl_) {
+    cx_ = cy_ = fx0_ = fy0_ = tl_ = 0.f;
+    if (q_ < total) {
+      const int n_ = (int)(q_ % p.N);
+      const int s_ = (int)((q_ / p.N) % p.S);
+      const int b_ = (int)(q_ / ((long long)p.N * p.S));
+      const float* cp = p.coords + b_ * p.c_sb + s_ * p.c_ss + n_ * p.c_sn;
+      cx_ = __ldg(cp); cy_ = __ldg(cp + 1);
+      if (TOKENS) {
+        const float* c0 = p.coords + b_ * p.c_sb + n_ * p.c_sn;  // frame 0
+        fx0_ = __ldg(c0); fy0_ = __ldg(c0 + 1);
+      }
+      tl_ = __ldg(p.targets + b_ * p.t_sb + s_ * p.t_ss + n_ * p.t_sn + lane);
+    }
+  };
+  float cx, cy, cx0, cy0, tl;
+  fetch((long long)blockIdx.x * 8 + warp, cx, cy, cx0, cy0, tl);
+
+  for (long long q = (long long)blockIdx.x * 8 + warp; q < total; q += nwarps) {
+    const int n = (int)(q % p.N);
+    const int s = (int)((q / p.N) % p.S);
+    const int b = (int)(q / ((long long)p.N * p.S));
+    const int bs = b * p.S + s;
+    AxisWindow ax[3], ay[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      if (l < p.L) {
+        const float inv = 1.f / (float)(1 << l);
+        ax[l].init(cx * inv, p.lvlW[l], R, p.pad_border);
+        ay[l].init(cy * inv, p.lvlH[l], R, p.pad_border);
+      }
+    }
+    // box origins: zeros -> the unclamped window corner (the TMA unit zero-fills what is off the map);
+    //              border -> the clamped corner (every clamped tap then lies inside the box)
+    int ox[3], oy[3];
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      if (l < p.L) {
+        ox[l] = p.pad_border ? min(max(ax[l].i0, 0), p.lvlW[l] - 1) : min(max(ax[l].i0, -G), p.lvlW[l]);
+        oy[l] = p.pad_border ? min(max(ay[l].i0, 0), p.lvlH[l] - 1) : min(max(ay[l].i0, -G), p.lvlH[l]);
+      }
+    }
+    __syncwarp();   // every lane is done with the boxes / Ts / Vs of the previous query
+    if (lane == 0) {
+      tma::mbar_expect_tx(bar, (uint32_t)((p.L - l_first) * BOX));
+#pragma unroll
+      for (int l = 0; l < 3; ++l)
+        if (l >= l_first && l < p.L) tma::load_box_4d(&maps.m[l], bar, mybox + l * BOXP, 0, ox[l], oy[l], bs);
+    }
+    Ts[lane] = BF16 ? round_bf16(tl) : tl;
+    const float tl_cur = tl, fx = cx - cx0, fy = cy - cy0;
+    float cx_n, cy_n, cx0_n, cy0_n, tl_n;
+    fetch(q + nwarps, cx_n, cy_n, cx0_n, cy0_n, tl_n);
+
+    float* op;
+    const float* pp = nullptr;
+    int corr_off = 0;
+    constexpr int NB = (WW + 31) / 32;
+    float pv[3][NB], pe0 = 0.f, pe1 = 0.f, pe2 = 0.f, pe3 = 0.f;   // position-embedding values of this token row, fetched up front
+    if (TOKENS) {
+      op = p.out + (((long long)b * p.N + n) * p.S + s) * p.D_tok;
+      pp = p.pos + ((long long)b * p.N + n) * p.D_tok;
+      corr_off = 32 + 2;
+#pragma unroll
+      for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) pv[l][k] = (l < p.L && lane + 32 * k < WW) ? __ldg(pp + corr_off + l * WW + lane + 32 * k) : 0.f;
+      pe0 = __ldg(pp + lane);
+      pe1 = lane < 2 ? __ldg(pp + 32 + lane) : 0.f;
+      pe2 = __ldg(pp + corr_off + p.L * WW + lane);
+      pe3 = (corr_off + p.L * WW + 32 + lane < p.D_tok) ? __ldg(pp + corr_off + p.L * WW + 32 + lane) : 0.f;
+    } else {
+      op = p.out + b * p.o_sb + s * p.o_ss + n * p.o_sn;
+#pragma unroll
+      for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int k = 0; k < NB; ++k) pv[l][k] = 0.f;
+    }
+    __syncwarp();
+    float4 t4[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t4[i] = *reinterpret_cast<const float4*>(Ts + 4 * i);
+
+    float acc0[ROWS0];
+    bool ok0[ROWS0];
+    if (!CL0) {
+      // level 0 in the caller's NCHW layout: per channel one warp-uniform plane pointer, gathers in flight with the boxes
+      const int Hl = p.lvlH[0], Wl = p.lvlW[0];
+      const int HW = Hl * Wl;
+      const float* F = p.fmaps + (long long)bs * 32 * HW;
+      int pos[ROWS0];
+#pragma unroll
+      for (int k = 0; k < ROWS0; ++k) {
+        const int idx = lane + 32 * k;
+        int gx = 0, gy = 0;
+        const bool vx = ax[0].tap(idx % G, gx), vy = ay[0].tap(idx / G, gy);
+        ok0[k] = idx < GG && vx && vy;
+        pos[k] = ok0[k] ? gy * Wl + gx : 0;
+        acc0[k] = 0.f;
+      }
+      float f[ROWS0][32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float* Fc = F + (long long)c * HW;
+#pragma unroll
+        for (int k = 0; k < ROWS0; ++k) f[k][c] = __ldg(Fc + pos[k]);
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float t = reinterpret_cast<const float*>(t4)[c];
+#pragma unroll
+        for (int k = 0; k < ROWS0; ++k) acc0[k] = fmaf(t, BF16 ? round_bf16(f[k][c]) : f[k][c], acc0[k]);
+      }
+    }
+
+    tma::mbar_wait(bar, phase);
+    phase ^= 1;
+
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      if (l < p.L) {
+        float acc[ROWS0];
+        bool ok[ROWS0];
+        if (l == 0 && !CL0) {
+#pragma unroll
+          for (int k = 0; k < ROWS0; ++k) { acc[k] = acc0[k]; ok[k] = ok0[k]; }
+        } else {
+          const uint8_t* box = mybox + l * BOXP;
+#pragma unroll
+          for (int k = 0; k < ROWS0; ++k) {
+            const int idx = lane + 32 * k;
+            int gx = 0, gy = 0;
+            const bool vx = ax[l].tap(idx % G, gx), vy = ay[l].tap(idx / G, gy);
+            ok[k] = idx < GG && vx && vy;
+            const int slot = ok[k] ? (gy - oy[l]) * G + (gx - ox[l]) : 0;
+            const uint8_t* line = box + slot * 128;
+            const int sw = slot & 7;
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 g = *reinterpret_cast<const float4*>(line + ((i ^ sw) << 4));
+              if (BF16) { g.x = round_bf16(g.x); g.y = round_bf16(g.y); g.z = round_bf16(g.z); g.w = round_bf16(g.w); }
+              a = fmaf(t4[i].x, g.x, a);
+              a = fmaf(t4[i].y, g.y, a);
+              a = fmaf(t4[i].z, g.z, a);
+              a = fmaf(t4[i].w, g.w, a);
+            }
+            acc[k] = a;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < ROWS0; ++k) {
+          const int idx = lane + 32 * k;
+          if (idx < GG) {
+            float v = acc[k];
+            if (BF16) v = round_bf16(v);
+            v = __fdiv_rn(v, p.sqrt_c);
+            if (BF16) v = round_bf16(v);
+            Vs[idx] = ok[k] ? v : 0.f;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < (WW + 31) / 32; ++k) {
+          const int o = lane + 32 * k;
+          if (o < WW) {
+            const int i = o / Wr, j = o - i * Wr;
+            float wx0, wx1, wy0, wy1;
+            ax[l].weights(i, wx0, wx1);
+            ay[l].weights(j, wy0, wy1);
+            const float* v = Vs + j * G + i;
+            float val = v[0] * (wx0 * wy0);
+            val += v[1] * (wx1 * wy0);
+            val += v[G] * (wx0 * wy1);
+            val += v[G + 1] * (wx1 * wy1);
+            const int d = corr_off + l * WW + o;
+            op[d] = val + pv[l][k];
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    if (TOKENS) {
+      const int w = lane & 15;                               // C_emb = 16: [pe_x (16) | pe_y (16)]
+      const float arg = __fmul_rn(lane >= 16 ? fy : fx, (float)(w & ~1) * (1000.0f / 16.f));
+      op[lane] = ((w & 1) ? cosf(arg) : sinf(arg)) + pe0;
+      if (lane < 2) op[32 + lane] = (lane ? fy : fx) + pe1;
+      const int feat_off = corr_off + p.L * WW;
+      op[feat_off + lane] = tl_cur + pe2;
+      if (feat_off + 32 + lane < p.D_tok) op[feat_off + 32 + lane] = pe3;          // zero pad + pos_emb
+      for (int d = feat_off + 64 + lane; d < p.D_tok; d += 32) op[d] = __ldg(pp + d);
+    }
+    cx = cx_n; cy = cy_n; cx0 = cx0_n; cy0 = cy0_n; tl = tl_n;
+  }
+}
+
+constexpr int tma_smem_bytes(int R) {
+  const int G = 2 * R + 2;
+  const int boxp = (G * G * 128 + 1023) & ~1023;
+  return 8 * 3 * boxp + 8 * 32 * 4 + 8 * 64 * 4 + 8 * 8;
+}
+
+template <int R, bool TOKENS>
+static int launch_c32_tma(const LookupParams& p, const TmaMaps& maps, int grid, cudaStream_t stream) {
+  const int smem = tma_smem_bytes(R);
+#define COMET_TMA_LAUNCH(BF, CL)                                                                               \
+  do {                                                                                                         \
+    COMET_CUDA(cudaFuncSetAttribute(corr_lookup_c32_tma_kernel<R, TOKENS, BF, CL>,                             \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                       \
+    corr_lookup_c32_tma_kernel<R, TOKENS, BF, CL><<<grid, 256, smem, stream>>>(maps, p);                       \
+  } while (0)
+  if (p.bf16) { if (p.cl0) COMET_TMA_LAUNCH(true, true); else COMET_TMA_LAUNCH(true, false); }
+  else { if (p.cl0) COMET_TMA_LAUNCH(false, true); else COMET_TMA_LAUNCH(false, false); }
+#undef COMET_TMA_LAUNCH
+  return launch_status("corr_lookup_c32_tma_kernel");
+}
+
+// 4-D tensor map over one channel-last level: dims (fastest first) {32 channels, W_l, H_l, BS}, box {32, G, G, 1},
+// 128-byte swizzle, zero fill outside the map.
+static int encode_level_map(CUtensorMap* tm, const float* base, int BS, int Hl, int Wl, int G) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return fail(COMET_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t gdim[4] = {32, (cuuint64_t)Wl, (cuuint64_t)Hl, (cuuint64_t)BS};
+  const cuuint64_t gstride[3] = {128, (cuuint64_t)Wl * 128, (cuuint64_t)Hl * Wl * 128};
+  const cuuint32_t box[4] = {32, (cuuint32_t)G, (cuuint32_t)G, 1};
+  const cuuint32_t estride[4] = {1, 1, 1, 1};
+  CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
+  return COMET_OK;
+}
+
 template <int R, bool TOKENS>
 static void launch_c32(const LookupParams& p, unsigned blocks, cudaStream_t stream) {
   if (p.bf16) corr_lookup_c32_kernel<R, TOKENS, true><<<blocks, 256, 0, stream>>>(p);
@@ -355,6 +661,27 @@ static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many queries for one launch");
   if (p.C == 32 && p.r >= 1 && p.r <= 3 && p.t_level_stride == 0 && ((uintptr_t)p.pyr % 16) == 0 &&
       (!p.cl0 || ((uintptr_t)p.fmaps % 16) == 0)) {
+    static int use_tma = -1;
+    if (use_tma < 0) {
+      const char* e = getenv("COMET_B200_DISABLE_TMA_LOOKUP");
+      use_tma = (!(e && atoi(e) == 1) && device_sm_count_if_sm100() > 0 && tensor_map_encoder() != nullptr) ? 1 : 0;
+    }
+    if (use_tma && p.cl0 && p.L <= 3 && total < (1LL << 40)) {
+      TmaMaps maps;
+      memset(&maps, 0, sizeof(maps));
+      const int G2 = 2 * p.r + 2;
+      for (int l = p.cl0 ? 0 : 1; l < p.L; ++l) {
+        const float* base = l == 0 ? p.fmaps : p.pyr + p.lvlOff[l];
+        int rc = encode_level_map(&maps.m[l], base, p.B * p.S, p.lvlH[l], p.lvlW[l], G2);
+        if (rc != COMET_OK) return rc;
+      }
+      const int sms = device_sm_count_if_sm100();
+      const long long want = (total + 7) / 8;
+      const int grid = (int)(want < sms ? want : sms);
+      if (p.r == 3) return launch_c32_tma<3, TOKENS>(p, maps, grid, stream);
+      if (p.r == 2) return launch_c32_tma<2, TOKENS>(p, maps, grid, stream);
+      return launch_c32_tma<1, TOKENS>(p, maps, grid, stream);
+    }
     if (p.r == 3) launch_c32<3, TOKENS>(p, (unsigned)blocks, stream);
     else if (p.r == 2) launch_c32<2, TOKENS>(p, (unsigned)blocks, stream);
     else launch_c32<1, TOKENS>(p, (unsigned)blocks, stream);

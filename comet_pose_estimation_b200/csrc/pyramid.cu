@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256, 4) pyramid_cl_fine_kernel(const float* __
 // (BS, H, W, C) and never copied; levels 1..L-1 are written channel-last.  One CTA per map, thread <-> (output
 // position, 4 channels): four 128-bit loads (one per 2x2 tap, lanes of a position read one contiguous line), one
 // 128-bit store; the level stays in shared memory for the next one.  Row / column H-1 of an odd map is never read.
-__global__ void __launch_bounds__(256, 4) pyramid_cl_in_kernel(const float4* __restrict__ in, float* __restrict__ pyr,
+__global__ void __launch_bounds__(256, 2) pyramid_cl_in_kernel(const float4* __restrict__ in, float* __restrict__ pyr,
                                                                int C4, int H, int W, int L, Levels lv) {
   extern __shared__ float4 tile4[];  // levels 1..L-1 back to back, dense (pos, C4)
   const long long map = blockIdx.x;
@@ -180,6 +180,51 @@ __global__ void __launch_bounds__(256, 4) pyramid_cl_in_kernel(const float4* __r
     in_off = out_off;
     out_off += items;
     Hi = Ho; Wi = Wo;
+  }
+}
+
+// Channel-last input at the fine tracker's shape (31x31, C = 32, L = 3): compile-time index math, two output items
+// (2 x 4 taps x 16 bytes) in flight per thread, level 1 kept in shared memory for level 2.
+__global__ void __launch_bounds__(256, 4) pyramid_cl_in_fine_kernel(const float4* __restrict__ in, float* __restrict__ pyr,
+                                                                    long long off1, long long off2) {
+  constexpr int W = 31, H1 = 15, H2 = 7, C4 = 8;
+  constexpr int N1 = H1 * H1 * C4, N2 = H2 * H2 * C4;   // float4 items per level
+  __shared__ float4 t1[N1];
+  const long long map = blockIdx.x;
+  const float4* src = in + map * (long long)(W * W * C4);
+  float4* d1 = reinterpret_cast<float4*>(pyr + off1) + map * (long long)N1;
+  float4* d2 = reinterpret_cast<float4*>(pyr + off2) + map * (long long)N2;
+  auto pool = [](const float4& a, const float4& b, const float4& c, const float4& d) {
+    return make_float4(((a.x + b.x) + (c.x + d.x)) * 0.25f, ((a.y + b.y) + (c.y + d.y)) * 0.25f,
+                       ((a.z + b.z) + (c.z + d.z)) * 0.25f, ((a.w + b.w) + (c.w + d.w)) * 0.25f);
+  };
+#pragma unroll 1
+  for (int i0 = threadIdx.x; i0 < N1; i0 += 512) {
+    float4 t[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = min(i0 + 256 * u, N1 - 1);
+      const int pos = i >> 3, c4 = i & 7;
+      const int yo = pos / H1, xo = pos - yo * H1;
+      const float4* s4 = src + ((2 * yo) * W + 2 * xo) * C4 + c4;
+      t[u][0] = __ldg(s4); t[u][1] = __ldg(s4 + C4); t[u][2] = __ldg(s4 + W * C4); t[u][3] = __ldg(s4 + (W + 1) * C4);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + 256 * u;
+      if (i < N1) {
+        const float4 v = pool(t[u][0], t[u][1], t[u][2], t[u][3]);
+        t1[i] = v;
+        d1[i] = v;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N2; i += 256) {
+    const int pos = i >> 3, c4 = i & 7;
+    const int yo = pos / H2, xo = pos - yo * H2;
+    const float4* s4 = t1 + ((2 * yo) * H1 + 2 * xo) * C4 + c4;
+    d2[i] = pool(s4[0], s4[C4], s4[H1 * C4], s4[(H1 + 1) * C4]);
   }
 }
 
@@ -234,6 +279,11 @@ extern "C" int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int 
     COMET_REQUIRE(fmaps && pyr, "null pointer");
     COMET_REQUIRE(((uintptr_t)fmaps % 16) == 0 && ((uintptr_t)pyr % 16) == 0, "channel-last pyramid needs 16-byte aligned buffers");
     Levels lv = make_levels(BS, C, H, W, L);
+    if (C == 32 && H == 31 && W == 31 && L == 3) {
+      pyramid_cl_in_fine_kernel<<<BS, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(fmaps), pyr, lv.off[1],
+                                                                      lv.off[2]);
+      return launch_status("pyramid_cl_in_fine_kernel");
+    }
     size_t items = 0;
     for (int l = 1; l < L; ++l) items += (size_t)lv.H[l] * lv.W[l];
     const size_t smem = items * C * sizeof(float);
