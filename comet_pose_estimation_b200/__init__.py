@@ -10,6 +10,8 @@ Python mirror of the reference interface for the path:
   (comet/models/track_modules/base_track_predictor.py:153-224)
 * :mod:`.base_track_predictor` -- drop-in ``BaseTrackerPredictor`` (same signature / state-dict keys) whose loop
   runs one fused kernel per iteration; :mod:`.update_former` is the torch plumbing it drives between iterations
+* :mod:`.refine_track` -- drop-in ``refine_track`` / ``compute_score_fn`` / ``ShallowEncoder`` (comet/models/refine_track.py,
+  blocks.py:114-196): the fine tracker's caller, feeding the kernels channels-last patch features without a copy
 
 All arithmetic runs in hand-written CUDA kernels behind the C ABI of ``include/comet_b200.h``
 (``libcomet_b200.so``).  PyTorch is used for device memory, streams and ``torch.distributed`` only.
@@ -29,5 +31,6 @@ from .utils import (  # noqa: F401
 from .track_tokens import TrackTokenizer, sampled_pos_emb, transformer_dim  # noqa: F401
 from .update_former import EfficientUpdateFormer  # noqa: F401
 from .base_track_predictor import BaseTrackerPredictor  # noqa: F401
+from .refine_track import ShallowEncoder, compute_score_fn, extract_patches, refine_track  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,166 @@
+"""Drop-in ``refine_track`` / ``compute_score_fn`` (comet/models/refine_track.py:26-278) and the patch encoder
+``ShallowEncoder`` (comet/models/track_modules/blocks.py:114-196) -- the caller of the hot path's second call site
+(SURVEY.md section 8f, rank 2/3).
+
+What is B200-specific here is the *data format between the caller and the path*:
+
+* the 31x31 patches are gathered in (b, n, s) order -- the order the fine tracker consumes -- so the reference's
+  1 GB ``rearrange("b s n c p q -> (b n) s c p q")`` copy of the encoder output (refine_track.py:122-123) disappears;
+* the encoder runs in ``torch.channels_last``; its output, viewed as (B*N, S, C, 31, 31), is the channels-last
+  view the fused kernels read zero-copy (one 128-byte line per position: ``_Pyramid.cl_input``).
+
+The encoder itself (three 3x3 convolutions on 16x16 / 8x8 / 4x4 maps, instance norm, bilinear resizes) is plain
+``torch.nn`` plumbing with the reference's parameter names, not a kernel of this round.  Results equal the
+reference's (tests/golden/refine.npz, produced by executing the reference).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class _ResidualBlock(nn.Module):
+    """comet/models/modules.py:39-117 with norm_fn="instance" (parameter-free norms); parameter names kept."""
+
+    def __init__(self, in_planes: int, planes: int, stride: int = 1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, kernel_size=3, padding=1, stride=stride)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, padding=1)
+        self.norm1 = nn.InstanceNorm2d(planes)
+        self.norm2 = nn.InstanceNorm2d(planes)
+        if stride == 1:
+            self.downsample = None
+        else:
+            self.norm3 = nn.InstanceNorm2d(planes)
+            self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride), self.norm3)
+
+    def forward(self, x):
+        y = F.relu(self.norm1(self.conv1(x)))
+        y = F.relu(self.norm2(self.conv2(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return F.relu(x + y)
+
+
+class ShallowEncoder(nn.Module):
+    """blocks.py:114-196 (``norm_fn="instance"``, the shipped configuration): state-dict keys ``conv1.*``,
+    ``layer1.{conv1,conv2,downsample.0}.*``, ``layer2.*``, ``conv2.*``."""
+
+    def __init__(self, input_dim=3, output_dim=32, stride=1, norm_fn="instance", cfg=None):
+        super().__init__()
+        if norm_fn != "instance":
+            raise NotImplementedError("only the shipped norm_fn='instance' configuration is mirrored")
+        self.stride = stride
+        self.norm_fn = norm_fn
+        self.in_planes = output_dim
+        self.norm1 = nn.InstanceNorm2d(output_dim)
+        self.norm2 = nn.InstanceNorm2d(output_dim * 2)  # constructed by the reference, never used
+        self.conv1 = nn.Conv2d(input_dim, output_dim, kernel_size=3, stride=2, padding=1)
+        self.layer1 = _ResidualBlock(output_dim, output_dim, stride=2)
+        self.layer2 = _ResidualBlock(output_dim, output_dim, stride=2)
+        self.conv2 = nn.Conv2d(output_dim, output_dim, kernel_size=1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x):
+        _, _, H, W = x.shape
+        x = F.relu(self.norm1(self.conv1(x)))
+        tmp = self.layer1(x)
+        x = x + F.interpolate(tmp, x.shape[-2:], mode="bilinear", align_corners=True)
+        tmp = self.layer2(tmp)
+        x = x + F.interpolate(tmp, x.shape[-2:], mode="bilinear", align_corners=True)
+        x = self.conv2(x) + x
+        return F.interpolate(x, (H // self.stride, W // self.stride), mode="bilinear", align_corners=True)
+
+
+def extract_patches(images: torch.Tensor, topleft: torch.Tensor, psize: int) -> torch.Tensor:
+    """``images`` (B,S,C,H,W), ``topleft`` (B,S,N,2) integer (x, y) corners -> patches (B*N*S, C, psize, psize) in
+    (b, n, s) order, channels-last memory format.  Same pixels as the reference's unfold + advanced indexing
+    (refine_track.py:71-111) without the (B*S, N, C, p, p) intermediate in (s, n) order."""
+    B, S, C, H, W = images.shape
+    N = topleft.shape[2]
+    dev = images.device
+    ar = torch.arange(psize, device=dev)
+    tl = topleft.permute(0, 2, 1, 3).long()                       # (B,N,S,2)
+    ys = tl[..., 1, None] + ar                                    # (B,N,S,p)
+    xs = tl[..., 0, None] + ar
+    bi = torch.arange(B, device=dev).view(B, 1, 1, 1, 1)
+    si = torch.arange(S, device=dev).view(1, 1, S, 1, 1)
+    img = images.permute(0, 1, 3, 4, 2)                            # (B,S,H,W,C) view
+    patches = img[bi, si, ys[..., :, None], xs[..., None, :]]     # (B,N,S,p,p,C)
+    return patches.reshape(B * N * S, psize, psize, C).permute(0, 3, 1, 2)  # NCHW shape, NHWC memory
+
+
+def refine_track(images, fine_fnet, fine_tracker, coarse_pred, pradius=15, sradius=2, compute_score=False):
+    """refine_track.py:26-171.  ``images`` (B,S,3,H,W); ``coarse_pred`` (B,S,N,2) pixels ->
+    (refined_tracks (B,S,N,2), score (B,S,N) | None)."""
+    B, S, N, _ = coarse_pred.shape
+    _, _, _, H, W = images.shape
+    psize = pradius * 2 + 1
+    query_points = coarse_pred[:, 0]
+
+    track_int = coarse_pred.floor().int()
+    track_frac = coarse_pred - track_int
+    topleft = track_int - pradius
+    topleft_BSN = topleft.clone()
+    topleft = topleft.clamp(0, H - psize)  # the reference assumes H == W here (refine_track.py:93-96)
+
+    with torch.no_grad():
+        patch_input = extract_patches(images, topleft, psize)
+    patch_feat = fine_fnet(patch_input)                            # (B*N*S, C_out, p, p), channels-last memory
+    C_out = patch_feat.shape[1]
+    patch_feat = patch_feat.reshape(B * N, S, C_out, psize, psize)  # a view: (b n) s c p q, no rearrange copy
+
+    patch_query_points = (track_frac[:, 0] + pradius).reshape(B * N, 2).unsqueeze(1)
+    fine_pred_track_lists, _, _, query_point_feat, _ = fine_tracker(
+        query_points=patch_query_points, fmaps=patch_feat, iters=6, return_feat=True, TRACKorPOSE=False)
+    fine_pred_track = fine_pred_track_lists[-1].clone()            # (B*N, S, 1, 2), relative to the patch corner
+
+    for idx in range(len(fine_pred_track_lists)):
+        lvl = fine_pred_track_lists[idx].reshape(B, N, S, 1, 2).permute(0, 2, 1, 3, 4).squeeze(-2)
+        fine_pred_track_lists[idx] = lvl + topleft_BSN
+    refined_tracks = fine_pred_track_lists[-1].clone()
+    refined_tracks[:, 0] = query_points
+
+    score = None
+    if compute_score:
+        score = compute_score_fn(query_point_feat, patch_feat, fine_pred_track, sradius, psize, B, N, S, C_out)
+    return refined_tracks, score
+
+
+def compute_score_fn(query_point_feat, patch_feat, fine_pred_track, sradius, psize, B, N, S, C_out):
+    """refine_track.py:174-278: std of the softmax similarity heat-map of the query feature against a
+    (2*sradius+1)^2 window of patch features.  Reproduces the reference's indexing exactly, including its quirk
+    (SURVEY.md A.6 iii): the k-th window is cut from patch map number ``b`` of the (b s n)-ordered list -- for
+    B == 1 always map 0 -- at the corner of the k-th track in (b n, s) order, then the list is re-read as (b, s, n)."""
+    ssize = sradius * 2 + 1
+    M = B * S * N
+    q = query_point_feat.reshape(B, N, C_out).unsqueeze(1).expand(-1, S - 1, -1, -1).reshape(B * (S - 1) * N, C_out)
+
+    corner = (fine_pred_track.floor().int() - sradius).clamp(0, psize - ssize).squeeze(2)   # (B*N, S, 2) = (x, y)
+    cx = corner[..., 0].flatten().long()          # k runs over (b n, s)
+    cy = corner[..., 1].flatten().long()
+    which = torch.arange(B, device=patch_feat.device)[:, None, None].expand(-1, S, N).reshape(-1)  # k over (b, s, n)
+
+    # map m of the (b s n)-ordered list = patch_feat[b*N + n, s]
+    m = which
+    mb, ms, mn = m // (S * N), (m // N) % S, m % N
+    ar = torch.arange(ssize, device=patch_feat.device)
+    rows = (cy[:, None] + ar)[:, :, None]         # (M, ss, 1)
+    cols = (cx[:, None] + ar)[:, None, :]         # (M, 1, ss)
+    win = patch_feat[(mb * N + mn)[:, None, None], ms[:, None, None], :, rows, cols]   # (M, ss, ss, C)
+    win = win.permute(0, 3, 1, 2).reshape(B, S, N, C_out, ssize, ssize)[:, 1:].reshape(B * (S - 1) * N, C_out, ssize * ssize)
+
+    sim = torch.einsum("mc,mcr->mr", q, win)
+    heat = torch.softmax(sim * (1.0 / C_out ** 0.5), dim=1)                                   # (M', ss*ss)
+    lin = torch.linspace(-1.0, 1.0, ssize, device=heat.device, dtype=heat.dtype)
+    gx = lin.repeat(ssize)                        # x varies fastest (kornia create_meshgrid, normalized)
+    gy = lin.repeat_interleave(ssize)
+    grid = torch.stack([gx, gy], -1)              # (ss*ss, 2)
+    mean = heat @ grid                            # spatial_expectation2d
+    var = heat @ (grid ** 2) - mean ** 2
+    std = torch.sqrt(torch.clamp(var, min=1e-10)).sum(-1)
+    score = std.reshape(B, S - 1, N)
+    return torch.cat([torch.ones_like(score[:, 0:1]), score], dim=1)

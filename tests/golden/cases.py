@@ -84,3 +84,16 @@ def tracker_case(seed, B, S, C, H, W, N, stride, down_ratio):
         [rng.uniform(1, (W - 2), (B, N)), rng.uniform(1, (H - 2), (B, N))], -1
     ).astype(F32) * F32(scale)
     return fmaps, q
+
+
+def refine_case(seed, B, S, N, HW):
+    """Images (B,S,3,HW,HW) ~ U[0,1) and a coarse track prediction (B,S,N,2) in pixels: query points inside the image,
+    later frames displaced by a few pixels; some tracks close to the border so the patch corner clamps."""
+    rng = np.random.default_rng(seed)
+    images = rng.random((B, S, 3, HW, HW)).astype(F32)
+    q = rng.uniform(3.0, HW - 4.0, (B, 1, N, 2))
+    q[:, :, 0] = [[2.25, HW - 3.5]]           # corner track: top-left patch corner clamps on both axes
+    coarse = (q + rng.normal(0.0, 2.0, (B, S, N, 2))).astype(F32)
+    coarse[:, 0] = q[:, 0].astype(F32)
+    coarse = np.clip(coarse, 0.0, HW - 1.001).astype(F32)
+    return images, coarse

@@ -186,6 +186,62 @@ def main():
                 out[f"{name}/sd/{k}"] = v.numpy()
     save("tracker", **out)
 
+    # ---- refine_track: patch extraction -> ShallowEncoder -> fine tracker -> score ----------------------
+    # kornia is not installed here: the two functions refine_track.py:20-21 imports are restated from their
+    # documented semantics -- create_meshgrid(h, w, normalized_coordinates=True) -> (1,h,w,2) with
+    # [...,0] = x, [...,1] = y in linspace(-1,1); spatial_expectation2d(heat (B,N,h,w), True) -> (B,N,2) = E[x], E[y].
+    def create_meshgrid(h, w, normalized_coordinates=True, device=None, dtype=torch.float32):
+        xs = torch.linspace(-1, 1, w, device=device, dtype=dtype) if normalized_coordinates else torch.arange(w, device=device, dtype=dtype)
+        ys = torch.linspace(-1, 1, h, device=device, dtype=dtype) if normalized_coordinates else torch.arange(h, device=device, dtype=dtype)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        return torch.stack([gx, gy], -1)[None]
+
+    def spatial_expectation2d(heat, normalized_coordinates=True):
+        b, n, h, w = heat.shape
+        g = create_meshgrid(h, w, normalized_coordinates, heat.device, heat.dtype).reshape(-1, 2)
+        flat = heat.reshape(b, n, -1)
+        return torch.stack([(flat * g[:, 0]).sum(-1), (flat * g[:, 1]).sum(-1)], -1)
+
+    kornia = types.ModuleType("kornia")
+    for name in ("kornia.utils", "kornia.utils.grid", "kornia.geometry", "kornia.geometry.subpix", "kornia.geometry.subpix.dsnt"):
+        sys.modules[name] = types.ModuleType(name)
+    sys.modules["kornia"] = kornia
+    sys.modules["kornia.utils.grid"].create_meshgrid = create_meshgrid
+    sys.modules["kornia.geometry.subpix.dsnt"].spatial_expectation2d = spatial_expectation2d
+    sys.modules["kornia.geometry.subpix"].dsnt = sys.modules["kornia.geometry.subpix.dsnt"]
+    import refine_track as rrt
+
+    out = {}
+    for name, case_kw, hidden in (("refine_small", dict(seed=51, B=1, S=3, N=5, HW=64), 32),):
+        torch.manual_seed(9)
+        fnet = blocks.ShallowEncoder(input_dim=3).eval()
+        ftr = btp.BaseTrackerPredictor(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=hidden,
+                                       depth=1, use_spaceatt=False, fine=True, cfg=cfg()).eval()
+        # random-init deltas of a few pixels per iteration make the 6-iteration loop chaotic (sin/cos(flow * 1e3)
+        # feeds back into the next delta), so that any two fp32 implementations diverge; damping the output head
+        # keeps the refinement contractive and the final tracks / scores comparable at a tight bar
+        for prm in ftr.updateformer.flow_head.parameters():
+            prm.mul_(0.02)
+        images, coarse = cases.refine_case(**case_kw)
+        toks = []
+        h = ftr.updateformer.register_forward_pre_hook(lambda mod, args: toks.append(args[0].detach().clone().numpy()))
+        refined, score = rrt.refine_track(t(images), fnet, ftr, t(coarse), compute_score=True)
+        h.remove()
+        out[name + "/digest"] = np.frombuffer(digest(images, coarse).encode(), dtype=np.uint8)
+        out[name + "/refined"] = refined.numpy()
+        out[name + "/score"] = score.numpy()
+        for i, x in enumerate(toks):
+            out[f"{name}/tok{i}"] = x
+        # the encoder alone on a handful of patches (pins ShallowEncoder separately from the loop)
+        pin = t(np.random.default_rng(52).random((4, 3, 31, 31)).astype(np.float32))
+        out[name + "/enc_in"] = pin.numpy()
+        out[name + "/enc_out"] = fnet(pin).numpy()
+        for k, v in fnet.state_dict().items():
+            out[f"{name}/fnet/{k}"] = v.numpy()
+        for k, v in ftr.state_dict().items():
+            out[f"{name}/ftr/{k}"] = v.numpy()
+    save("refine", **out)
+
 
 if __name__ == "__main__":
     main()

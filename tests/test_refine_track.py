@@ -1,0 +1,164 @@
+"""``refine_track`` (the fine tracker's caller: patch gather -> ShallowEncoder -> fine BaseTrackerPredictor -> score)
+against tensors produced by executing the reference (tests/golden/refine.npz).
+
+CPU part: the host logic -- patch extraction in (b, n, s) order, the channels-last encoder mirror with the
+reference's state dict, coordinate bookkeeping and ``compute_score_fn`` with the reference's indexing quirk -- driven
+by the numpy oracle as the fine tracker.  GPU part: the full drop-in (fused kernels on channels-last patch features),
+the "refined tracks / score" check-point of BASELINE.md section 5."""
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_to_max
+from oracle import comet_oracle as O
+
+NAME = "refine_small"
+CASE = dict(seed=51, B=1, S=3, N=5, HW=64)
+FINE = dict(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=32, depth=1, use_spaceatt=False, fine=True)
+
+
+# tokens of iteration i >= 1 contain sin/cos(flow * k * 1000/16): a 1e-6 px difference in the previous iteration's
+# coordinates is ~1e-3 in those channels (see test_tracker_loop.py); the tracks and scores themselves are held to 1e-4
+TOK_BAR = 5e-3
+
+
+def cfg():
+    return NS(track_conf=False, MODEL=NS(TRACK=NS(efficient_corr=False)))
+
+
+def modules(g):
+    from comet_pose_estimation_b200.base_track_predictor import BaseTrackerPredictor
+    from comet_pose_estimation_b200.refine_track import ShallowEncoder
+
+    fnet = ShallowEncoder(input_dim=3).eval()
+    ftr = BaseTrackerPredictor(cfg=cfg(), **FINE).eval()
+    for mod, tag in ((fnet, "fnet"), (ftr, "ftr")):
+        pre = f"{NAME}/{tag}/"
+        sd = {k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}
+        assert sorted(sd) == sorted(mod.state_dict().keys())  # same parameter names as the reference
+        mod.load_state_dict(sd, strict=True)
+    return fnet, ftr
+
+
+def test_shallow_encoder_matches_reference(golden):
+    g = golden("refine")
+    fnet, _ = modules(g)
+    x = torch.from_numpy(g[NAME + "/enc_in"])
+    with torch.no_grad():
+        y = fnet(x)
+        y_cl = fnet.to(memory_format=torch.channels_last)(x.contiguous(memory_format=torch.channels_last))
+    assert rel_to_max(y.numpy(), g[NAME + "/enc_out"]) < 1e-5
+    assert rel_to_max(y_cl.numpy(), g[NAME + "/enc_out"]) < 1e-5
+
+
+def test_patch_extraction_order_and_layout():
+    from comet_pose_estimation_b200.refine_track import extract_patches
+
+    images, coarse = cases.refine_case(**CASE)
+    B, S, N = coarse.shape[:3]
+    tl = (np.floor(coarse).astype(np.int32) - 15).clip(0, 64 - 31)
+    p = extract_patches(torch.from_numpy(images), torch.from_numpy(tl), 31)
+    assert p.shape == (B * N * S, 3, 31, 31)
+    assert p.permute(0, 2, 3, 1).is_contiguous()  # channels-last memory
+    for (b, n, s) in ((0, 0, 0), (0, 3, 2), (0, 4, 1)):
+        x0, y0 = tl[b, s, n]
+        want = images[b, s, :, y0:y0 + 31, x0:x0 + 31]
+        assert np.array_equal(p[(b * N + n) * S + s].numpy(), want)
+
+
+def test_refine_track_host_logic_with_oracle_tracker(golden):
+    """refine_track + compute_score_fn on CPU; the fine tracker is the numpy oracle driven by this package's torch
+    update transformer (reference weights)."""
+    from comet_pose_estimation_b200.refine_track import refine_track
+
+    g = golden("refine")
+    fnet, ftr = modules(g)
+    images, coarse = cases.refine_case(**CASE)
+    toks = []
+
+    def oracle_tracker(query_points, fmaps, iters, return_feat, TRACKorPOSE):
+        assert not TRACKorPOSE and return_feat
+        assert fmaps.permute(0, 1, 3, 4, 2).is_contiguous()  # channels-last view handed to the path, no copy
+        preds, feats, qfeat, tk = O.tracker_forward(
+            query_points.numpy(), fmaps.numpy(),
+            lambda x: ftr.updateformer(torch.from_numpy(x)).numpy(),
+            lambda d: ftr.ffeat_updater(ftr.norm(torch.from_numpy(d))).numpy(),
+            iters=iters, stride=1, corr_levels=3, corr_radius=3, latent_dim=32, fine=True, down_ratio=1)
+        toks.extend(tk)
+        return [torch.from_numpy(p) for p in preds], None, torch.from_numpy(feats), torch.from_numpy(qfeat), None
+
+    with torch.no_grad():
+        fnet = fnet.to(memory_format=torch.channels_last)
+        refined, score = refine_track(torch.from_numpy(images), fnet, oracle_tracker, torch.from_numpy(coarse),
+                                      compute_score=True)
+    assert rel_to_max(toks[0], g[NAME + "/tok0"]) < 1e-4      # patch gather + encoder + first tokens
+    for i in range(1, 6):
+        assert rel_to_max(toks[i], g[f"{NAME}/tok{i}"]) < TOK_BAR
+    assert refined.shape == g[NAME + "/refined"].shape
+    assert np.array_equal(refined[:, 0].numpy(), coarse[:, 0])  # frame 0 is pinned to the query points
+    assert rel_to_max(refined.numpy(), g[NAME + "/refined"]) < 1e-4
+    assert rel_to_max(score.numpy(), g[NAME + "/score"]) < 1e-4
+    assert float(score[:, 0].min()) == 1.0 and float(score[:, 0].max()) == 1.0
+
+
+def test_compute_score_indexing_quirk(golden):
+    """with B == 1 every score is computed from patch (n=0, s=0); randomising every other patch
+    leaves the score unchanged."""
+    from comet_pose_estimation_b200.refine_track import compute_score_fn
+
+    rng = np.random.default_rng(5)
+    B, N, S, C, P = 1, 4, 3, 32, 31
+    pf = torch.from_numpy(rng.standard_normal((B * N, S, C, P, P)).astype(np.float32))
+    qf = torch.from_numpy(rng.standard_normal((B, N, C)).astype(np.float32))
+    tr = torch.from_numpy(rng.uniform(3, 27, (B * N, S, 1, 2)).astype(np.float32))
+    a = compute_score_fn(qf, pf, tr, 2, P, B, N, S, C)
+    pf2 = pf.clone()
+    pf2[1:] = torch.from_numpy(rng.standard_normal((B * N - 1, S, C, P, P)).astype(np.float32))
+    pf2[0, 1:] = 0.0
+    b = compute_score_fn(qf, pf2, tr, 2, P, B, N, S, C)
+    assert torch.equal(a, b)
+    assert a.shape == (B, S, N)
+
+
+@pytest.mark.gpu
+def test_dropin_refine_track_matches_reference(golden):
+    from comet_pose_estimation_b200.refine_track import refine_track
+
+    g = golden("refine")
+    fnet, ftr = modules(g)
+    fnet = fnet.cuda().to(memory_format=torch.channels_last)
+    ftr = ftr.cuda()
+    images, coarse = cases.refine_case(**CASE)
+    toks, layouts = [], []
+    h = ftr.updateformer.register_forward_pre_hook(lambda mod, a: toks.append(a[0].detach().cpu().numpy()))
+    import comet_pose_estimation_b200.blocks as blk
+
+    orig = blk._Pyramid.__init__
+
+    def spy(self, fmaps, num_levels):
+        orig(self, fmaps, num_levels)
+        layouts.append(self.cl_input)
+
+    blk._Pyramid.__init__ = spy
+    # the golden comes from the reference on CPU (strict fp32); cuDNN would otherwise run the encoder's convolutions
+    # in TF32 (PyTorch's default), which is an encoder-precision choice outside the path under test
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            refined, score = refine_track(torch.from_numpy(images).cuda(), fnet, ftr, torch.from_numpy(coarse).cuda(),
+                                          compute_score=True)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+        blk._Pyramid.__init__ = orig
+        h.remove()
+    assert layouts == [True]  # the encoder output reached the kernels as a channels-last view, zero-copy
+    assert rel_to_max(toks[0], g[NAME + "/tok0"]) < 1e-4
+    for i in range(1, 6):
+        assert rel_to_max(toks[i], g[f"{NAME}/tok{i}"]) < TOK_BAR
+    assert rel_to_max(refined.cpu().numpy(), g[NAME + "/refined"]) < 1e-4   # "refined tracks" check-point, fp32 bar
+    assert np.array_equal(refined[:, 0].cpu().numpy(), coarse[:, 0])
+    assert rel_to_max(score.cpu().numpy(), g[NAME + "/score"]) < 1e-4       # "pred_score" check-point
