@@ -273,9 +273,11 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--fine-layout", default="nchw", choices=["nchw", "cl"],
-                    help="memory layout of the fine tracker's patch features: nchw = contiguous (B,S,C,H,W) as the "
-                         "reference's encoder returns them; cl = channels-last view (a torch.channels_last encoder)")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--fine-layout", default="cl", choices=["nchw", "cl"],
+                    help="memory layout of the fine tracker's patch features: cl = channels-last view, what this "
+                         "package's refine_track hands to the path (torch.channels_last encoder, zero-copy); nchw = "
+                         "contiguous (B,S,C,H,W) as the reference's own refine_track would hand over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -355,38 +357,80 @@ def main():
         if k in ab:
             kern[k]["algorithmic_MB"] = ab[k] / 1e6
             kern[k]["GBps"] = ab[k] / (kern[k]["ms_avg"] * 1e-3) / 1e9
-    ft = kern["fine_tokens"]
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this batch size, from the
-    # committed ncu --set full capture (profiles/traffic.json, written by scripts/ncu_traffic.py)
-    traffic, traffic_src = None, None
+    # roofline of the dominant kernel class (by device time inside the timed region).  Every class of this path is
+    # HBM-bound; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this batch size and layout
+    # from the committed ncu --set full captures (profiles/traffic.json, written by scripts/ncu_traffic.py).
+    KNAME = {
+        "fine_tokens": {"cl": "corr_lookup_c32_tma_kernel<R=3,TOKENS> (fine tracker: TMA-staged corr + lookup + tokens)",
+                        "nchw": "corr_lookup_c32_kernel<R=3,TOKENS> (fine tracker: fused corr + lookup + tokens)"},
+        "fine_pyramid": {"cl": "pyramid_cl_in_fine_kernel (fine tracker: channel-last pyramid)",
+                         "nchw": "pyramid_cl_fine_kernel (fine tracker: NCHW -> channel-last pyramid)"},
+        "coarse_tokens": {"cl": "tc_pre_kernel + corr_tc_kernel (coarse tracker: tcgen05 corr + lookup + tokens)"},
+        "coarse_pyramid": {"cl": "tc_prepare_kernel (coarse pyramid + bf16 hi/lo split)"},
+    }
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)["fine_tokens"]
-        if tj.get("batch") == Q:
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+            tj_all = json.load(f)
     except Exception:
-        pass
-    roof = {"bound": "hbm", "kernel": "corr_lookup_c32_kernel<R=3,TOKENS> (fine tracker: fused corr + lookup + tokens)",
-            "achieved": ft["GBps"], "peak": peak, "unit": "GB/s", "frac": ft["GBps"] / peak, "traffic": traffic,
-            "traffic_source": traffic_src, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": ab["fine_tokens"], "ms_per_launch": ft["ms_avg"],
-            "dominant_by_time": dom,
-            "note": "algorithmic bytes = window neighbourhoods (SURVEY 8d, 194 MB/sequence definition); traffic above "
-                    "them is the 32-byte NCHW level-0 window rows fetched at DRAM granularity"}
-    # correlation on the tensor pipe (coarse tracker): FLOPs as the reference defines them (all pyramid levels,
-    # one pass) and as executed (3 bf16 passes for fp32 parity, 86 tiles of 64 positions incl. 48 padded columns)
+        tj_all = {}
+
+    def roofline_of(cls):
+        k = kern[cls]
+        tj = tj_all.get(f"{cls}/{args.fine_layout}") or tj_all.get(cls) or {}
+        traffic = tj.get("dram_bytes_per_launch") if tj.get("batch") == Q else None
+        names = KNAME.get(cls, {})
+        return {"bound": "hbm", "kernel": names.get(args.fine_layout, names.get("cl", cls)),
+                "achieved": k.get("GBps"), "peak": peak, "unit": "GB/s",
+                "frac": (k["GBps"] / peak) if "GBps" in k else None, "traffic": traffic,
+                "traffic_source": tj.get("source") if traffic else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab.get(cls), "ms_per_launch": k["ms_avg"]}
+
+    roof = roofline_of(dom if dom in ab else "fine_tokens")
+    roof["dominant_by_time"] = dom
+    roof["note"] = ("algorithmic bytes: fine_tokens = window neighbourhoods + target + coords + token row (SURVEY 8d, the "
+                    "194 MB/sequence definition); fine_pyramid = level 0 read once + levels 1-2 written; coarse_tokens = "
+                    "SURVEY 8d compulsory traffic (fp32 maps + targets + coords + tokens)")
+    rooflines = {c: roofline_of(c) for c in kern if c in ab}
+    # correlation on the tensor pipe (coarse tracker): FLOPs as the reference defines them (dense, all pyramid levels,
+    # one pass).  The kernel issues 3 bf16 passes (fp32 parity) but only for the band of map rows each sorted query
+    # tile touches (~45 % of the tiles at this query distribution), and it is bounded by the HBM read of the packed
+    # pyramid, not by the tensor pipe.
     ct = kern["coarse_tokens"]
     flop_alg = 2.0 * Q * COARSE["S"] * COARSE["N"] * COARSE["C"] * 5456
-    flop_exec = 3 * 2.0 * Q * COARSE["S"] * COARSE["N"] * COARSE["C"] * 5504
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             tpeak = float(json.load(f)["bf16_tflops_sustained"])
     except Exception:
         tpeak = 1400.0
     tensor = {"bound": "tensor", "kernel": "corr_tc_kernel (coarse tracker: tcgen05 correlation + lookup + tokens)",
-              "achieved": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12, "executed_TFLOPs": flop_exec / (ct["ms_avg"] * 1e-3) / 1e12,
-              "peak": tpeak, "unit": "TFLOP/s", "frac": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12 / tpeak,
-              "frac_executed": flop_exec / (ct["ms_avg"] * 1e-3) / 1e12 / tpeak, "ms_per_launch": ct["ms_avg"]}
+              "achieved": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+              "frac": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12 / tpeak, "ms_per_launch": ct["ms_avg"],
+              "note": "reference-defined dense FLOPs / time; ms_per_launch includes the plan + token pre-kernel"}
+
+    # ---- the other memory layout of the fine tracker's patch features, same run (reported, not the headline) ----
+    variants = {}
+    if not args.no_variants:
+        other = "nchw" if args.fine_layout == "cl" else "cl"
+        f0 = devin["fine"]["fmaps"]
+        if other == "nchw":
+            alt = f0.contiguous()
+        else:
+            alt = f0.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        alt_in = {"coarse": devin["coarse"], "fine": dict(devin["fine"], fmaps=alt)}
+        for _ in range(args.warmup):
+            hp.run(alt_in)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            hp.run(alt_in)
+        e1.record()
+        barrier()
+        ms_alt = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        variants["fine_" + other] = {"value": Q * world / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt,
+                                     "what": "same step with the fine tracker's patch features " +
+                                             ("NCHW-contiguous (the reference encoder's own output layout)"
+                                              if other == "nchw" else "as a channels-last view")}
+        del alt, alt_in
 
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------
     e2e = None
@@ -435,9 +479,12 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
                        "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
-                       "fine_layout": args.fine_layout,
+                       "fine_layout": args.fine_layout + (" (channels-last view of the patch encoder output, as "
+                                                          "comet_pose_estimation_b200.refine_track produces it)"
+                                                          if args.fine_layout == "cl" else " (contiguous)"),
                        "l2": "inputs per step exceed L2 (fine patch features: %.1f GB)" % (Q * 1.008)},
-            "roofline": roof, "roofline_tensor": tensor, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roof, "rooflines": rooflines, "roofline_tensor": tensor, "variants": variants,
+            "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "kernels": kern,
             "tensor_path": bool(cb._lib.lib.comet_has_tensor_path()),
         }
