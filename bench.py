@@ -141,7 +141,8 @@ def algorithmic_bytes(Q):
     per_q = taps * f["C"] * 4 + f["C"] * 4 + 8 + tdf * 4 + tdf * 4 / f["S"]
     fine = Q * f["P"] * f["S"] * per_q
     pyr_c = Q * c["S"] * c["C"] * 4 * (64 * 64 + 2 * (32 * 32 + 16 * 16 + 8 * 8) + 4 * 4)
-    pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (31 * 31 + 15 * 15 + 7 * 7)   # read level 0 once, write levels 1-2
+    # read the 30x30 positions of level 0 that floor-mode pooling uses, write levels 1-2
+    pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (30 * 30 + 15 * 15 + 7 * 7)
     return dict(coarse_tokens=coarse, fine_tokens=fine, coarse_pyramid=pyr_c, fine_pyramid=pyr_f)
 
 

@@ -183,48 +183,101 @@ __global__ void __launch_bounds__(256, 2) pyramid_cl_in_kernel(const float4* __r
   }
 }
 
-// Channel-last input at the fine tracker's shape (31x31, C = 32, L = 3): compile-time index math, two output items
-// (2 x 4 taps x 16 bytes) in flight per thread, level 1 kept in shared memory for level 2.
-__global__ void __launch_bounds__(256, 4) pyramid_cl_in_fine_kernel(const float4* __restrict__ in, float* __restrict__ pyr,
-                                                                    long long off1, long long off2) {
-  constexpr int W = 31, H1 = 15, H2 = 7, C4 = 8;
-  constexpr int N1 = H1 * H1 * C4, N2 = H2 * H2 * C4;   // float4 items per level
-  __shared__ float4 t1[N1];
-  const long long map = blockIdx.x;
-  const float4* src = in + map * (long long)(W * W * C4);
-  float4* d1 = reinterpret_cast<float4*>(pyr + off1) + map * (long long)N1;
-  float4* d2 = reinterpret_cast<float4*>(pyr + off2) + map * (long long)N2;
+// Channel-last input at the fine tracker's shape (31x31, C = 32, L = 3).  The register version of this kernel kept
+// only ~110 KB per SM in flight (every in-flight byte of a load lives in a register) and reached 81 % of the DRAM
+// rate; here the map streams through shared memory instead: two input rows (2 x 31 positions x 128 B = 7936 B,
+// contiguous in a channel-last map) are one bulk async copy (cp.async.bulk -> mbarrier), ten of them in flight per
+// CTA, two persistent CTAs per SM.  Threads pool a landed row pair (4 x LDS.128, conflict-free), keep level 1 in shared
+// memory for level 2 and write both levels with 128-bit stores.
+namespace bulk {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();  // a protocol bug must fail fast, not hang the device
+  }
+}
+__device__ __forceinline__ void copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+}  // namespace bulk
+
+constexpr int PF_STAGES = 10;
+constexpr int PF_ROWPAIR = 2 * 31 * 8;                 // float4 per row pair
+constexpr int PF_N1 = 15 * 15 * 8, PF_N2 = 7 * 7 * 8;  // float4 items per pooled level
+constexpr int PF_SMEM = PF_STAGES * PF_ROWPAIR * 16 + PF_N1 * 16 + PF_STAGES * 8;
+
+__global__ void __launch_bounds__(128, 2) pyramid_cl_in_fine_kernel(const float4* __restrict__ in, float* __restrict__ pyr,
+                                                                    long long off1, long long off2, int nmaps) {
+  constexpr int W = 31, H1 = 15, H2 = 7, C4 = 8, RP = 15;   // RP: row pairs per map (row 30 is never read)
+  extern __shared__ __align__(128) float4 pf_smem[];
+  float4* ring = pf_smem;                                   // [PF_STAGES][PF_ROWPAIR]
+  float4* t1 = ring + PF_STAGES * PF_ROWPAIR;               // level 1 of the current map
+  uint64_t* full = reinterpret_cast<uint64_t*>(t1 + PF_N1);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < PF_STAGES; ++i) bulk::mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_maps = (nmaps - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // maps blockIdx.x, +gridDim.x, ...
+  const long long total = (long long)my_maps * RP;
+  auto issue = [&](long long g) {   // row pair g of this CTA's sequence -> stage g % PF_STAGES
+    const long long k = g / RP;
+    const int rp = (int)(g - k * RP);
+    const long long map = blockIdx.x + k * gridDim.x;
+    const int st = (int)(g % PF_STAGES);
+    bulk::mbar_expect_tx(&full[st], PF_ROWPAIR * 16);
+    bulk::copy_g2s(ring + st * PF_ROWPAIR, in + (map * (W * W) + (long long)rp * 2 * W) * C4, PF_ROWPAIR * 16, &full[st]);
+  };
+  if (tid == 0)
+    for (long long g = 0; g < PF_STAGES && g < total; ++g) issue(g);
+
   auto pool = [](const float4& a, const float4& b, const float4& c, const float4& d) {
     return make_float4(((a.x + b.x) + (c.x + d.x)) * 0.25f, ((a.y + b.y) + (c.y + d.y)) * 0.25f,
                        ((a.z + b.z) + (c.z + d.z)) * 0.25f, ((a.w + b.w) + (c.w + d.w)) * 0.25f);
   };
-#pragma unroll 1
-  for (int i0 = threadIdx.x; i0 < N1; i0 += 512) {
-    float4 t[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = min(i0 + 256 * u, N1 - 1);
-      const int pos = i >> 3, c4 = i & 7;
-      const int yo = pos / H1, xo = pos - yo * H1;
-      const float4* s4 = src + ((2 * yo) * W + 2 * xo) * C4 + c4;
-      t[u][0] = __ldg(s4); t[u][1] = __ldg(s4 + C4); t[u][2] = __ldg(s4 + W * C4); t[u][3] = __ldg(s4 + (W + 1) * C4);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = i0 + 256 * u;
-      if (i < N1) {
-        const float4 v = pool(t[u][0], t[u][1], t[u][2], t[u][3]);
-        t1[i] = v;
-        d1[i] = v;
+  const int xo = tid >> 3, c4 = tid & 7;    // this thread's level-1 item within a row (tid < 120)
+  long long g = 0;
+  for (int k = 0; k < my_maps; ++k) {
+    const long long map = blockIdx.x + (long long)k * gridDim.x;
+    float4* d1 = reinterpret_cast<float4*>(pyr + off1) + map * PF_N1;
+    float4* d2 = reinterpret_cast<float4*>(pyr + off2) + map * PF_N2;
+    for (int rp = 0; rp < RP; ++rp, ++g) {
+      const int st = (int)(g % PF_STAGES);
+      bulk::mbar_wait(&full[st], (uint32_t)((g / PF_STAGES) & 1));
+      if (tid < H1 * C4) {
+        const float4* s4 = ring + st * PF_ROWPAIR + (2 * xo) * C4 + c4;
+        const float4 v = pool(s4[0], s4[C4], s4[W * C4], s4[(W + 1) * C4]);
+        t1[rp * (H1 * C4) + tid] = v;
+        d1[rp * (H1 * C4) + tid] = v;
       }
+      __syncthreads();   // the stage is drained (and this level-1 row is visible)
+      if (tid == 0 && g + PF_STAGES < total) issue(g + PF_STAGES);
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < N2; i += 256) {
-    const int pos = i >> 3, c4 = i & 7;
-    const int yo = pos / H2, xo = pos - yo * H2;
-    const float4* s4 = t1 + ((2 * yo) * H1 + 2 * xo) * C4 + c4;
-    d2[i] = pool(s4[0], s4[C4], s4[H1 * C4], s4[(H1 + 1) * C4]);
+    for (int i = tid; i < PF_N2; i += 128) {
+      const int pos = i >> 3, cc = i & 7;
+      const int yo = pos / H2, xx = pos - yo * H2;
+      const float4* s4 = t1 + ((2 * yo) * H1 + 2 * xx) * C4 + cc;
+      d2[i] = pool(s4[0], s4[C4], s4[H1 * C4], s4[(H1 + 1) * C4]);
+    }
+    __syncthreads();     // level 2 has read t1 before the next map overwrites it
   }
 }
 
@@ -280,8 +333,16 @@ extern "C" int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int 
     COMET_REQUIRE(((uintptr_t)fmaps % 16) == 0 && ((uintptr_t)pyr % 16) == 0, "channel-last pyramid needs 16-byte aligned buffers");
     Levels lv = make_levels(BS, C, H, W, L);
     if (C == 32 && H == 31 && W == 31 && L == 3) {
-      pyramid_cl_in_fine_kernel<<<BS, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(fmaps), pyr, lv.off[1],
-                                                                      lv.off[2]);
+      int sms = device_sm_count_if_sm100();
+      if (sms <= 0) sms = 148;
+      const int grid = BS < 2 * sms ? BS : 2 * sms;
+      static bool attr_set = false;
+      if (!attr_set) {
+        COMET_CUDA(cudaFuncSetAttribute(pyramid_cl_in_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+        attr_set = true;
+      }
+      pyramid_cl_in_fine_kernel<<<grid, 128, PF_SMEM, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(fmaps), pyr,
+                                                                             lv.off[1], lv.off[2], BS);
       return launch_status("pyramid_cl_in_fine_kernel");
     }
     size_t items = 0;

@@ -11,7 +11,7 @@ try:
     print("value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", d["e2e"] and round(d["e2e"]["value"], 1), "launches", d["gpu_launches"])
     for k, v in d["kernels"].items():
         print(" ", k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items()})
-    print(" roofline", {k: d["roofline"][k] for k in ("achieved", "frac")}, "tensor", {k: d["roofline_tensor"][k] for k in ("achieved", "frac", "frac_executed", "ms_per_launch")})
+    print(" roofline", {k: d["roofline"][k] for k in ("achieved", "frac")}, "tensor", {k: d["roofline_tensor"][k] for k in ("achieved", "frac", "ms_per_launch")}, "variants", {k: round(v["value"], 1) for k, v in d.get("variants", {}).items()})
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/bench_quick.log").read()[-3000:])
 PY

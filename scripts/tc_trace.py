@@ -19,8 +19,8 @@ t0 = int(s[s > 0].min())
 print("debug", os.environ.get("COMET_TC_DEBUG", "0"))
 print("tile  prod_issue | mma_start mma_end | epi_full epi_rel   (clk since first event)")
 print('stager per job: [A start, A done] [rest done] [last WU got, last WU done]')
-for j in range(6):
-    print(j, [int(x) - t0 if x else -1 for x in s[3, j*4:(j+1)*4].flatten().tolist()])
-for i in list(range(0, 40)):
+for j in range(8):
+    print("stager job", j, [int(x) - t0 if x else -1 for x in s[3, j*4:(j+1)*4].flatten().tolist()])
+for i in list(range(0, 64)):
     r = [int(s[0, i, 0]), int(s[1, i, 0]), int(s[1, i, 1]), int(s[2, i, 0]), int(s[2, i, 1])]
     print(f"{i:3d}  " + "  ".join(f"{(x - t0) if x else -1:8d}" for x in r))
