@@ -38,6 +38,7 @@ constexpr int TILE_N = 64;     // positions per accumulator tile
 constexpr int NSTAGE = 3;      // B-tile ring
 constexpr int NACC = 4;        // accumulator ring (4 x 64 TMEM columns)
 constexpr int P_TOTAL = 5504;  // packed positions per (frame, channel)
+constexpr int NTILES = 86;     // P_TOTAL / TILE_N tiles of 64 positions per frame
 constexpr int MAX_WR = 9;      // 2*4+1
 constexpr int THREADS = 320;   // 10 warps: TMA | MMA | 4 epilogue | 4 stager
 
@@ -49,8 +50,13 @@ constexpr int B_TILE_BYTES = TILE_N * KC * 2;   // 16 KB per hi / lo
 constexpr int STAGE_BYTES = 2 * B_TILE_BYTES;   // hi + lo
 constexpr int DUMP_STRIDE = 68;                 // floats per private accumulator row (64 + 4: conflict-free STS.128)
 constexpr int DUMP_BYTES = TILE_M * DUMP_STRIDE * 4;
-constexpr int WIN_STRIDE = 84;                  // floats per staged window row (81 + 3, 16-byte aligned rows)
-constexpr int WIN_BYTES = TILE_M * WIN_STRIDE * 4;
+// staged windows: per (buffer, epilogue warp) a [83 entries][33] float array -- entry-major, one column per query lane
+// (+1 padding), so that both the epilogue (lanes write the same entry of different queries) and the stager (lanes read
+// different entries of one query) are bank-conflict free.  Entries 81 / 82 carry the window rows the job owns.
+constexpr int WIN_LD = 33;
+constexpr int WIN_JLO = 81, WIN_JHI = 82;
+constexpr int WIN_WARP = 2740;                  // 83 * 33 = 2739 floats, rounded to a 16-byte multiple
+constexpr int WIN_BYTES = 4 * WIN_WARP * 4;
 constexpr int NWIN = 2;                         // window buffers (epilogue -> stager hand-off)
 constexpr int ROWOFF_BYTES = 2 * TILE_M * 8;      // per query: element offset of its pos_emb row and of its output row
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + DUMP_BYTES + NWIN * WIN_BYTES + ROWOFF_BYTES + 512;
@@ -102,6 +108,7 @@ struct Params {
   float* vol[5]; int volume_mode;                      // volume mode: per-level (BS,N,H_l,W_l)
   int B, S, N, L, r, npass, bf16;
   int BS, mtiles, npad, nsplit, npyr, nchunk, njobs;
+  const uint8_t* split; // packed pyramid (tile-major, pre-swizzled bf16 hi/lo), written by tc_prepare_kernel
   const int* perm;      // [BS][npad]: query index of sorted slot (or -1), written by tc_plan_kernel
   const JobRec* jobs;   // [njobs]
   float inv_sqrt_c;
@@ -158,6 +165,10 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -395,6 +406,7 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
 }
 
 // ------------------------------------------------------------------ the kernel
+template <int R, bool BF16, bool VOLUME>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   // dynamic shared memory is the only shared allocation of this kernel, so it starts 1024-byte aligned (SWIZZLE_128B
@@ -403,7 +415,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint8_t* sB = smem;                                                   // NSTAGE x [hi 16 KB][lo 16 KB]
   float* dump = reinterpret_cast<float*>(sB + NSTAGE * STAGE_BYTES);   // private accumulator rows
   float* win = dump + TILE_M * DUMP_STRIDE;                            // staged window rows
-  long long* rowoff = reinterpret_cast<long long*>(win + NWIN * TILE_M * WIN_STRIDE);  // [2][TILE_M]
+  long long* rowoff = reinterpret_cast<long long*>(win + NWIN * 4 * WIN_WARP);  // [2][TILE_M]
   uint64_t* bars = reinterpret_cast<uint64_t*>(rowoff + 2 * TILE_M);
   uint64_t* full = bars;                  // [NSTAGE]  TMA -> MMA
   uint64_t* empty = full + NSTAGE;        // [NSTAGE]  MMA -> TMA
@@ -456,9 +468,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             if (p.debug & 64) {
               mbar_arrive(&full[stage]);
             } else {
-              mbar_expect_tx(&full[stage], STAGE_BYTES);
-              tma_load_2d(&tmap, &full[stage], dst, t * TILE_N, jr.bs * KC);
-              tma_load_2d(&tmap, &full[stage], dst + B_TILE_BYTES, t * TILE_N, (p.BS + jr.bs) * KC);
+              // autocast mode issues the hi x hi pass only: fetch just the hi half of the stage
+              const uint32_t nbytes = BF16 ? B_TILE_BYTES : STAGE_BYTES;
+              mbar_expect_tx(&full[stage], nbytes);
+              bulk_load(dst, p.split + ((long long)jr.bs * NTILES + t) * STAGE_BYTES, nbytes, &full[stage]);
             }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
@@ -513,14 +526,20 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     }
   } else if (warp < 6) {
     // ===================== epilogue warps (2..5) =====================
+    // One lane = one query (TMEM lane).  Per pyramid level the lane precomputes, once, everything that does not
+    // depend on the map row: clamped column offsets of its x window, horizontal lerp weights with the zero-padding
+    // mask and the 1/sqrt(C) scale folded in, and (level 0) which 16-byte groups of a row it must park.  Per needed
+    // tile the work is then: tcgen05.ld -> park the row (predicated STS.128) -> per map row 10 LDS + 18 FMA
+    // (horizontal) + 9 x (FMA + STS) (vertical lerp with the previous row, written to the staged window).
     const int wq = warp & 3;                    // TMEM lane quarter this warp may access
     const int q = 32 * wq + lane;               // TMEM lane == sorted query slot in the tile
     float* myrow = dump + q * DUMP_STRIDE;
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
-    const int Wr = 2 * p.r + 1;
+    constexpr int Wr = 2 * R + 1;
     uint32_t acc = 0, acc_phase = 0, wu = 0;  // wu: window units handed to the stager so far
     int tcount = 0;
-    float* mywin = win;
+    float* wcol = win + lane;                 // this lane's column of the warp's staged window: entry e at wcol[e * WIN_LD]
+    float* wwarp = win;
 
     // software pipeline over jobs: the record of job i+2 and the query (slot -> index -> coordinates) of job i+1 are
     // fetched while job i is processed, so no dependent global load sits between two jobs
@@ -552,41 +571,66 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         const int tfirst = jr.t0(sg), tend = jr.t1(sg);
         const TileInfo t0i = tile_info(tfirst);
         const int level = t0i.level, Hl = t0i.H, Wl = t0i.W;
+        const bool is0 = level == 0;
         // ---- window geometry of this query at this level; row band of the whole warp ----
         int x0, y0;
         float fx, fy;
-        level_y(cy, level, p.r, y0, fy);
+        level_y(cy, level, R, y0, fy);
         {
           const float inv = 1.f / (float)(1 << level);
           const float px = fminf(fmaxf(cx * inv, -1.0e6f), 1.0e6f);
           const float flx = floorf(px);
           fx = px - flx;
-          x0 = (int)flx - p.r;
+          x0 = (int)flx - R;
         }
-        int rl = max(y0, 0), rh = min(y0 + Wr, Hl - 1);   // map rows this query touches
-        if (!valid || rl > rh) { rl = BIG; rh = -BIG; }
+        // x window: clamped column offsets; lerp weights with the zero-padding mask (and, in fp32 mode, the scale)
+        int xo[Wr + 1];
+        float wa[Wr], wb[Wr];
+        uint32_t xmask = 0, dmask = 0;
+#pragma unroll
+        for (int i = 0; i <= Wr; ++i) {
+          const int xi = x0 + i;
+          if (xi >= 0 && xi < Wl) xmask |= 1u << i;
+          xo[i] = min(max(xi, 0), Wl - 1);
+        }
+        // map rows this query touches; a window that misses the map (in x or in y) touches none -- such a lane never
+        // reads its parked row (a clamped offset could otherwise hit stale shared memory)
+        int rl = max(y0, 0), rh = min(y0 + Wr, Hl - 1);
+        if (!valid || rl > rh || xmask == 0) { rl = BIG; rh = -BIG; }
         const int wlo = __reduce_min_sync(0xffffffffu, rl), whi = __reduce_max_sync(0xffffffffu, rh);
-        const bool is0 = level == 0;
+#pragma unroll
+        for (int i = 0; i < Wr; ++i) {
+          const float sc = BF16 ? 1.f : p.inv_sqrt_c;
+          wa[i] = ((xmask >> i) & 1) ? (1.f - fx) * sc : 0.f;
+          wb[i] = ((xmask >> (i + 1)) & 1) ? fx * sc : 0.f;
+        }
+        if (is0) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (4 * k + 3 >= x0 && 4 * k <= x0 + Wr) dmask |= 1u << k;
+        }
         // window rows ("tops") written while streaming: [ta, tb_]; top = H-1 is finished at the end of the level
         const int ta = is0 ? jr.own_lo : -BIG;
         const int tb_ = is0 ? min(jr.own_hi, Hl - 2) : Hl - 2;
-        float hprev[MAX_WR];
+        float hprev[Wr];
 #pragma unroll
-        for (int i = 0; i < MAX_WR; ++i) hprev[i] = 0.f;
-        if (!p.volume_mode && !(p.debug & 1)) {
-          // claim a window buffer and clear it (entries whose rows are off the map stay 0)
+        for (int i = 0; i < Wr; ++i) hprev[i] = 0.f;
+        if (!VOLUME && !(p.debug & 1)) {
+          // claim a window buffer and clear it cooperatively (entries whose rows are off the map stay 0)
           const uint32_t wbuf = wu % NWIN;
           mbar_wait(&win_empty[wbuf * 4 + wq], ((wu / NWIN) & 1) ^ 1, p.status, 7);
-          mywin = win + (wbuf * TILE_M + q) * WIN_STRIDE;
-#pragma unroll
-          for (int i = 0; i < WIN_STRIDE; i += 4) *reinterpret_cast<float4*>(mywin + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+          wwarp = win + (wbuf * 4 + wq) * WIN_WARP;
+          wcol = wwarp + lane;
+#pragma unroll 1
+          for (int k = lane * 4; k < WIN_WARP; k += 128) *reinterpret_cast<float4*>(wwarp + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+          __syncwarp();
         }
 
         for (int t = tfirst; t < tend; ++t) {
           const TileInfo ti = tile_info(t);
           const int ylast = ti.y_first + ti.rows - 1;
           // does any query of this warp touch the rows of this tile?  (warp-uniform)
-          const bool wneed = p.volume_mode || ((ti.y_first <= whi && ylast >= wlo) && !(p.debug & 32));
+          const bool wneed = VOLUME || ((ti.y_first <= whi && ylast >= wlo) && !(p.debug & 32));
           mbar_wait(&acc_full[acc], acc_phase, p.status, 5);
           if (warp == 2 && lane == 0) stamp(p, 2, tcount, 0);
           float v[64];
@@ -603,7 +647,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           ++tcount;
           if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
 
-          if (p.volume_mode) {
+          if (VOLUME) {
             if (valid) {
               const int cols = ti.level == 4 ? 16 : 64;
               const int HW = ti.W * ti.W;
@@ -612,7 +656,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
               for (int i = 0; i < 64; i += 4) {
                 if (i < cols) {
                   float4 o;
-                  if (p.bf16) {
+                  if (BF16) {
                     o = make_float4(round_bf16(round_bf16(v[i]) * p.inv_sqrt_c), round_bf16(round_bf16(v[i + 1]) * p.inv_sqrt_c),
                                     round_bf16(round_bf16(v[i + 2]) * p.inv_sqrt_c), round_bf16(round_bf16(v[i + 3]) * p.inv_sqrt_c));
                   } else {
@@ -624,58 +668,55 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             }
             continue;
           }
-          if (p.debug & 1) continue;
+          if ((p.debug & 1) || !wneed) continue;
 
-          if (wneed) {
-            // private smem row: the window columns are indexed dynamically (x0 differs per query); only the queries
-            // that touch this tile park their row, and at level 0 only the 16-byte groups under their x window
-            const bool lneed = ti.y_first <= rh && ylast >= rl;
-            if (lneed) {
-              if (is0) {
+          // park the accumulator row in this lane's private smem row (the window columns are indexed dynamically):
+          // only queries that touch this tile, and at level 0 only the 16-byte groups under their x window
+          if (ti.y_first <= rh && ylast >= rl) {
+            if (is0) {
 #pragma unroll
-                for (int i = 0; i < 64; i += 4)
-                  if (i + 3 >= x0 && i <= x0 + Wr)
-                    *reinterpret_cast<float4*>(myrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              } else {
+              for (int k = 0; k < 16; ++k)
+                if ((dmask >> k) & 1)
+                  *reinterpret_cast<float4*>(myrow + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            } else {
 #pragma unroll
-                for (int i = 0; i < 64; i += 4)
-                  *reinterpret_cast<float4*>(myrow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              }
+              for (int k = 0; k < 16; ++k)
+                *reinterpret_cast<float4*>(myrow + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
-            // ---- stream the map rows of this tile ----
-            for (int rr = 0; rr < ti.rows; ++rr) {
-              const int y = ti.y_first + rr;
-              float h[MAX_WR];
-              const bool needed = y >= rl && y <= rh;
-              if (needed) {
-                const float* row = myrow + rr * Wl;
-                float vv[MAX_WR + 1];
+          }
+          // ---- stream the map rows of this tile ----
+#pragma unroll 1
+          for (int rr = 0; rr < ti.rows; ++rr) {
+            const int y = ti.y_first + rr;
+            float h[Wr];
+            if (y >= rl && y <= rh) {
+              const float* row = myrow + rr * Wl;
+              float vv[Wr + 1];
 #pragma unroll
-                for (int i = 0; i <= MAX_WR; ++i) {
-                  const int xi = x0 + i;
-                  float c = (i <= Wr && xi >= 0 && xi < Wl) ? row[xi] : 0.f;
-                  // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
-                  vv[i] = p.bf16 ? round_bf16(round_bf16(c) * p.inv_sqrt_c) : c * p.inv_sqrt_c;
-                }
+              for (int i = 0; i <= Wr; ++i) vv[i] = row[xo[i]];
+              if (BF16) {
+                // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
 #pragma unroll
-                for (int i = 0; i < MAX_WR; ++i) h[i] = (1.f - fx) * vv[i] + fx * vv[i + 1];
-              } else {
-#pragma unroll
-                for (int i = 0; i < MAX_WR; ++i) h[i] = 0.f;
-              }
-              const int top = y - 1, j = top - y0;
-              if (valid && j >= 0 && j < Wr && top >= ta && top <= tb_) {
-#pragma unroll
-                for (int i = 0; i < MAX_WR; ++i)
-                  if (i < Wr) mywin[i * Wr + j] = (1.f - fy) * hprev[i] + fy * h[i];
+                for (int i = 0; i <= Wr; ++i) vv[i] = round_bf16(round_bf16(vv[i]) * p.inv_sqrt_c);
               }
 #pragma unroll
-              for (int i = 0; i < MAX_WR; ++i) hprev[i] = h[i];
+              for (int i = 0; i < Wr; ++i) h[i] = wa[i] * vv[i] + wb[i] * vv[i + 1];
+            } else {
+#pragma unroll
+              for (int i = 0; i < Wr; ++i) h[i] = 0.f;
             }
+            const int top = y - 1, j = top - y0;
+            if (j >= 0 && j < Wr && top >= ta && top <= tb_ && valid) {
+              float* wdst = wcol + j * WIN_LD;
+#pragma unroll
+              for (int i = 0; i < Wr; ++i) wdst[i * Wr * WIN_LD] = (1.f - fy) * hprev[i] + fy * h[i];
+            }
+#pragma unroll
+            for (int i = 0; i < Wr; ++i) hprev[i] = h[i];
           }
         }
 
-        if (p.volume_mode || (p.debug & 1)) continue;
+        if (VOLUME || (p.debug & 1)) continue;
         // ---- end of the level inside this job: finish the window and hand it to the stager warp ----
         {
           const bool last = !is0 || (jr.flags() & JF_LAST0);
@@ -683,17 +724,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             const int jb = (Hl - 1) - y0;  // top = H-1: its bottom row is off the map (hprev is row H-1: jb in range
                                            // means this query touches row H-1, so its warp streamed up to it)
             if (jb >= 0 && jb < Wr) {
+              float* wdst = wcol + jb * WIN_LD;
 #pragma unroll
-              for (int i = 0; i < MAX_WR; ++i)
-                if (i < Wr) mywin[i * Wr + jb] = (1.f - fy) * hprev[i];
+              for (int i = 0; i < Wr; ++i) wdst[i * Wr * WIN_LD] = (1.f - fy) * hprev[i];
             }
           }
           // window rows (index j) this job owns: tops in [lo_top, hi_top]
           const int lo_top = is0 ? jr.own_lo : -BIG;
           const int hi_top = is0 ? jr.own_hi : BIG;
           const int j_lo = valid ? max(0, lo_top - y0) : 1, j_hi = valid ? min(Wr - 1, hi_top - y0) : 0;
-          mywin[81] = __int_as_float(j_lo);
-          mywin[82] = __int_as_float(j_hi);
+          wcol[WIN_JLO * WIN_LD] = __int_as_float(j_lo);
+          wcol[WIN_JHI * WIN_LD] = __int_as_float(j_hi);
           __syncwarp();
           if (lane == 0) mbar_arrive(&win_full[(wu % NWIN) * 4 + wq]);  // release.cta: the STS above are visible
           ++wu;
@@ -712,7 +753,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
     const int wq = warp & 3;
     const int q = 32 * wq + lane;
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
-    const int Wr = 2 * p.r + 1, WW = Wr * Wr;
+    constexpr int Wr = 2 * R + 1, WW = Wr * Wr;
     uint32_t wu = 0;
 
     // stage the 128 target rows of job record `r` (hi/lo split) into TMEM A buffer (ji & 1); `nq` = this lane's query
@@ -784,7 +825,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         __syncwarp();
       }
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 1, 0);
-      const bool do_windows = !(p.volume_mode || (p.debug & 1));
+      const bool do_windows = !(VOLUME || (p.debug & 1));
       const int nvalid = min(32, p.N - (jr.mt() * TILE_M + 32 * wq));   // sorted slots: valid first, padding last
       // window units of this job: one per tile run (= one pyramid level)
       for (int sg = 0; do_windows && sg < nseg; ++sg, ++wu) {
@@ -792,7 +833,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
         const uint32_t wbuf = wu % NWIN;
         mbar_wait(&win_full[wbuf * 4 + wq], (wu / NWIN) & 1, p.status, 8);
         if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 0);
-        const float* wrows = win + (wbuf * TILE_M + 32 * wq) * WIN_STRIDE;
+        const float* wbase = win + (wbuf * 4 + wq) * WIN_WARP;   // [entry][WIN_LD] of this lane quarter
         const int lvl_off = (p.tokens ? KC + 2 : 0) + lvl * WW;
         const int jj0 = lane % Wr, jj1 = (lane + 32) % Wr, jj2 = (lane + 64) % Wr;
         const bool ok1 = lane + 32 < WW, ok2 = lane + 64 < WW;
@@ -816,15 +857,14 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
               val[u][0] = 0.f; val[u][1] = 0.f; val[u][2] = 0.f;
             }
           }
-          const float* wsrc = wrows + q16 * WIN_STRIDE;
+          const float* wsrc = wbase + q16;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             float* dst = obase + rowoff[TILE_M + 32 * wq + q16 + u];
-            const int jl = __float_as_int(wsrc[81]), jh = __float_as_int(wsrc[82]);
-            if (ok0 && jj0 >= jl && jj0 <= jh) dst[0] = wsrc[lane] + val[u][0];
-            if (ok1 && jj1 >= jl && jj1 <= jh) dst[32] = wsrc[lane + 32] + val[u][1];
-            if (ok2 && jj2 >= jl && jj2 <= jh) dst[64] = wsrc[lane + 64] + val[u][2];
-            wsrc += WIN_STRIDE;
+            const int jl = __float_as_int(wsrc[WIN_JLO * WIN_LD + u]), jh = __float_as_int(wsrc[WIN_JHI * WIN_LD + u]);
+            if (ok0 && jj0 >= jl && jj0 <= jh) dst[0] = wsrc[lane * WIN_LD + u] + val[u][0];
+            if (ok1 && jj1 >= jl && jj1 <= jh) dst[32] = wsrc[(lane + 32) * WIN_LD + u] + val[u][1];
+            if (ok2 && jj2 >= jl && jj2 <= jh) dst[64] = wsrc[(lane + 64) * WIN_LD + u] + val[u][2];
           }
         }
         __syncwarp();
@@ -868,13 +908,21 @@ __global__ void __launch_bounds__(256) tc_prepare_kernel(const float* __restrict
   }
   for (int i = 5456 + threadIdx.x; i < P_TOTAL; i += 256) s[i] = 0.f;
   __syncthreads();
-  __nv_bfloat162* hi = reinterpret_cast<__nv_bfloat162*>(split + plane * P_TOTAL);
-  __nv_bfloat162* lo = reinterpret_cast<__nv_bfloat162*>(split + ((long long)BS * KC + plane) * P_TOTAL);
+  // tile-major, pre-swizzled layout: split[bs][tile 0..85][hi|lo][channel 0..127][64 positions] holds, per (frame,
+  // tile), the exact 32 KB shared-memory image of the two [128 x 64] bf16 operand tiles in the MN-major SWIZZLE_128B
+  // UMMA layout (16-byte chunk index XOR (channel & 7)).  One pipeline stage is then ONE contiguous 32 KB bulk copy:
+  // a tiled TMA load of the same data spends ~10 clk per 128-byte row (2600 clk per stage, measured) and starves the MMA.
+  const long long bs = plane / KC;
+  const int c = (int)(plane - bs * KC);
+  __nv_bfloat162* base = reinterpret_cast<__nv_bfloat162*>(split) + (bs * NTILES) * (long long)(2 * KC * TILE_N / 2);
   for (int i = threadIdx.x; i < P_TOTAL / 2; i += 256) {
     const float a = s[2 * i], b = s[2 * i + 1];
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    hi[i] = h;
-    lo[i] = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+    const int t = i >> 5, n2 = i & 31;                       // tile, bf16-pair inside the tile row
+    const int chunk = n2 >> 2, within = n2 & 3;              // 16-byte chunk of the 128-byte row
+    const long long o = (long long)t * (2 * KC * TILE_N / 2) + c * (TILE_N / 2) + ((chunk ^ (c & 7)) << 2) + within;
+    base[o] = h;
+    base[o + KC * TILE_N / 2] = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
   }
   if (pyr) {
     const long long offs[5] = {0, off1, off2, off3, off4};
@@ -975,10 +1023,12 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   int* perm = reinterpret_cast<int*>(jobs + (long long)p.BS * p.mtiles * MAX_CHUNK);
   p.jobs = jobs;
   p.perm = perm;
+  p.split = reinterpret_cast<const uint8_t*>(split);
 
   CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {(cuuint64_t)P_TOTAL, (cuuint64_t)2 * p.BS * KC};
-  const cuuint64_t gstride[1] = {(cuuint64_t)P_TOTAL * 2};
+  // rows = (hi|lo, frame, tile, channel), 64 positions (128 bytes) each
+  const cuuint64_t gdim[2] = {(cuuint64_t)TILE_N, (cuuint64_t)2 * p.BS * NTILES * KC};
+  const cuuint64_t gstride[1] = {(cuuint64_t)TILE_N * 2};
   const cuuint32_t box[2] = {TILE_N, KC};
   const cuuint32_t estride[2] = {1, 1};
   CUresult cr = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(split), gdim, gstride, box,
@@ -986,11 +1036,6 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    COMET_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   const int full = (p.volume_mode || (p.debug & 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
   // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
   long long misc = 0;
@@ -1002,7 +1047,29 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   int rc = launch_status("tc_pre_kernel");
   if (rc != COMET_OK) return rc;
   const int grid = (int)(njobs < sms ? njobs : sms);
-  corr_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);
+#define COMET_TC_LAUNCH(RR, BF, VOL)                                                                              \
+  do {                                                                                                            \
+    COMET_CUDA(cudaFuncSetAttribute(corr_tc_kernel<RR, BF, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                    SMEM_BYTES));                                                                 \
+    corr_tc_kernel<RR, BF, VOL><<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);                                  \
+  } while (0)
+#define COMET_TC_LAUNCH_R(RR)                                                                                     \
+  do {                                                                                                            \
+    if (p.bf16) COMET_TC_LAUNCH(RR, true, false); else COMET_TC_LAUNCH(RR, false, false);                         \
+  } while (0)
+  if (p.volume_mode) {
+    if (p.bf16) COMET_TC_LAUNCH(0, true, true); else COMET_TC_LAUNCH(0, false, true);
+  } else {
+    switch (p.r) {
+      case 0: COMET_TC_LAUNCH_R(0); break;
+      case 1: COMET_TC_LAUNCH_R(1); break;
+      case 2: COMET_TC_LAUNCH_R(2); break;
+      case 3: COMET_TC_LAUNCH_R(3); break;
+      default: COMET_TC_LAUNCH_R(4); break;
+    }
+  }
+#undef COMET_TC_LAUNCH_R
+#undef COMET_TC_LAUNCH
   return launch_status("corr_tc_kernel");
 }
 

@@ -296,6 +296,42 @@ def test_full_size_properties(cb):
     assert float((x[..., 663] - tok.pos[:, :, None, 663]).abs().max()) == 0.0  # zero pad channel
 
 
+def test_config4_long_sequence_dense_grid(cb):
+    """BASELINE.json configs[3]: S=64, N=4096 = dense query grid at the pixel centres (8i+4, 8j+4) of a 512^2 image
+    (= cell coordinates (i+.5, j+.5) of the 64x64 map), displaced per frame.  The reference would materialise a
+    5.7 GB volume per iteration; here nothing larger than the 696 MB token tensor exists.  The oracle checks a slice
+    of (frame, query) pairs; linearity and tokens-vs-lookup consistency cover the rest."""
+    S, N, L, r = 64, 4096, 5, 4
+    g = torch.Generator(device="cuda").manual_seed(4)
+    fmaps = torch.randn(1, S, 128, 64, 64, device="cuda", generator=g)
+    feats = torch.randn(1, S, N, 128, device="cuda", generator=g)
+    ii, jj = torch.meshgrid(torch.arange(64, device="cuda"), torch.arange(64, device="cuda"), indexing="ij")
+    q = torch.stack([jj.flatten() + 0.5, ii.flatten() + 0.5], -1).float()            # (4096, 2) = (x, y)
+    coords = q[None, None] + torch.randn(1, S, N, 2, device="cuda", generator=g) * 1.5
+    coords[:, 0] = q
+    blk = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+    blk.corr(feats)
+    out = blk.sample(coords)
+    assert out.shape == (1, S, N, 405)
+    if cb._lib.lib.comet_has_tensor_path():
+        assert cb._lib.lib.comet_tc_status() == 0
+    fs, qs = [0, 17, 46], slice(5, N, 397)   # frame 0 first: the oracle's flows / position embedding refer to it
+    fm_s, ft_s, co_s = host(fmaps[:, fs]), host(feats[:, fs][:, :, qs]), host(coords[:, fs][:, :, qs])
+    want = O.corr_lookup(fm_s, ft_s, co_s, L, r)
+    assert rel_to_max(host(out[:, fs][:, :, qs]), want) < FP32_BAR
+    tdim = cb.transformer_dim(L, r, 128, False)
+    tok = cb.TrackTokenizer(blk, coords[:, 0], tdim)
+    x = tok.tokens(coords, feats)
+    assert x.shape == (1, N, S, 664)
+    corr_part = x[..., 130:535] - tok.pos[:, :, None, 130:535]
+    assert float((corr_part.permute(0, 2, 1, 3) - out).abs().max()) < 1e-4 * float(out.abs().max())
+    want_x = O.track_tokens(want, co_s, ft_s, (64, 64), tdim)
+    assert rel_to_max(host(x[:, qs][:, :, fs]), want_x) < FP32_BAR
+    # linearity in the target at full size
+    blk.corr(feats * 0.5)
+    assert rel_to_max(host(blk.sample(coords)), host(out) * 0.5) < 1e-5
+
+
 def test_full_size_fine_config_subset_vs_oracle(cb):
     """Fine tracker shape: B' = 512 patches, S=16, one query per 31x31 patch, C=32, L=3, r=3."""
     g = torch.Generator(device="cuda").manual_seed(2)
