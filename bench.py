@@ -432,6 +432,28 @@ def main():
                                              ("NCHW-contiguous (the reference encoder's own output layout)"
                                               if other == "nchw" else "as a channels-last view")}
         del alt, alt_in
+        # the reference's shipped configuration runs under torch.autocast(bf16) (mixed_precision: bf16, abl_ours.yaml:102):
+        # CorrBlock.corr then rounds operands and volume to bf16.  Same step with that rounding mode selected.
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(args.warmup):
+                hp.run(devin)
+            barrier()
+            hp.events = []
+            e0.record()
+            for _ in range(args.steps):
+                hp.run(devin)
+            e1.record()
+            barrier()
+        ev_bf, hp.events = hp.events, None
+        per_bf = {}
+        for (t0, a), (t1, b) in zip(ev_bf[:-1], ev_bf[1:]):
+            if t1 is not None:
+                per_bf.setdefault(t1, []).append(a.elapsed_time(b))
+        ms_bf = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        variants["autocast_bf16"] = {"value": Q * world / (ms_bf * 1e-3), "unit": UNIT, "ms_per_step": ms_bf,
+                                     "ms_per_step_by_class": {k: sum(v) / args.steps for k, v in per_bf.items()},
+                                     "what": "same step under torch.autocast(bf16): one tensor-core pass, bf16-rounded "
+                                             "operands and volume, fp32 lookup (parity bar 2e-2)"}
 
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------
     e2e = None

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
 // ------------------------------------------------------------------ the kernel
 template <int R, bool BF16, bool VOLUME>
 __global__ void __launch_bounds__(THREADS, 1)
-corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+corr_tc_kernel(const Params p) {
   // dynamic shared memory is the only shared allocation of this kernel, so it starts 1024-byte aligned (SWIZZLE_128B
   // tiles need that); no integer round trip on the pointer, so that accesses stay LDS/STS rather than generic LD/ST
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -669,10 +669,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             continue;
           }
           if ((p.debug & 1) || !wneed) continue;
+          const int dbg_t = tcount - 1;
+          const bool dbg_on = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && dbg_t >= 8 && dbg_t < 16;
+          if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 0) * 2 + 0] = clock64();
 
           // park the accumulator row in this lane's private smem row (the window columns are indexed dynamically):
           // only queries that touch this tile, and at level 0 only the 16-byte groups under their x window
-          if (ti.y_first <= rh && ylast >= rl) {
+          if ((ti.y_first <= rh && ylast >= rl) && !(p.debug & 4096)) {
             if (is0) {
 #pragma unroll
               for (int k = 0; k < 16; ++k)
@@ -684,6 +687,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
                 *reinterpret_cast<float4*>(myrow + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
           }
+          if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 0) * 2 + 1] = clock64();
           // ---- stream the map rows of this tile ----
 #pragma unroll 1
           for (int rr = 0; rr < ti.rows; ++rr) {
@@ -692,8 +696,13 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
             if (y >= rl && y <= rh) {
               const float* row = myrow + rr * Wl;
               float vv[Wr + 1];
+              if (p.debug & 4096) {   // experiment: no shared-memory round trip (wrong results)
 #pragma unroll
-              for (int i = 0; i <= Wr; ++i) vv[i] = row[xo[i]];
+                for (int i = 0; i <= Wr; ++i) vv[i] = v[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i <= Wr; ++i) vv[i] = row[xo[i]];
+              }
               if (BF16) {
                 // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
 #pragma unroll
@@ -705,6 +714,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 #pragma unroll
               for (int i = 0; i < Wr; ++i) h[i] = 0.f;
             }
+            if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 1) * 2 + 1] = clock64();
             const int top = y - 1, j = top - y0;
             if (j >= 0 && j < Wr && top >= ta && top <= tb_ && valid) {
               float* wdst = wcol + j * WIN_LD;
@@ -714,6 +724,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 #pragma unroll
             for (int i = 0; i < Wr; ++i) hprev[i] = h[i];
           }
+          if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 1) * 2 + 0] = clock64();
         }
 
         if (VOLUME || (p.debug & 1)) continue;
@@ -1025,17 +1036,6 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   p.perm = perm;
   p.split = reinterpret_cast<const uint8_t*>(split);
 
-  CUtensorMap tmap;
-  // rows = (hi|lo, frame, tile, channel), 64 positions (128 bytes) each
-  const cuuint64_t gdim[2] = {(cuuint64_t)TILE_N, (cuuint64_t)2 * p.BS * NTILES * KC};
-  const cuuint64_t gstride[1] = {(cuuint64_t)TILE_N * 2};
-  const cuuint32_t box[2] = {TILE_N, KC};
-  const cuuint32_t estride[2] = {1, 1};
-  CUresult cr = encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(split), gdim, gstride, box,
-                            estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
-
   const int full = (p.volume_mode || (p.debug & 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
   // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
   long long misc = 0;
@@ -1051,7 +1051,7 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   do {                                                                                                            \
     COMET_CUDA(cudaFuncSetAttribute(corr_tc_kernel<RR, BF, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                     SMEM_BYTES));                                                                 \
-    corr_tc_kernel<RR, BF, VOL><<<grid, THREADS, SMEM_BYTES, stream>>>(tmap, p);                                  \
+    corr_tc_kernel<RR, BF, VOL><<<grid, THREADS, SMEM_BYTES, stream>>>(p);                                  \
   } while (0)
 #define COMET_TC_LAUNCH_R(RR)                                                                                     \
   do {                                                                                                            \
