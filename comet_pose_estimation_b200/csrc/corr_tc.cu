@@ -669,13 +669,10 @@ corr_tc_kernel(const Params p) {
             continue;
           }
           if ((p.debug & 1) || !wneed) continue;
-          const int dbg_t = tcount - 1;
-          const bool dbg_on = p.stamps && blockIdx.x == 0 && warp == 2 && lane == 0 && dbg_t >= 8 && dbg_t < 16;
-          if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 0) * 2 + 0] = clock64();
 
           // park the accumulator row in this lane's private smem row (the window columns are indexed dynamically):
           // only queries that touch this tile, and at level 0 only the 16-byte groups under their x window
-          if ((ti.y_first <= rh && ylast >= rl) && !(p.debug & 4096)) {
+          if (ti.y_first <= rh && ylast >= rl) {
             if (is0) {
 #pragma unroll
               for (int k = 0; k < 16; ++k)
@@ -687,7 +684,6 @@ corr_tc_kernel(const Params p) {
                 *reinterpret_cast<float4*>(myrow + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
           }
-          if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 0) * 2 + 1] = clock64();
           // ---- stream the map rows of this tile ----
 #pragma unroll 1
           for (int rr = 0; rr < ti.rows; ++rr) {
@@ -696,13 +692,8 @@ corr_tc_kernel(const Params p) {
             if (y >= rl && y <= rh) {
               const float* row = myrow + rr * Wl;
               float vv[Wr + 1];
-              if (p.debug & 4096) {   // experiment: no shared-memory round trip (wrong results)
 #pragma unroll
-                for (int i = 0; i <= Wr; ++i) vv[i] = v[i];
-              } else {
-#pragma unroll
-                for (int i = 0; i <= Wr; ++i) vv[i] = row[xo[i]];
-              }
+              for (int i = 0; i <= Wr; ++i) vv[i] = row[xo[i]];
               if (BF16) {
                 // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
 #pragma unroll
@@ -714,7 +705,6 @@ corr_tc_kernel(const Params p) {
 #pragma unroll
               for (int i = 0; i < Wr; ++i) h[i] = 0.f;
             }
-            if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 1) * 2 + 1] = clock64();
             const int top = y - 1, j = top - y0;
             if (j >= 0 && j < Wr && top >= ta && top <= tb_ && valid) {
               float* wdst = wcol + j * WIN_LD;
@@ -724,7 +714,6 @@ corr_tc_kernel(const Params p) {
 #pragma unroll
             for (int i = 0; i < Wr; ++i) hprev[i] = h[i];
           }
-          if (dbg_on) p.stamps[(2 * 64 + 32 + (dbg_t - 8) * 4 + 1) * 2 + 0] = clock64();
         }
 
         if (VOLUME || (p.debug & 1)) continue;

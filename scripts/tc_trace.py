@@ -28,7 +28,3 @@ for i in list(range(0, 30)):
     r = [int(s[0, i, 0]), int(s[1, i, 0]), int(s[1, i, 1]), int(s[2, i, 0]), int(s[2, i, 1])]
     print(f"{i:3d}  " + "  ".join(f"{(x - t0) if x else -1:8d}" for x in r))
 
-print("epilogue sub-phases for tiles 8..15: [dump start, dump done, horizontal done, rows done]")
-for k in range(8):
-    a = [int(s[2, 32 + k*4 + 0, 0]), int(s[2, 32 + k*4 + 0, 1]), int(s[2, 32 + k*4 + 1, 1]), int(s[2, 32 + k*4 + 1, 0])]
-    print(8 + k, [x - t0 if x else -1 for x in a])
