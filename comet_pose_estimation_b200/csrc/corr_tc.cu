@@ -8,21 +8,26 @@
 // K=384 bf16 GEMM.  In COMET_PREC_BF16_AUTOCAST mode only hi*hi is issued and the accumulator is rounded to bf16
 // exactly where torch.autocast rounds the reference's volume.
 //
-// Data layout (HBM).  comet_tc_prepare_f32 (once per tracker call) pools the pyramid in float32 and writes, per
-// (frame, channel), ONE packed row of P=5504 positions  [L0 4096 | L1 1024 | L2 256 | L3 64 | L4 16 | 48 zeros]
-// as bf16 hi and bf16 lo:  split[2][BS][C][P].  A 64-position tile of any level is then one TMA box
-// [64 positions x 128 channels] = 16 KB that lands in shared memory in the MN-major SWIZZLE_128B UMMA layout.
+// Data layout (HBM).  comet_tc_prepare_f32 (once per tracker call) pools the pyramid in float32 and packs, per frame,
+// P=5504 positions  [L0 4096 | L1 1024 | L2 256 | L3 64 | L4 16 | 48 zeros] = 86 tiles of 64 positions.  Each tile is
+// stored as the exact 32 KB shared-memory image of its two [128 channels x 64 positions] bf16 operand tiles (hi, lo)
+// in the MN-major SWIZZLE_128B UMMA layout: split[bs][tile][hi|lo][channel][64].  One pipeline stage is ONE contiguous
+// 32 KB bulk async copy (cp.async.bulk -> mbarrier); a tiled TMA load of the same bytes costs ~10 clk per 128-byte row.
 //
-// Work decomposition.  job = (frame bs, 128-query tile, chunk); chunks 0..3 = level-0 rows [16c, 16c+16] (one row
-// of overlap so that every window entry has both of its rows in one chunk), chunk 4 = levels 1..4 (22 tiles).
-// Persistent CTAs (one per SM) walk the job list; jobs of one frame are adjacent so concurrent CTAs share the
-// feature tiles through L2.
+// Work decomposition.  Launch 1 (tc_pre_kernel): per frame, the queries are counting-sorted by floor(y), so the 128
+// queries of an MMA tile -- and the 32 of an epilogue warp -- share a narrow band of map rows; the per-(tile, level)
+// band is reduced and turned into job records (nsplit level-0 row chunks with one row of overlap + npyr jobs for
+// levels 1..L-1); the remaining CTAs of that launch write the correlation-independent token channels (flow sin/cos,
+// flow, track_feats, pad) with one warp per token row.  Launch 2 (corr_tc_kernel): persistent CTAs (one per SM) walk
+// the job list; only the tiles of a band are loaded and multiplied (~45 % of the dense GEMM at 512 random queries per
+// frame), and an epilogue warp skips the tiles none of its queries touches.
 //
-// CTA = 6 warps:  warp 0 TMA producer (B tiles, 3-stage ring) | warp 1 TMEM alloc + single-thread tcgen05.mma issue
-// (D 128x64 fp32 in TMEM, 4-stage accumulator ring) | warps 2-5 epilogue: load + hi/lo-split the 128x128 target
-// tile into the K-major SWIZZLE_128B layout at job start, then per tile tcgen05.ld the accumulator row of "their"
-// query (TMEM lane == query), park it in a private shared-memory row (dynamic column indexing), and stream the map
-// rows: horizontal lerp at the query's x window, vertical lerp with the previous row, store.
+// CTA = 10 warps:  warp 0 bulk-copy producer (3-stage ring) | warp 1 TMEM alloc + single-thread tcgen05.mma issue
+// (A operand = targets in TMEM, `.ts` form; D 128x64 fp32 in TMEM, 4-stage accumulator ring) | warps 2-5 epilogue:
+// tcgen05.ld the accumulator row of "their" query (TMEM lane == sorted query slot), park it in a private shared-memory
+// row (the window columns are indexed dynamically), horizontal lerp at the query's x window, vertical lerp with the
+// previous row, write the staged window | warps 6-9 stager: every global access -- stage the next job's targets into
+// TMEM (hi/lo split, tcgen05.st), and write the staged windows + position embedding with coalesced stores.
 #include "comet_common.cuh"
 
 #include <cuda.h>

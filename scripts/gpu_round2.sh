@@ -22,5 +22,7 @@ cap fine_tokens_cl corr_lookup_c32_tma 8
 cap fine_pyramid_cl pyramid_cl_in_fine 2
 cap coarse_tc corr_tc_kernel 6
 cap coarse_pre tc_pre_kernel 6
+if [ "${NCHW:-0}" = "1" ]; then
 cap fine_tokens_nchw "corr_lookup_c32_kernel" 8 "--fine-layout nchw"
 cap fine_pyramid_nchw "pyramid_cl_fine_kernel" 2 "--fine-layout nchw"
+fi
