@@ -124,6 +124,41 @@ __global__ void __launch_bounds__(256) features4d_kernel(const float* __restrict
   }
 }
 
+// Channel-last input (B,H,W,C): one warp per (b, r) point, lanes stride over the channels, so each of the four taps is a
+// contiguous C-float line (coalesced).  Serves sample_features4d on a channels-last fmaps view and the sampled position
+// embedding from the cached channel-last sin/cos table (in_sb = 0: one table shared by the batch).
+__global__ void __launch_bounds__(256) features4d_cl_kernel(const float* __restrict__ in, long long in_sb,
+                                                             const float* __restrict__ coords, long long c_sb,
+                                                             long long c_sr, float* __restrict__ out, int B, int C, int H,
+                                                             int W, int R) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pt < (long long)B * R; pt += nw) {
+    const int r = (int)(pt % R);
+    const int b = (int)(pt / R);
+    const float* cp = coords + b * c_sb + r * c_sr;
+    Tap tx, ty;
+    tx.init(ref_pixel(__ldg(cp), W, true), W, true);
+    ty.init(ref_pixel(__ldg(cp + 1), H, true), H, true);
+    const float* img = in + b * in_sb;
+    const float* p00 = img + ((long long)ty.i0 * W + tx.i0) * C;
+    const float* p01 = img + ((long long)ty.i0 * W + tx.i1) * C;
+    const float* p10 = img + ((long long)ty.i1 * W + tx.i0) * C;
+    const float* p11 = img + ((long long)ty.i1 * W + tx.i1) * C;
+    const bool k00 = ty.ok0 && tx.ok0, k01 = ty.ok0 && tx.ok1, k10 = ty.ok1 && tx.ok0, k11 = ty.ok1 && tx.ok1;
+    const float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
+    float* o = out + pt * C;
+    for (int c = lane; c < C; c += 32) {
+      float v = 0.f;   // ATen accumulation order: nw, ne, sw, se
+      if (k00) v += __ldg(p00 + c) * w00;
+      if (k01) v += __ldg(p01 + c) * w01;
+      if (k10) v += __ldg(p10 + c) * w10;
+      if (k11) v += __ldg(p11 + c) * w11;
+      o[c] = v;
+    }
+  }
+}
+
 static inline unsigned grid_for(long long total) {
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
@@ -173,4 +208,18 @@ extern "C" int comet_sample_features4d_f32(const float* input, long long in_sb, 
   features4d_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(input, in_sb, coords, c_sb, c_sr, out, B, C, H,
                                                                        W, R);
   return launch_status("features4d_kernel");
+}
+
+extern "C" int comet_sample_features4d_cl_f32(const float* input, long long in_sb, const float* coords, long long c_sb,
+                                              long long c_sr, float* out, int B, int C, int H, int W, int R,
+                                              comet_stream_t stream) {
+  COMET_REQUIRE(B >= 0 && C >= 0 && R >= 0 && H >= 1 && W >= 1, "bad shape");
+  const long long pts = (long long)B * R;
+  if (pts == 0 || C == 0) return COMET_OK;
+  COMET_REQUIRE(input && coords && out, "null pointer");
+  long long blocks = (pts + 7) / 8;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  features4d_cl_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(input, in_sb, coords, c_sb, c_sr, out, B, C, H, W,
+                                                                         R);
+  return launch_status("features4d_cl_kernel");
 }

@@ -28,17 +28,39 @@ def transformer_dim(corr_levels: int, corr_radius: int, latent_dim: int, fine: b
     return d
 
 
-def sampled_pos_emb(coords0: torch.Tensor, embed_dim: int, H: int, W: int) -> torch.Tensor:
+_TABLES = {}  # (D, H, W, device) -> channel-last sin/cos table (H, W, D); the reference rebuilds and uploads it per iteration
+
+
+def _sincos_table_cl(embed_dim: int, H: int, W: int, device) -> torch.Tensor:
+    key = (embed_dim, H, W, str(device))
+    t = _TABLES.get(key)
+    if t is None:
+        from .utils import get_2d_sincos_pos_embed
+
+        t = get_2d_sincos_pos_embed(embed_dim, (H, W), device=device)[0].permute(1, 2, 0).contiguous()
+        _TABLES[key] = t
+    return t
+
+
+def sampled_pos_emb(coords0: torch.Tensor, embed_dim: int, H: int, W: int, cached_table: bool = True) -> torch.Tensor:
     """``sample_features4d(get_2d_sincos_pos_embed(D,(H,W)).expand(B,...), coords[:,0])``
-    (base_track_predictor.py:200-208) -> (B,N,D); iteration-invariant, so computed once per tracker call."""
+    (base_track_predictor.py:200-208) -> (B,N,D); iteration-invariant, so computed once per tracker call.
+    The float64-evaluated table depends on (D,H,W) only: it is built once per device (channel-last, so each bilinear tap
+    is one contiguous line) and sampled by one kernel.  ``cached_table=False`` evaluates the four taps on the fly
+    instead (no table at all; same values)."""
     require_cuda(coords0, "coords0")
     B, N, two = coords0.shape
     assert two == 2
     c = inner_contig(coords0)
     out = torch.empty((B, N, embed_dim), dtype=torch.float32, device=c.device)
     with torch.cuda.device(c.device):
-        _lib.check(lib.comet_sampled_pos_emb_f32(c.data_ptr(), c.stride(0), c.stride(1), out.data_ptr(), B, N,
-                                                 embed_dim, H, W, stream_ptr(c.device)))
+        if cached_table and B * N:
+            tab = _sincos_table_cl(embed_dim, H, W, c.device)
+            _lib.check(lib.comet_sample_features4d_cl_f32(tab.data_ptr(), 0, c.data_ptr(), c.stride(0), c.stride(1),
+                                                          out.data_ptr(), B, embed_dim, H, W, N, stream_ptr(c.device)))
+        else:
+            _lib.check(lib.comet_sampled_pos_emb_f32(c.data_ptr(), c.stride(0), c.stride(1), out.data_ptr(), B, N,
+                                                     embed_dim, H, W, stream_ptr(c.device)))
     return out
 
 

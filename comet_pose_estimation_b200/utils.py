@@ -56,12 +56,19 @@ def sample_features4d(input, coords):
     require_cuda(coords, "coords")
     B, C, H, W = input.shape
     x = input if input.dtype == torch.float32 else input.float()
-    if B and C and not (x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W):
-        x = x.contiguous()
     c = inner_contig(coords)
     assert c.dim() == 3 and c.shape[0] == B and c.shape[2] == 2
     R = c.shape[1]
     out = torch.empty((B, R, C), dtype=torch.float32, device=x.device)
+    if B and C > 1 and x.stride(1) == 1 and x.stride(3) == C and x.stride(2) == W * C:
+        # channels-last view (e.g. fmaps[:, 0] of a channels-last patch-feature tensor): sampled in place
+        with torch.cuda.device(x.device):
+            _lib.check(lib.comet_sample_features4d_cl_f32(x.data_ptr(), x.stride(0), c.data_ptr(), c.stride(0),
+                                                          c.stride(1), out.data_ptr(), B, C, H, W, R,
+                                                          stream_ptr(x.device)))
+        return out
+    if B and C and not (x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W):
+        x = x.contiguous()
     with torch.cuda.device(x.device):
         _lib.check(lib.comet_sample_features4d_f32(x.data_ptr(), x.stride(0), c.data_ptr(), c.stride(0), c.stride(1),
                                                    out.data_ptr(), B, C, H, W, R, stream_ptr(x.device)))

@@ -130,6 +130,12 @@ int comet_sample_features4d_f32(const float* input, long long in_sb, const float
                                 long long c_sr, float* out, int B, int C, int H, int W, int R,
                                 comet_stream_t stream);
 
+/* Same, input channel-last (B,H,W,C) with batch stride in_sb (0 = one map shared by the whole batch, e.g. the cached
+ * sin/cos table): every tap is one contiguous C-float line. */
+int comet_sample_features4d_cl_f32(const float* input, long long in_sb, const float* coords, long long c_sb,
+                                   long long c_sr, float* out, int B, int C, int H, int W, int R,
+                                   comet_stream_t stream);
+
 /* ---- sin/cos encodings: comet/models/utils.py:37-101, :724-832 ----------- */
 /* get_2d_embedding(xy, C, cat_coords): xy (M,2) contiguous -> out (M, 2*C [+2 in front if cat_coords]). */
 int comet_embed2d_f32(const float* xy, float* out, long long M, int C, int cat_coords, comet_stream_t stream);

@@ -385,6 +385,30 @@ def test_channels_last_fmaps_are_used_zero_copy(cb, shape):
     assert rel_to_max(host(x), host(x_ref)) < 1e-5
 
 
+def test_channels_last_point_sampler_and_cached_pos_emb(cb, golden):
+    """sample_features4d on a channels-last view == on the contiguous tensor == the oracle; the sampled position
+    embedding from the cached channel-last sin/cos table == the on-the-fly evaluation == the oracle."""
+    from comet_pose_estimation_b200.track_tokens import sampled_pos_emb
+
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(6, 32, 31, 31, device="cuda", generator=g)
+    pts = torch.rand(6, 9, 2, device="cuda", generator=g) * 36 - 3
+    xcl = x.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    a, b = cb.sample_features4d(x, pts), cb.sample_features4d(xcl, pts)
+    assert rel_to_max(host(b), O.sample_features4d(host(x), host(pts))) < 1e-5
+    assert rel_to_max(host(b), host(a)) < 1e-5
+    view = _channels_last_view(torch.randn(4, 3, 32, 31, 31, device="cuda", generator=g))[:, 0]   # fmaps[:, 0]
+    assert rel_to_max(host(cb.sample_features4d(view, pts[:4])), O.sample_features4d(host(view), host(pts[:4]))) < 1e-5
+    for (D, H, W) in ((664, 64, 64), (216, 31, 31), (12, 3, 5)):
+        c0 = torch.rand(2, 17, 2, device="cuda", generator=g) * torch.tensor([W + 4.0, H + 4.0], device="cuda") - 2
+        t1 = sampled_pos_emb(c0, D, H, W, cached_table=True)
+        t2 = sampled_pos_emb(c0, D, H, W, cached_table=False)
+        tab = O.get_2d_sincos_pos_embed(D, (H, W))
+        want = O.sample_features4d(np.broadcast_to(tab, (2,) + tab.shape[1:]), host(c0))
+        assert rel_to_max(host(t1), want) < 1e-5
+        assert rel_to_max(host(t2), want) < 1e-5
+
+
 def test_full_size_fine_config_channels_last(cb):
     """Fine tracker at full size with channels-last patch features == the NCHW result (same oracle slice)."""
     g = torch.Generator(device="cuda").manual_seed(2)
