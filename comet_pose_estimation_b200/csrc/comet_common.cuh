@@ -94,6 +94,16 @@ inline Levels make_levels(int BS, int C, int H, int W, int L) {
 
 // ---- device helpers ----------------------------------------------------
 __device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// Round the four floats of a vector to bf16 precision (round-to-nearest-even, like round_bf16): two packed conversions
+// + four bit operations instead of four scalar conversions + four shifts.
+__device__ __forceinline__ void round_bf16x4(float4& g) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(g.x, g.y), b = __floats2bfloat162_rn(g.z, g.w);
+  const uint32_t ua = *reinterpret_cast<const uint32_t*>(&a), ub = *reinterpret_cast<const uint32_t*>(&b);
+  g.x = __uint_as_float(ua << 16);
+  g.y = __uint_as_float(ua & 0xffff0000u);
+  g.z = __uint_as_float(ub << 16);
+  g.w = __uint_as_float(ub & 0xffff0000u);
+}
 
 // Per-axis description of a (2r+1)-wide window of bilinear samples whose centre is `p`
 // (grid_sample semantics, align_corners=True, restated from ATen GridSampler):

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) corr_lookup_c32_kernel(const LookupPar
         for (int i = 0; i < 8; ++i) {
           const float4 t = *reinterpret_cast<const float4*>(Ts + 4 * i);
           float4 g = f[i];
-          if (BF16) { g.x = round_bf16(g.x); g.y = round_bf16(g.y); g.z = round_bf16(g.z); g.w = round_bf16(g.w); }
+          if (BF16) round_bf16x4(g);
           acc[k] = fmaf(t.x, g.x, acc[k]);
           acc[k] = fmaf(t.y, g.y, acc[k]);
           acc[k] = fmaf(t.z, g.z, acc[k]);
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(256, 1) corr_lookup_c32_tma_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               float4 g = *reinterpret_cast<const float4*>(line + ((i ^ sw) << 4));
-              if (BF16) { g.x = round_bf16(g.x); g.y = round_bf16(g.y); g.z = round_bf16(g.z); g.w = round_bf16(g.w); }
+              if (BF16) round_bf16x4(g);
               a = fmaf(t4[i].x, g.x, a);
               a = fmaf(t4[i].y, g.y, a);
               a = fmaf(t4[i].z, g.z, a);
