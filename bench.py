@@ -360,7 +360,7 @@ def main():
             kern[k]["GBps"] = ab[k] / (kern[k]["ms_avg"] * 1e-3) / 1e9
     # roofline of the dominant kernel class (by device time inside the timed region).  Every class of this path is
     # HBM-bound; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this batch size and layout
-    # from the committed ncu --set full captures (profiles/traffic.json, written by scripts/ncu_traffic.py).
+    # from the committed ncu --set full captures (profiles/traffic.json, written by scripts/ncu_summary.py --traffic).
     KNAME = {
         "fine_tokens": {"cl": "corr_lookup_c32_tma_kernel<R=3,TOKENS> (fine tracker: TMA-staged corr + lookup + tokens)",
                         "nchw": "corr_lookup_c32_kernel<R=3,TOKENS> (fine tracker: fused corr + lookup + tokens)"},
