@@ -42,6 +42,7 @@ SIGNATURES = {
     "comet_bilinear_sampler5d_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "comet_sample_features4d_f32": (_i, [_p, _ll, _p, _ll, _ll, _p, _i, _i, _i, _i, _i, _p]),
     "comet_sample_features4d_cl_f32": (_i, [_p, _ll, _p, _ll, _ll, _p, _i, _i, _i, _i, _i, _p]),
+    "comet_upsample_bilinear_ac_f32": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _i, _p]),
     "comet_embed2d_f32": (_i, [_p, _p, _ll, _i, _i, _p]),
     "comet_sincos1d_from_grid_f32": (_i, [_p, _p, _ll, _i, _p]),
     "comet_sincos2d_f32": (_i, [_p, _i, _i, _i, _p]),

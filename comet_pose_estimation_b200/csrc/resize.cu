@@ -1,0 +1,99 @@
+// Bilinear resize with align_corners=True -- F.interpolate(x, size, mode="bilinear", align_corners=True) as the patch
+// encoder of the fine tracker calls it (ShallowEncoder.forward, comet/models/track_modules/blocks.py:176-190: two
+// 8->16 / 4->16 residual up-samplings and the final 16x16 -> 31x31 map that becomes the fine tracker's `fmaps`).
+// ATen's CUDA kernel walks batch x channels inside every thread; at the fine tracker's shape (8192 patches x 32
+// channels, 31x31 outputs) that is 961 threads doing 262144 iterations each: 192-314 ms per sequence on B200, 90 % of
+// refine_track.  Here one thread produces one output element (NCHW) or one 4-channel group (channel-last): HBM-bound.
+#include "comet_common.cuh"
+
+namespace comet {
+
+// ATen semantics (UpSample.cuh, area_pixel_compute_source_index with align_corners): src = dst * (in-1)/(out-1);
+// i0 = (int)src, i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1; value = wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11).
+struct ResizeTap {
+  int i0, i1;
+  float w0, w1;
+  __device__ __forceinline__ void init(int dst, float scale, int in) {
+    const float src = scale * (float)dst;
+    i0 = (int)src;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    w1 = src - (float)i0;
+    w0 = 1.f - w1;
+  }
+};
+
+__global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            long long planes, int Hi, int Wi, int Ho, int Wo, float sy,
+                                                            float sx) {
+  const long long total = planes * Ho * Wo;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % Wo);
+    const long long t = idx / Wo;
+    const int yo = (int)(t % Ho);
+    const long long pl = t / Ho;
+    ResizeTap ty, tx;
+    ty.init(yo, sy, Hi);
+    tx.init(xo, sx, Wi);
+    const float* p = in + pl * Hi * Wi;
+    const float v00 = __ldg(p + ty.i0 * Wi + tx.i0), v01 = __ldg(p + ty.i0 * Wi + tx.i1);
+    const float v10 = __ldg(p + ty.i1 * Wi + tx.i0), v11 = __ldg(p + ty.i1 * Wi + tx.i1);
+    out[idx] = ty.w0 * (tx.w0 * v00 + tx.w1 * v01) + ty.w1 * (tx.w0 * v10 + tx.w1 * v11);
+  }
+}
+
+// channel-last (N, H, W, C), C % 4 == 0: thread <-> (n, yo, xo, 4 channels)
+__global__ void __launch_bounds__(256) upsample_cl_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long N,
+                                                          int C4, int Hi, int Wi, int Ho, int Wo, float sy, float sx) {
+  const long long total = N * Ho * Wo * C4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    long long t = idx / C4;
+    const int xo = (int)(t % Wo);
+    t /= Wo;
+    const int yo = (int)(t % Ho);
+    const long long n = t / Ho;
+    ResizeTap ty, tx;
+    ty.init(yo, sy, Hi);
+    tx.init(xo, sx, Wi);
+    const float4* p = in + n * (long long)Hi * Wi * C4 + c4;
+    const float4 v00 = __ldg(p + (ty.i0 * Wi + tx.i0) * C4), v01 = __ldg(p + (ty.i0 * Wi + tx.i1) * C4);
+    const float4 v10 = __ldg(p + (ty.i1 * Wi + tx.i0) * C4), v11 = __ldg(p + (ty.i1 * Wi + tx.i1) * C4);
+    float4 o;
+    o.x = ty.w0 * (tx.w0 * v00.x + tx.w1 * v01.x) + ty.w1 * (tx.w0 * v10.x + tx.w1 * v11.x);
+    o.y = ty.w0 * (tx.w0 * v00.y + tx.w1 * v01.y) + ty.w1 * (tx.w0 * v10.y + tx.w1 * v11.y);
+    o.z = ty.w0 * (tx.w0 * v00.z + tx.w1 * v01.z) + ty.w1 * (tx.w0 * v10.z + tx.w1 * v11.z);
+    o.w = ty.w0 * (tx.w0 * v00.w + tx.w1 * v01.w) + ty.w1 * (tx.w0 * v10.w + tx.w1 * v11.w);
+    out[idx] = o;
+  }
+}
+
+}  // namespace comet
+
+using namespace comet;
+
+extern "C" int comet_upsample_bilinear_ac_f32(const float* in, float* out, long long N, int C, int Hi, int Wi, int Ho,
+                                              int Wo, int layout, comet_stream_t stream) {
+  COMET_REQUIRE(N >= 0 && C >= 0 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "bad shape");
+  COMET_REQUIRE(layout == COMET_FMAPS_NCHW || layout == COMET_FMAPS_CHANNEL_LAST, "bad layout %d", layout);
+  const long long total = N * C * (long long)Ho * Wo;
+  if (total == 0) return COMET_OK;
+  COMET_REQUIRE(in && out, "null pointer");
+  const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  auto blocks_for = [](long long n) {
+    long long b = (n + 255) / 256;
+    if (b > 148LL * 64) b = 148LL * 64;
+    return (unsigned)(b < 1 ? 1 : b);
+  };
+  if (layout == COMET_FMAPS_CHANNEL_LAST) {
+    COMET_REQUIRE(C % 4 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0,
+                  "channel-last resize needs C %% 4 == 0 and 16-byte aligned buffers");
+    upsample_cl_kernel<<<blocks_for(total / 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), N, C / 4, Hi, Wi, Ho, Wo, sy, sx);
+    return launch_status("upsample_cl_kernel");
+  }
+  upsample_nchw_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(in, out, N * C, Hi, Wi, Ho, Wo, sy, sx);
+  return launch_status("upsample_nchw_kernel");
+}

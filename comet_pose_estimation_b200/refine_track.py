@@ -9,15 +9,33 @@ What is B200-specific here is the *data format between the caller and the path*:
 * the encoder runs in ``torch.channels_last``; its output, viewed as (B*N, S, C, 31, 31), is the channels-last
   view the fused kernels read zero-copy (one 128-byte line per position: ``_Pyramid.cl_input``).
 
-The encoder itself (three 3x3 convolutions on 16x16 / 8x8 / 4x4 maps, instance norm, bilinear resizes) is plain
-``torch.nn`` plumbing with the reference's parameter names, not a kernel of this round.  Results equal the
-reference's (tests/golden/refine.npz, produced by executing the reference).
+* the encoder's three bilinear resizes (blocks.py:176-190; the last one, 16x16 -> 31x31, *is* the fine tracker's
+  ``fmaps``) run in the library's own kernel: ATen's up-sampling kernel walks batch x channels inside every thread and
+  took 192 ms (channels-last) / 314 ms (NCHW) per sequence at 8192 patches on B200 -- 90 % of ``refine_track``;
+  with ``comet_upsample_bilinear_ac_f32`` the encoder drops from 207 ms to 13 ms and ``refine_track`` from 226 ms to
+  35 ms per sequence (``scripts/refine_profile.py``).
+
+The rest of the encoder (3x3 convolutions on 16x16 / 8x8 / 4x4 maps, instance norm) is plain ``torch.nn`` plumbing with
+the reference's parameter names.  Results equal the reference's (tests/golden/refine.npz, produced by executing the
+reference).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+def _resize(x: torch.Tensor, size) -> torch.Tensor:
+    """``F.interpolate(x, size, mode="bilinear", align_corners=True)``.  On the GPU (inference, float32) this is the
+    library's own kernel: ATen's up-sampling kernel walks batch x channels inside every thread and, at 8192 patches,
+    is 90 % of ``refine_track`` (192-314 ms per sequence on B200 against ~1 ms here).  Anything else (CPU tensors in
+    the host-logic tests, autograd) takes the torch op."""
+    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+        from .utils import upsample_bilinear_align_corners
+
+        return upsample_bilinear_align_corners(x, size)
+    return F.interpolate(x, size, mode="bilinear", align_corners=True)
 
 
 class _ResidualBlock(nn.Module):
@@ -68,11 +86,11 @@ class ShallowEncoder(nn.Module):
         _, _, H, W = x.shape
         x = F.relu(self.norm1(self.conv1(x)))
         tmp = self.layer1(x)
-        x = x + F.interpolate(tmp, x.shape[-2:], mode="bilinear", align_corners=True)
+        x = x + _resize(tmp, x.shape[-2:])
         tmp = self.layer2(tmp)
-        x = x + F.interpolate(tmp, x.shape[-2:], mode="bilinear", align_corners=True)
+        x = x + _resize(tmp, x.shape[-2:])
         x = self.conv2(x) + x
-        return F.interpolate(x, (H // self.stride, W // self.stride), mode="bilinear", align_corners=True)
+        return _resize(x, (H // self.stride, W // self.stride))
 
 
 def extract_patches(images: torch.Tensor, topleft: torch.Tensor, psize: int) -> torch.Tensor:

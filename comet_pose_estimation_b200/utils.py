@@ -138,3 +138,26 @@ def get_1d_sincos_pos_embed(embed_dim: int, length: int, return_grid: bool = Fal
     if return_grid:
         return pe, grid.unsqueeze(0)
     return pe
+
+
+def upsample_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
+    """``F.interpolate(x, size, mode="bilinear", align_corners=True)`` for a 4-D float32 CUDA tensor, contiguous or
+    channels-last (the output keeps the input's memory format).  The patch encoder of the fine tracker
+    (ShallowEncoder.forward, blocks.py:176-190) spends 90 % of ``refine_track`` in ATen's kernel for this op at 8192
+    patches; this one is HBM-bound."""
+    require_cuda(x, "x")
+    assert x.dim() == 4
+    N, C, Hi, Wi = x.shape
+    Ho, Wo = (size, size) if isinstance(size, int) else tuple(size)
+    x = x if x.dtype == torch.float32 else x.float()
+    cl = (C % 4 == 0 and C > 1 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+          and x.data_ptr() % 16 == 0)
+    if not cl:
+        x = x.contiguous()
+    out = torch.empty((N, C, Ho, Wo), dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last if cl else torch.contiguous_format)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.comet_upsample_bilinear_ac_f32(x.data_ptr(), out.data_ptr(), N, C, Hi, Wi, Ho, Wo,
+                                                      _lib.FMAPS_CHANNEL_LAST if cl else _lib.FMAPS_NCHW,
+                                                      stream_ptr(x.device)))
+    return out

@@ -136,6 +136,12 @@ int comet_sample_features4d_cl_f32(const float* input, long long in_sb, const fl
                                    long long c_sr, float* out, int B, int C, int H, int W, int R,
                                    comet_stream_t stream);
 
+/* ---- bilinear resize, align_corners=True: the F.interpolate calls of the fine tracker's patch encoder
+ *      (ShallowEncoder.forward, comet/models/track_modules/blocks.py:176-190), whose last one produces the fine
+ *      tracker's fmaps.  in (N,C,Hi,Wi) -> out (N,C,Ho,Wo), both COMET_FMAPS_NCHW or both COMET_FMAPS_CHANNEL_LAST. */
+int comet_upsample_bilinear_ac_f32(const float* in, float* out, long long N, int C, int Hi, int Wi, int Ho, int Wo,
+                                   int layout, comet_stream_t stream);
+
 /* ---- sin/cos encodings: comet/models/utils.py:37-101, :724-832 ----------- */
 /* get_2d_embedding(xy, C, cat_coords): xy (M,2) contiguous -> out (M, 2*C [+2 in front if cat_coords]). */
 int comet_embed2d_f32(const float* xy, float* out, long long M, int C, int cat_coords, comet_stream_t stream);

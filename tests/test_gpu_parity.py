@@ -409,6 +409,24 @@ def test_channels_last_point_sampler_and_cached_pos_emb(cb, golden):
         assert rel_to_max(host(t2), want) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(37, 32, 16, 16, 31, 31), (5, 32, 8, 8, 16, 16), (3, 32, 4, 4, 16, 16),
+                                   (2, 6, 7, 5, 12, 9), (4, 8, 3, 3, 1, 1), (2, 4, 1, 1, 5, 4)])
+def test_bilinear_resize_matches_interpolate(cb, shape):
+    """upsample_bilinear_align_corners == F.interpolate(..., mode="bilinear", align_corners=True), contiguous and
+    channels-last (the three resizes of the fine tracker's patch encoder, blocks.py:176-190, and odd shapes)."""
+    N, C, Hi, Wi, Ho, Wo = shape
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(N, C, Hi, Wi, device="cuda", generator=g)
+    want = torch.nn.functional.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=True)
+    got = cb.upsample_bilinear_align_corners(x, (Ho, Wo))
+    assert got.is_contiguous() and rel_to_max(host(got), host(want)) < 1e-6
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    got_cl = cb.upsample_bilinear_align_corners(xcl, (Ho, Wo))
+    assert got_cl.shape == want.shape and rel_to_max(host(got_cl), host(want)) < 1e-6
+    if C % 4 == 0 and C > 1 and Ho * Wo > 1 and not xcl.is_contiguous():
+        assert got_cl.is_contiguous(memory_format=torch.channels_last)   # the memory format is preserved
+
+
 def test_full_size_fine_config_channels_last(cb):
     """Fine tracker at full size with channels-last patch features == the NCHW result (same oracle slice)."""
     g = torch.Generator(device="cuda").manual_seed(2)
