@@ -28,6 +28,7 @@ from .utils import (  # noqa: F401
     get_1d_sincos_pos_embed,
     get_1d_sincos_pos_embed_from_grid,
     upsample_bilinear_align_corners,
+    instance_norm,
 )
 from .track_tokens import TrackTokenizer, sampled_pos_emb, transformer_dim  # noqa: F401
 from .update_former import EfficientUpdateFormer  # noqa: F401

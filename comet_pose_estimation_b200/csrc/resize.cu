@@ -97,3 +97,78 @@ extern "C" int comet_upsample_bilinear_ac_f32(const float* in, float* out, long 
   upsample_nchw_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(in, out, N * C, Hi, Wi, Ho, Wo, sy, sx);
   return launch_status("upsample_nchw_kernel");
 }
+
+// ---- instance normalisation (+ optional ReLU) of the patch encoder ---------------------------------------------------
+// nn.InstanceNorm2d(affine=False, track_running_stats=False, eps) as ShallowEncoder / ResidualBlock use it
+// (blocks.py:128-131, modules.py:86-90): y = (x - mean) / sqrt(var + eps) per (sample, channel) plane, biased variance.
+// ATen routes it through batch_norm over N*C "channels" (batch_norm_collect_statistics: 8.6 ms per sequence at 8192
+// patches, the largest item of the encoder once the resizes are fixed).  Two passes over a plane that stays in L1/L2.
+namespace comet {
+
+// NCHW: one warp per (n, c) plane of HW contiguous elements
+__global__ void __launch_bounds__(256) instance_norm_nchw_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                 long long planes, int HW, float eps, int relu) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long pl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pl < planes; pl += nw) {
+    const float* p = in + pl * HW;
+    float s = 0.f;
+    for (int i = lane; i < HW; i += 32) s += __ldg(p + i);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)HW;
+    float v = 0.f;
+    for (int i = lane; i < HW; i += 32) { const float d = __ldg(p + i) - mean; v = fmaf(d, d, v); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v / (float)HW + eps);
+    float* q = out + pl * HW;
+    for (int i = lane; i < HW; i += 32) {
+      float y = (__ldg(p + i) - mean) * rstd;
+      q[i] = relu ? fmaxf(y, 0.f) : y;
+    }
+  }
+}
+
+// channel-last (N, HW, C): one thread per (n, c), consecutive threads <-> consecutive channels (coalesced lines)
+__global__ void __launch_bounds__(256) instance_norm_cl_kernel(const float* __restrict__ in, float* __restrict__ out, long long N,
+                                                               int C, int HW, float eps, int relu) {
+  const long long total = N * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long n = idx / C;
+    const int c = (int)(idx - n * C);
+    const float* p = in + n * (long long)HW * C + c;
+    float s = 0.f;
+    for (int i = 0; i < HW; ++i) s += __ldg(p + (long long)i * C);
+    const float mean = s / (float)HW;
+    float v = 0.f;
+    for (int i = 0; i < HW; ++i) { const float d = __ldg(p + (long long)i * C) - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(v / (float)HW + eps);
+    float* q = out + n * (long long)HW * C + c;
+    for (int i = 0; i < HW; ++i) {
+      float y = (__ldg(p + (long long)i * C) - mean) * rstd;
+      q[(long long)i * C] = relu ? fmaxf(y, 0.f) : y;
+    }
+  }
+}
+
+}  // namespace comet
+
+extern "C" int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int HW, int layout, int relu,
+                                       float eps, comet_stream_t stream) {
+  COMET_REQUIRE(N >= 0 && C >= 0 && HW >= 1, "bad shape");
+  COMET_REQUIRE(layout == COMET_FMAPS_NCHW || layout == COMET_FMAPS_CHANNEL_LAST, "bad layout %d", layout);
+  if (N * C == 0) return COMET_OK;
+  COMET_REQUIRE(in && out, "null pointer");
+  if (layout == COMET_FMAPS_CHANNEL_LAST) {
+    long long blocks = (N * C + 255) / 256;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    comet::instance_norm_cl_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N, C, HW, eps, relu);
+    return comet::launch_status("instance_norm_cl_kernel");
+  }
+  long long blocks = (N * C + 7) / 8;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  comet::instance_norm_nchw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N * C, HW, eps, relu);
+  return comet::launch_status("instance_norm_nchw_kernel");
+}

@@ -12,11 +12,13 @@ What is B200-specific here is the *data format between the caller and the path*:
 * the encoder's three bilinear resizes (blocks.py:176-190; the last one, 16x16 -> 31x31, *is* the fine tracker's
   ``fmaps``) run in the library's own kernel: ATen's up-sampling kernel walks batch x channels inside every thread and
   took 192 ms (channels-last) / 314 ms (NCHW) per sequence at 8192 patches on B200 -- 90 % of ``refine_track``;
-  with ``comet_upsample_bilinear_ac_f32`` the encoder drops from 207 ms to 13 ms and ``refine_track`` from 226 ms to
-  35 ms per sequence (``scripts/refine_profile.py``).
+  with ``comet_upsample_bilinear_ac_f32`` the encoder drops from 207 ms to 13 ms; its instance norms (ATen:
+  ``batch_norm`` over N*C "channels", 8.6 ms) run in ``comet_instance_norm_f32`` (+ fused ReLU): 2.4 ms for the
+  whole encoder, and ``refine_track`` goes from 226 ms to 26 ms per sequence (``scripts/refine_profile.py``; what
+  remains is the torch update transformer).
 
-The rest of the encoder (3x3 convolutions on 16x16 / 8x8 / 4x4 maps, instance norm) is plain ``torch.nn`` plumbing with
-the reference's parameter names.  Results equal the reference's (tests/golden/refine.npz, produced by executing the
+The convolutions of the encoder (3x3 on 16x16 / 8x8 / 4x4 maps, ~1 ms in cuDNN) stay ``torch.nn`` with the reference's
+parameter names.  Results equal the reference's (tests/golden/refine.npz, produced by executing the
 reference).
 """
 from __future__ import annotations
@@ -38,6 +40,17 @@ def _resize(x: torch.Tensor, size) -> torch.Tensor:
     return F.interpolate(x, size, mode="bilinear", align_corners=True)
 
 
+def _inorm(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool) -> torch.Tensor:
+    """``relu(norm(x))`` / ``norm(x)``: the library's instance-norm kernel for float32 CUDA inference (ATen routes
+    InstanceNorm2d through batch_norm over N*C channels: 8.6 ms per sequence at 8192 patches), torch otherwise."""
+    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+        from .utils import instance_norm
+
+        return instance_norm(x, relu=relu, eps=norm.eps)
+    y = norm(x)
+    return F.relu(y) if relu else y
+
+
 class _ResidualBlock(nn.Module):
     """comet/models/modules.py:39-117 with norm_fn="instance" (parameter-free norms); parameter names kept."""
 
@@ -54,10 +67,10 @@ class _ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride), self.norm3)
 
     def forward(self, x):
-        y = F.relu(self.norm1(self.conv1(x)))
-        y = F.relu(self.norm2(self.conv2(y)))
+        y = _inorm(self.norm1, self.conv1(x), True)
+        y = _inorm(self.norm2, self.conv2(y), True)
         if self.downsample is not None:
-            x = self.downsample(x)
+            x = _inorm(self.norm3, self.downsample[0](x), False)
         return F.relu(x + y)
 
 
@@ -84,7 +97,7 @@ class ShallowEncoder(nn.Module):
 
     def forward(self, x):
         _, _, H, W = x.shape
-        x = F.relu(self.norm1(self.conv1(x)))
+        x = _inorm(self.norm1, self.conv1(x), True)
         tmp = self.layer1(x)
         x = x + _resize(tmp, x.shape[-2:])
         tmp = self.layer2(tmp)

@@ -161,3 +161,21 @@ def upsample_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
                                                       _lib.FMAPS_CHANNEL_LAST if cl else _lib.FMAPS_NCHW,
                                                       stream_ptr(x.device)))
     return out
+
+
+def instance_norm(x: torch.Tensor, relu: bool = False, eps: float = 1e-5) -> torch.Tensor:
+    """``nn.InstanceNorm2d(C)(x)`` (affine=False, no running stats; optionally followed by ReLU) for a 4-D float32 CUDA
+    tensor, contiguous or channels-last (memory format preserved)."""
+    require_cuda(x, "x")
+    assert x.dim() == 4
+    N, C, H, W = x.shape
+    x = x if x.dtype == torch.float32 else x.float()
+    cl = C > 1 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+    if not cl:
+        x = x.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.comet_instance_norm_f32(x.data_ptr(), out.data_ptr(), N, C, H * W,
+                                               _lib.FMAPS_CHANNEL_LAST if cl else _lib.FMAPS_NCHW, int(relu), float(eps),
+                                               stream_ptr(x.device)))
+    return out

@@ -142,6 +142,11 @@ int comet_sample_features4d_cl_f32(const float* input, long long in_sb, const fl
 int comet_upsample_bilinear_ac_f32(const float* in, float* out, long long N, int C, int Hi, int Wi, int Ho, int Wo,
                                    int layout, comet_stream_t stream);
 
+/* nn.InstanceNorm2d(affine=False, eps) (+ ReLU when relu != 0) of the same encoder (blocks.py:128-131,
+ * comet/models/modules.py:86-90): per (sample, channel) plane of HW elements, biased variance. */
+int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int HW, int layout, int relu, float eps,
+                            comet_stream_t stream);
+
 /* ---- sin/cos encodings: comet/models/utils.py:37-101, :724-832 ----------- */
 /* get_2d_embedding(xy, C, cat_coords): xy (M,2) contiguous -> out (M, 2*C [+2 in front if cat_coords]). */
 int comet_embed2d_f32(const float* xy, float* out, long long M, int C, int cat_coords, comet_stream_t stream);

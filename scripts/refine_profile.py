@@ -35,3 +35,8 @@ with torch.no_grad():
         torch.cuda.synchronize()
         print(f"cudnn tf32={tf32}: patch gather {e0.elapsed_time(e1):.2f} ms, ShallowEncoder {e1.elapsed_time(e2):.2f} ms, "
               f"whole refine_track (6 it, depth-4 time-attention transformer) {t0.elapsed_time(t1):.2f} ms", flush=True)
+
+from torch.profiler import profile, ProfilerActivity
+with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+    refine_track(images, fnet, ftr, coarse, compute_score=True); torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))

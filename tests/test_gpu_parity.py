@@ -427,6 +427,20 @@ def test_bilinear_resize_matches_interpolate(cb, shape):
         assert got_cl.is_contiguous(memory_format=torch.channels_last)   # the memory format is preserved
 
 
+@pytest.mark.parametrize("shape", [(9, 32, 16, 16), (5, 32, 8, 8), (3, 32, 4, 4), (2, 5, 7, 3), (4, 1, 6, 6)])
+def test_instance_norm_matches_torch(cb, shape):
+    g = torch.Generator(device="cuda").manual_seed(19)
+    x = torch.randn(*shape, device="cuda", generator=g) * 3 + 1.5
+    norm = torch.nn.InstanceNorm2d(shape[1])
+    for relu in (False, True):
+        want = norm(x)
+        want = torch.relu(want) if relu else want
+        assert rel_to_max(host(cb.instance_norm(x, relu=relu)), host(want)) < 2e-6
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        got = cb.instance_norm(xcl, relu=relu)
+        assert got.stride() == xcl.stride() and rel_to_max(host(got), host(want)) < 2e-6
+
+
 def test_full_size_fine_config_channels_last(cb):
     """Fine tracker at full size with channels-last patch features == the NCHW result (same oracle slice)."""
     g = torch.Generator(device="cuda").manual_seed(2)
