@@ -455,6 +455,41 @@ def main():
                                      "what": "same step under torch.autocast(bf16): one tensor-core pass, bf16-rounded "
                                              "operands and volume, fp32 lookup (parity bar 2e-2)"}
 
+    # ---- the producer of the fine tracker's input (outside `value`): patch gather + ShallowEncoder for
+    # ONE sequence (8192 patches of a 16-frame 512x512 sequence), with the library's resize / instance-norm kernels and
+    # with the ATen ops the reference calls (F.interpolate, InstanceNorm2d) ----------------------------------------
+    if not args.no_variants:
+        import importlib
+
+        rt = importlib.import_module("comet_pose_estimation_b200.refine_track")  # (the package exports a function of that name)
+        torch.manual_seed(0)
+        enc = rt.ShallowEncoder(3).eval().to(dev).to(memory_format=torch.channels_last)
+        imgs = torch.rand(1, FINE["S"], 3, 512, 512, device=dev)
+        tl = (torch.rand(1, FINE["S"], FINE["P"], 2, device=dev) * (512 - 31)).int()
+
+        def producer():
+            with torch.no_grad():
+                return enc(rt.extract_patches(imgs, tl, 31))
+
+        res = {}
+        for tag, flag in (("library_kernels", True), ("aten_ops", False)):
+            rt.USE_LIBRARY_KERNELS = flag
+            for _ in range(2):
+                producer()
+            barrier()
+            e0.record()
+            for _ in range(3):
+                producer()
+            e1.record()
+            barrier()
+            res[tag] = max_over_ranks(e0.elapsed_time(e1)) / 3
+        rt.USE_LIBRARY_KERNELS = True
+        variants["patch_encoder"] = {"ms_per_sequence": res["library_kernels"], "ms_per_sequence_aten_ops": res["aten_ops"],
+                                     "what": "refine_track's producer of the fine patch features (extract_patches + "
+                                             "ShallowEncoder, channels-last, cuDNN convolutions) for one sequence: "
+                                             "library resize + instance-norm kernels vs the ATen ops"}
+        del enc, imgs, tl
+
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------
     e2e = None
     if not args.no_e2e:

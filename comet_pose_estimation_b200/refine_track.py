@@ -28,12 +28,16 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# False routes the encoder's resizes / instance norms through the ATen ops even on the GPU (A/B timing in bench.py)
+USE_LIBRARY_KERNELS = True
+
+
 def _resize(x: torch.Tensor, size) -> torch.Tensor:
     """``F.interpolate(x, size, mode="bilinear", align_corners=True)``.  On the GPU (inference, float32) this is the
     library's own kernel: ATen's up-sampling kernel walks batch x channels inside every thread and, at 8192 patches,
     is 90 % of ``refine_track`` (192-314 ms per sequence on B200 against ~1 ms here).  Anything else (CPU tensors in
     the host-logic tests, autograd) takes the torch op."""
-    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+    if USE_LIBRARY_KERNELS and x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
         from .utils import upsample_bilinear_align_corners
 
         return upsample_bilinear_align_corners(x, size)
@@ -43,7 +47,7 @@ def _resize(x: torch.Tensor, size) -> torch.Tensor:
 def _inorm(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool) -> torch.Tensor:
     """``relu(norm(x))`` / ``norm(x)``: the library's instance-norm kernel for float32 CUDA inference (ATen routes
     InstanceNorm2d through batch_norm over N*C channels: 8.6 ms per sequence at 8192 patches), torch otherwise."""
-    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+    if USE_LIBRARY_KERNELS and x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
         from .utils import instance_norm
 
         return instance_norm(x, relu=relu, eps=norm.eps)
