@@ -271,7 +271,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="sequences per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--cpu-reps", type=int, default=30, help="CPU baseline: sequences timed after one warm-up (~0.27 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
@@ -301,6 +301,10 @@ def main():
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     import comet_pose_estimation_b200 as cb
+    from comet_pose_estimation_b200 import launch as cl
+
+    # host buffers node-local to the GPU (matters for the end-to-end arm once several ranks copy at the same time)
+    prev_affinity = cl.bind_to_gpu_numa_node(local) if world > 1 else None
 
     Q = args.batch
     host = make_inputs(Q, 1000 + rank, torch, pin=True, fine_layout=args.fine_layout)
@@ -523,6 +527,8 @@ def main():
                "api": "CorrBlock + TrackTokenizer (ctypes -> C ABI), pinned host tensors"}
         del stage
 
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, mean_s, ncores = cpu_reference_seq_per_s(torch, args.cpu_reps)
@@ -537,6 +543,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
                        "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
+                       "numa_bound": prev_affinity is not None,
                        "fine_layout": args.fine_layout + (" (channels-last view of the patch encoder output, as "
                                                           "comet_pose_estimation_b200.refine_track produces it)"
                                                           if args.fine_layout == "cl" else " (contiguous)"),

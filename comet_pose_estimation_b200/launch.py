@@ -42,6 +42,46 @@ def init_distributed(backend: Optional[str] = None) -> Dict[str, int]:
     return env
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (read from sysfs), so that pinned host buffers
+    allocated afterwards are node-local and H2D copies of several ranks do not cross the socket interconnect.
+    Returns the previous affinity (to restore with ``os.sched_setaffinity(0, prev)``) or None if nothing was changed
+    (no sysfs entry, single node, not Linux)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
+    except Exception:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception:
+            return None
+    try:
+        bus = str(bus).lower()
+        if len(bus.split(":")[0]) == 8:  # nvml reports a 32-bit domain
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = []
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.extend(range(int(a), int(b or a) + 1))
+        prev = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in prev]
+        if not cpus or len(cpus) == len(prev):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     """Sequences owned by ``rank``: r, r+W, r+2W, ... (round-robin keeps ranks within one item of each other)."""
     assert 0 <= rank < world

@@ -383,6 +383,22 @@ def test_channels_last_fmaps_are_used_zero_copy(cb, shape):
     x = cb.TrackTokenizer(blk, coords[:, 0], tdim).tokens(coords, feats)
     x_ref = cb.TrackTokenizer(ref, coords[:, 0], tdim).tokens(coords, feats)
     assert rel_to_max(host(x), host(x_ref)) < 1e-5
+    # the autocast (bf16 rounding) variant of the same kernels, both layouts, against the oracle's bf16 restatement
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        a = cb.CorrBlock(fcl, num_levels=L, radius=r)
+        a.corr(feats)
+        out_cl = a.sample(coords)
+        b = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+        b.corr(feats)
+        out_nchw = b.sample(coords)
+        x_bf = cb.TrackTokenizer(a, coords[:, 0], tdim).tokens(coords, feats)
+    want_bf = O.corr_lookup_bf16_autocast(host(fmaps), host(feats), host(coords), L, r)
+    assert rel_to_max(host(out_cl), want_bf) < 4e-3
+    assert rel_to_max(host(out_cl), host(out_nchw)) < 4e-3
+    WW = (2 * r + 1) ** 2
+    pos = cb.TrackTokenizer(a, coords[:, 0], tdim).pos
+    assert rel_to_max(host((x_bf[..., C + 2:C + 2 + L * WW] - pos[:, :, None, C + 2:C + 2 + L * WW]).permute(0, 2, 1, 3)),
+                      host(out_cl)) < 1e-5
 
 
 def test_channels_last_point_sampler_and_cached_pos_emb(cb, golden):
