@@ -499,6 +499,8 @@ def test_tensor_path_degenerate_query_sets(cb):
     c = torch.rand(1, S, 257, 2, device="cuda", generator=g) * 63
     c[..., 1] = c[..., 1] * 0.02 + 62.5   # band hugging the bottom border
     sets["bottom_band"] = c
+    # more than 256 query tiles per frame: the plan kernel stops tracking bands and every job covers the full maps
+    sets["more_tiles_than_tracked"] = torch.rand(1, S, 256 * 128 + 77, 2, device="cuda", generator=g) * 66 - 1.5
     for name, coords in sets.items():
         N = coords.shape[2]
         feats = torch.randn(1, S, N, 128, device="cuda", generator=g)
