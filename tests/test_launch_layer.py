@@ -86,3 +86,16 @@ def test_cuda_graph_replay_matches_eager():
         got = runner(c, f).clone()
         want = tok.tokens(c, f)
         assert torch.equal(got, want)
+
+
+def test_numa_binding_is_a_noop_without_a_gpu_or_sysfs():
+    """bind_to_gpu_numa_node never raises: without a CUDA device / sysfs entry it changes nothing and returns None."""
+    import os
+
+    from comet_pose_estimation_b200 import launch
+
+    before = sorted(os.sched_getaffinity(0))
+    prev = launch.bind_to_gpu_numa_node(0)
+    if prev is not None:  # a GPU box with several NUMA nodes: restore
+        os.sched_setaffinity(0, prev)
+    assert sorted(os.sched_getaffinity(0)) == before
