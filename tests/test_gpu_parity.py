@@ -140,6 +140,35 @@ def test_edge_cases(cb):
     assert rel_to_max(host(blk.sample(c)), want) < FP32_BAR
 
 
+def test_edge_cases_tensor_and_channels_last_paths(cb):
+    """Empty inputs through the specialised paths: no queries on the tcgen05 path, no maps / no queries on the
+    channels-last TMA path, empty batches through the encoder kernels."""
+    f = torch.randn(1, 2, 128, 64, 64, device="cuda")
+    blk = cb.CorrBlock(f, num_levels=5, radius=4)
+    blk.corr(torch.zeros(1, 2, 0, 128, device="cuda"))
+    c0 = torch.zeros(1, 2, 0, 2, device="cuda")
+    assert blk.sample(c0).shape == (1, 2, 0, 405)
+    x = cb.TrackTokenizer(blk, c0[:, 0], 664).tokens(c0, torch.zeros(1, 2, 0, 128, device="cuda"))
+    assert x.shape == (1, 0, 2, 664)
+    fcl = _channels_last_view(torch.randn(3, 2, 32, 31, 31, device="cuda"))
+    blk = cb.CorrBlock(fcl, num_levels=3, radius=3)
+    blk.corr(torch.zeros(3, 2, 0, 32, device="cuda"))
+    assert blk.sample(torch.zeros(3, 2, 0, 2, device="cuda")).shape == (3, 2, 0, 147)
+    empty = torch.zeros(0, 2, 32, 31, 31, device="cuda")
+    blk = cb.CorrBlock(empty, num_levels=3, radius=3)
+    blk.corr(torch.zeros(0, 2, 1, 32, device="cuda"))
+    assert blk.sample(torch.zeros(0, 2, 1, 2, device="cuda")).shape == (0, 2, 1, 147)
+    assert cb.upsample_bilinear_align_corners(torch.zeros(0, 32, 16, 16, device="cuda"), (31, 31)).shape == (0, 32, 31, 31)
+    assert cb.instance_norm(torch.zeros(0, 32, 8, 8, device="cuda"), relu=True).shape == (0, 32, 8, 8)
+    assert cb.sample_features4d(fcl[:0, 0], torch.zeros(0, 4, 2, device="cuda")).shape == (0, 4, 32)
+    # a single query and a single frame on the TMA path; coordinates far outside / non-finite -> zeros (zero padding)
+    one = _channels_last_view(torch.randn(1, 1, 32, 31, 31, device="cuda"))
+    blk = cb.CorrBlock(one, num_levels=3, radius=3)
+    blk.corr(torch.randn(1, 1, 1, 32, device="cuda"))
+    for bad in (1.0e9, -1.0e9, float("inf")):
+        assert float(blk.sample(torch.full((1, 1, 1, 2), bad, device="cuda")).abs().max()) == 0.0
+
+
 # ------------------------------------------------------------------ samplers / encodings
 def test_samplers_vs_reference_golden(cb, golden):
     g = golden("samplers_encodings")
