@@ -974,13 +974,15 @@ static int device_is_sm100() {
 
 static long long* g_stamps = nullptr;
 
-static int* status_word() {
-  static int* d = nullptr;
-  if (!d) {
-    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(d, 0, sizeof(int));
+static int* status_word() {   // one watchdog word per device (a process may drive several GPUs)
+  static int* d[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
+  if (!d[dev]) {
+    if (cudaMalloc(&d[dev], sizeof(int)) != cudaSuccess) { cudaGetLastError(); d[dev] = nullptr; return nullptr; }
+    cudaMemset(d[dev], 0, sizeof(int));
   }
-  return d;
+  return d[dev];
 }
 
 // Work decomposition chosen on the host: `nsplit` level-0 row chunks + `npyr` pyramid jobs per (frame, query tile),
