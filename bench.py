@@ -502,30 +502,50 @@ def main():
         out_f = torch.empty(td_f.shape, dtype=torch.float32).pin_memory()
         h2d = sum(t.numel() * 4 for v in host.values() for t in v.values())
         d2h = out_c.numel() * 4 + out_f.numel() * 4
-        stage = {k: {n: torch.empty_like(t, device=dev) for n, t in v.items()} for k, v in host.items()}
+        # Two device-side staging sets: the H2D copy of step i+1 (copy stream) overlaps the kernels and the D2H of step i
+        # (current stream).  Every step still copies all of its inputs from pinned host memory and reads its result
+        # back; the pipeline fill (first copy) is inside the timed region.
+        stages = [{k: {n: torch.empty_like(t, device=dev) for n, t in v.items()} for k, v in host.items()}
+                  for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step():
-            for k, v in host.items():
-                for n, t in v.items():
-                    stage[k][n].copy_(t, non_blocking=True)
-            a, b = hp.run(stage)
-            out_c.copy_(a, non_blocking=True)
-            out_f.copy_(b, non_blocking=True)
+        def issue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])       # the kernels of step i-2 are done with this set
+                for k, v in host.items():
+                    for n, t in v.items():
+                        stages[i % 2][k][n].copy_(t, non_blocking=True)
+                copied[i % 2].record(copy_stream)
 
-        n_e2e = max(2, min(args.steps, 5))
-        for _ in range(2):
-            e2e_step()
+        def e2e_run(nsteps):
+            cur = torch.cuda.current_stream(dev)
+            for ev in consumed:
+                ev.record(cur)
+            issue_copy(0)
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    issue_copy(i + 1)
+                cur.wait_event(copied[i % 2])
+                a, b = hp.run(stages[i % 2])
+                consumed[i % 2].record(cur)
+                out_c.copy_(a, non_blocking=True)
+                out_f.copy_(b, non_blocking=True)
+
+        n_e2e = max(2, min(args.steps, 10))
+        e2e_run(2)
         barrier()
         e0.record()
-        for _ in range(n_e2e):
-            e2e_step()
+        e2e_run(n_e2e)
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
         e2e = {"value": Q * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": n_e2e,
-               "api": "CorrBlock + TrackTokenizer (ctypes -> C ABI), pinned host tensors"}
-        del stage
+               "api": "CorrBlock + TrackTokenizer (ctypes -> C ABI), pinned host tensors; H2D of step i+1 overlapped "
+                      "with the kernels / D2H of step i (two staging sets)"}
+        del stages
 
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
