@@ -172,3 +172,42 @@ extern "C" int comet_instance_norm_f32(const float* in, float* out, long long N,
   comet::instance_norm_nchw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N * C, HW, eps, relu);
   return comet::launch_status("instance_norm_nchw_kernel");
 }
+
+// ---- patch gather of refine_track (comet/models/refine_track.py:71-111) ----------------------------------------------
+// The reference unfolds the image into all psize x psize windows (a view) and picks N of them per frame with advanced
+// indexing, in (b s n) order.  Here one thread writes one output pixel (all C channels) of patch (b, n, s) -- the order
+// the fine tracker consumes -- in channel-last memory, straight from the NCHW image.
+namespace comet {
+__global__ void __launch_bounds__(256) extract_patches_kernel(const float* __restrict__ images, const int* __restrict__ topleft,
+                                                              float* __restrict__ out, int B, int S, int N, int C, int H, int W,
+                                                              int P) {
+  const long long total = (long long)B * N * S * P * P;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(idx % P);
+    long long t = idx / P;
+    const int py = (int)(t % P);
+    t /= P;                                  // patch index in (b, n, s) order
+    const int s = (int)(t % S);
+    const long long bn = t / S;
+    const int n = (int)(bn % N), b = (int)(bn / N);
+    const int* tl = topleft + (((long long)b * S + s) * N + n) * 2;   // (B,S,N,2) = (x, y)
+    const int x = __ldg(tl) + px, y = __ldg(tl + 1) + py;
+    const float* img = images + ((long long)b * S + s) * C * H * W + (long long)y * W + x;
+    float* o = out + idx * C;
+    for (int c = 0; c < C; ++c) o[c] = __ldg(img + (long long)c * H * W);
+  }
+}
+}  // namespace comet
+
+extern "C" int comet_extract_patches_f32(const float* images, const int* topleft, float* out, int B, int S, int N, int C,
+                                         int H, int W, int P, comet_stream_t stream) {
+  COMET_REQUIRE(B >= 0 && S >= 0 && N >= 0 && C >= 1 && P >= 1 && H >= P && W >= P, "bad shape");
+  const long long total = (long long)B * N * S * P * P;
+  if (total == 0) return COMET_OK;
+  COMET_REQUIRE(images && topleft && out, "null pointer");
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  comet::extract_patches_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(images, topleft, out, B, S, N, C, H, W, P);
+  return comet::launch_status("extract_patches_kernel");
+}

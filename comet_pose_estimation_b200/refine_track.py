@@ -117,6 +117,17 @@ def extract_patches(images: torch.Tensor, topleft: torch.Tensor, psize: int) -> 
     B, S, C, H, W = images.shape
     N = topleft.shape[2]
     dev = images.device
+    if USE_LIBRARY_KERNELS and images.is_cuda and images.dtype == torch.float32:
+        from . import _lib
+        from ._dev import stream_ptr
+
+        img = images.contiguous()
+        tl32 = topleft.to(torch.int32).contiguous()
+        out = torch.empty((B * N * S, psize, psize, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.comet_extract_patches_f32(img.data_ptr(), tl32.data_ptr(), out.data_ptr(), B, S, N, C, H, W,
+                                                          psize, stream_ptr(dev)))
+        return out.permute(0, 3, 1, 2)  # NCHW shape, NHWC memory
     ar = torch.arange(psize, device=dev)
     tl = topleft.permute(0, 2, 1, 3).long()                       # (B,N,S,2)
     ys = tl[..., 1, None] + ar                                    # (B,N,S,p)

@@ -147,6 +147,12 @@ int comet_upsample_bilinear_ac_f32(const float* in, float* out, long long N, int
 int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int HW, int layout, int relu, float eps,
                             comet_stream_t stream);
 
+/* Patch gather of refine_track (comet/models/refine_track.py:71-111): images (B,S,C,H,W) contiguous, topleft (B,S,N,2)
+ * int32 (x, y) corners already clamped to [0, W-P] x [0, H-P] -> out (B*N*S, P, P, C) channel-last, patches in
+ * (b, n, s) order. */
+int comet_extract_patches_f32(const float* images, const int* topleft, float* out, int B, int S, int N, int C, int H, int W,
+                              int P, comet_stream_t stream);
+
 /* ---- sin/cos encodings: comet/models/utils.py:37-101, :724-832 ----------- */
 /* get_2d_embedding(xy, C, cat_coords): xy (M,2) contiguous -> out (M, 2*C [+2 in front if cat_coords]). */
 int comet_embed2d_f32(const float* xy, float* out, long long M, int C, int cat_coords, comet_stream_t stream);

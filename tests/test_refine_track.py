@@ -124,6 +124,26 @@ def test_compute_score_indexing_quirk(golden):
 
 
 @pytest.mark.gpu
+def test_patch_gather_kernel_matches_torch_indexing():
+    import importlib
+
+    rt = importlib.import_module("comet_pose_estimation_b200.refine_track")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    images = torch.rand(2, 3, 3, 70, 70, device="cuda", generator=g)
+    tl = torch.randint(0, 70 - 31 + 1, (2, 3, 9, 2), device="cuda", generator=g, dtype=torch.int32)
+    tl[0, 0, 0] = 0
+    tl[1, 2, 8] = 70 - 31
+    a = rt.extract_patches(images, tl, 31)
+    rt.USE_LIBRARY_KERNELS = False
+    try:
+        b = rt.extract_patches(images, tl, 31)
+    finally:
+        rt.USE_LIBRARY_KERNELS = True
+    assert a.shape == b.shape == (2 * 9 * 3, 3, 31, 31) and a.stride() == b.stride()
+    assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
 def test_dropin_refine_track_matches_reference(golden):
     from comet_pose_estimation_b200.refine_track import refine_track
 
