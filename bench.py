@@ -155,7 +155,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -328,10 +328,10 @@ def main():
         return float(t.item())
 
     # ---- device-resident arm ------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None   # samples every 20 ms from the warm-up to the end of the timed region
     for _ in range(args.warmup):
         hp.run(devin)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = cb._lib.lib.comet_launch_count()
     hp.events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
