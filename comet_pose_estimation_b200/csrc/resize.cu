@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(256) extract_patches_kernel(const float* __res
     const long long bn = t / S;
     const int n = (int)(bn % N), b = (int)(bn / N);
     const int* tl = topleft + (((long long)b * S + s) * N + n) * 2;   // (B,S,N,2) = (x, y)
-    const int x = __ldg(tl) + px, y = __ldg(tl + 1) + py;
+    // corners are clamped to the image (memory safety for arbitrary callers; refine_track already hands over
+    // clamped corners, for which this is the identity)
+    const int x = min(max(__ldg(tl), 0), W - P) + px, y = min(max(__ldg(tl + 1), 0), H - P) + py;
     const float* img = images + ((long long)b * S + s) * C * H * W + (long long)y * W + x;
     float* o = out + idx * C;
     for (int c = 0; c < C; ++c) o[c] = __ldg(img + (long long)c * H * W);

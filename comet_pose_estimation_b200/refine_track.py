@@ -113,10 +113,13 @@ class ShallowEncoder(nn.Module):
 def extract_patches(images: torch.Tensor, topleft: torch.Tensor, psize: int) -> torch.Tensor:
     """``images`` (B,S,C,H,W), ``topleft`` (B,S,N,2) integer (x, y) corners -> patches (B*N*S, C, psize, psize) in
     (b, n, s) order, channels-last memory format.  Same pixels as the reference's unfold + advanced indexing
-    (refine_track.py:71-111) without the (B*S, N, C, p, p) intermediate in (s, n) order."""
+    (refine_track.py:71-111) without the (B*S, N, C, p, p) intermediate in (s, n) order.  Corners outside
+    [0, W-psize] x [0, H-psize] are clamped to it (the reference's indexing would raise IndexError)."""
     B, S, C, H, W = images.shape
     N = topleft.shape[2]
     dev = images.device
+    assert H >= psize and W >= psize, "images smaller than the patch"
+    topleft = torch.stack([topleft[..., 0].clamp(0, W - psize), topleft[..., 1].clamp(0, H - psize)], dim=-1)
     if USE_LIBRARY_KERNELS and images.is_cuda and images.dtype == torch.float32:
         from . import _lib
         from ._dev import stream_ptr
@@ -151,7 +154,9 @@ def refine_track(images, fine_fnet, fine_tracker, coarse_pred, pradius=15, sradi
     track_frac = coarse_pred - track_int
     topleft = track_int - pradius
     topleft_BSN = topleft.clone()
-    topleft = topleft.clamp(0, H - psize)  # the reference assumes H == W here (refine_track.py:93-96)
+    # the reference clamps both axes with H - psize (refine_track.py:93-96: it assumes H == W and raises IndexError
+    # otherwise); clamping x with W and y with H is the same for square images and stays in bounds for the others
+    topleft = torch.stack([topleft[..., 0].clamp(0, W - psize), topleft[..., 1].clamp(0, H - psize)], dim=-1)
 
     with torch.no_grad():
         patch_input = extract_patches(images, topleft, psize)
@@ -174,6 +179,13 @@ def refine_track(images, fine_fnet, fine_tracker, coarse_pred, pradius=15, sradi
     if compute_score:
         score = compute_score_fn(query_point_feat, patch_feat, fine_pred_track, sradius, psize, B, N, S, C_out)
     return refined_tracks, score
+
+
+def inverted_score(track_score: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """``COMET.forward_all``'s conversion of the fine tracker's score into the track confidence the camera predictor
+    consumes (E2Epose2.py:232-236): ``1 / (score + eps)`` normalised by its maximum over the frames of each track."""
+    inv = 1.0 / (track_score + eps)
+    return inv / inv.max(dim=1, keepdim=True)[0]
 
 
 def compute_score_fn(query_point_feat, patch_feat, fine_pred_track, sradius, psize, B, N, S, C_out):

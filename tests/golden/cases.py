@@ -97,3 +97,45 @@ def refine_case(seed, B, S, N, HW):
     coarse[:, 0] = q[:, 0].astype(F32)
     coarse = np.clip(coarse, 0.0, HW - 1.001).astype(F32)
     return images, coarse
+
+
+# ---- full-size (shipped) configurations: weights by name from a counter-based seed -------------------------------
+def seeded_state_dict(shapes, seed, flow_head_gain=1.0):
+    """Deterministic weights for a module, keyed by parameter NAME (not by construction order), so the fixture
+    generator (reference classes) and the tests (this package's classes) build bit-identical 170 MB state dicts
+    without committing them.  ``shapes``: {name: shape}.  Distribution: what torch's default initialisers give in
+    magnitude -- matrices / conv kernels U(-1/sqrt(fan_in), 1/sqrt(fan_in)), biases U(-0.05, 0.05), 1-D ``weight``
+    (affine norms) 1 + 0.1 N(0,1), the learned virtual tracks N(0,1)."""
+    import zlib
+
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(int(s) for s in shapes[name])
+        rng = np.random.default_rng([int(seed), zlib.crc32(name.encode())])
+        if name.endswith("virual_tracks"):
+            a = rng.standard_normal(shape)
+        elif len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            b = 1.0 / np.sqrt(fan_in)
+            a = rng.uniform(-b, b, shape)
+            if "flow_head" in name:
+                a = a * flow_head_gain
+        elif name.endswith("weight"):
+            a = 1.0 + 0.1 * rng.standard_normal(shape)
+        else:
+            a = rng.uniform(-0.05, 0.05, shape)
+            if "flow_head" in name:
+                a = a * flow_head_gain
+        out[name] = a.astype(F32)
+    return out
+
+
+# shipped tracker configuration (abl_ours.yaml:399-428): coarse 4 iterations, fine 6 iterations (refine_track.py:136)
+FULL_COARSE_CTOR = dict(stride=4, corr_levels=5, corr_radius=4, latent_dim=128, hidden_size=384, depth=6,
+                        use_spaceatt=True, fine=False)
+FULL_FINE_CTOR = dict(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=256, depth=4,
+                      use_spaceatt=False, fine=True)   # abl_ours.yaml:419-428
+FULL_COARSE_CASE = dict(seed=61, B=1, S=16, C=128, H=64, W=64, N=512, stride=4, down_ratio=2)
+FULL_COARSE_ITERS = 4
+FULL_REFINE_CASE = dict(seed=62, B=1, S=16, N=512, HW=512)
+FULL_SEEDS = dict(coarse=71, fine=72, fnet=73, camera=74)
