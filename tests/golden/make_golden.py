@@ -184,6 +184,26 @@ def main():
             out[name + "/query_feat"] = qf.numpy()
             for k, v in m.state_dict().items():
                 out[f"{name}/sd/{k}"] = v.numpy()
+            # the same run in float64: the yard-stick for the per-iteration bars (tests/test_tracker_loop.py).  The
+            # reference casts its float64-built sin/cos table to float32 (utils.py:724-755) and F.grid_sample refuses
+            # mixed dtypes, so for this run only the table is widened back to float64 (same values).
+            toks64 = []
+            m64 = m.double()
+            h = m64.updateformer.register_forward_pre_hook(lambda mod, args: toks64.append(args[0].detach().clone().numpy()))
+            orig = btp.get_2d_sincos_pos_embed
+            btp.get_2d_sincos_pos_embed = lambda *a, **k: orig(*a, **k).double()
+            try:
+                res64 = m64(query_points=t(q).double(), fmaps=t(fmaps).double(), iters=iters, return_feat=True,
+                            down_ratio=dr, TRACKorPOSE=False)
+            finally:
+                btp.get_2d_sincos_pos_embed = orig
+                h.remove()
+            for i, p64 in enumerate(res64[0]):
+                out[f"{name}/pred64_{i}"] = p64.numpy()
+                out[f"{name}/tok64_{i}"] = toks64[i]
+            out[name + "/track_feats64"] = res64[2].numpy()
+            if res64[1] is not None:
+                out[name + "/vis64"] = res64[1].numpy()
     save("tracker", **out)
 
     # ---- refine_track: patch extraction -> ShallowEncoder -> fine tracker -> score ----------------------

@@ -26,14 +26,21 @@ SPECS = {
 }
 
 
-# Per-iteration bars.  Iteration 0 is a pure function of the inputs: fp32 bar 1e-4 (observed ~1e-7).  From iteration
-# 1 on, the tokens contain sin/cos(flow * k * 1000/C) (utils.py:84-96): a 1e-7 relative difference in the previous
-# iteration's coordinates (different-but-valid fp32 summation order inside matmul / softmax) is multiplied by up to
-# ~1e3 inside the sine argument, so ANY two fp32 implementations (including the reference on CPU vs GPU) drift
-# apart by ~1e3 per iteration in those channels.  The bars below bound that drift; the kernels themselves are held
-# to 1e-4 on identical inputs by the other tests.
-PRED_BARS = [1e-4, 1e-4, 2e-2, 2e-1]
-TOK_BARS = [1e-4, 5e-3, 1e-1, 1.0]
+# Per-iteration bars.  From iteration 1 on the tokens contain sin/cos(flow * k * 1000/C) (utils.py:84-96): rounding
+# differences in the previous iteration's coordinates are multiplied by up to ~1e3 inside the sine argument, so ANY two
+# float32 implementations drift apart.  How much is not asserted but MEASURED: tracker.npz holds the reference's own
+# float32 and float64 runs of every case, and an implementation passes iteration i when
+#     |impl - ref64| / max|ref64| <= max(1e-4, 3 * |ref32 - ref64| / max|ref64|)
+# -- the north-star float32 tolerance, or three times the reference's own float32 noise where that is larger.  Every
+# kernel is held to 1e-4 on identical inputs by the other tests; tests/test_full_size.py applies the same criterion at
+# the shipped sizes.
+SPEC = 1e-4
+
+
+def bar(g, name, what, i=None):
+    k32 = f"{name}/{what}{i}" if i is not None else f"{name}/{what}"
+    k64 = f"{name}/{what}64_{i}" if i is not None else f"{name}/{what}64"
+    return max(SPEC, 3.0 * rel_to_max(g[k32], g[k64])), g[k64]
 
 
 def cfg(eff):
@@ -77,10 +84,21 @@ def test_oracle_loop_with_torch_updateformer(golden, name):
             iters=iters, stride=ck["stride"], corr_levels=ck["corr_levels"], corr_radius=ck["corr_radius"],
             latent_dim=ck["latent_dim"], fine=ck["fine"], down_ratio=dr, efficient_corr=eff)
     for i in range(iters):
-        assert rel_to_max(toks[i], g[f"{name}/tok{i}"]) < TOK_BARS[i]
-        assert rel_to_max(preds[i], g[f"{name}/pred{i}"]) < PRED_BARS[i]
-    assert rel_to_max(feats, g[name + "/track_feats"]) < PRED_BARS[iters - 1] * 10
+        b, ref = bar(g, name, "tok", i)
+        assert rel_to_max(toks[i], ref) <= b, (i, "tokens")
+        b, ref = bar(g, name, "pred", i)
+        assert rel_to_max(preds[i], ref) <= b, (i, "tracks")
+    b, ref = bar(g, name, "track_feats")
+    assert rel_to_max(feats, ref) <= b
     assert rel_to_max(qfeat, g[name + "/query_feat"]) < 1e-5
+
+
+def test_fixture_holds_the_reference_drift(golden):
+    """The fixtures demonstrate the drift statement above: iteration 0 of the reference agrees between float32 and
+    float64 to ~1e-7, and the difference grows by orders of magnitude per iteration."""
+    g = golden("tracker")
+    d = [rel_to_max(g[f"coarse_tiny/pred{i}"], g[f"coarse_tiny/pred64_{i}"]) for i in range(3)]
+    assert d[0] < 1e-6 and d[2] > 20 * d[0]
 
 
 @pytest.mark.gpu
@@ -100,14 +118,18 @@ def test_dropin_predictor_matches_reference(golden, name):
     h.remove()
     assert conf is None and len(preds) == iters
     for i in range(iters):
-        assert rel_to_max(toks[i], g[f"{name}/tok{i}"]) < TOK_BARS[i]
-        assert rel_to_max(preds[i].cpu().numpy(), g[f"{name}/pred{i}"]) < PRED_BARS[i]
-    assert rel_to_max(feats.cpu().numpy(), g[name + "/track_feats"]) < PRED_BARS[iters - 1] * 10
+        b, ref = bar(g, name, "tok", i)
+        assert rel_to_max(toks[i], ref) <= b, (i, "tokens")
+        b, ref = bar(g, name, "pred", i)
+        assert rel_to_max(preds[i].cpu().numpy(), ref) <= b, (i, "tracks")
+    b, ref = bar(g, name, "track_feats")
+    assert rel_to_max(feats.cpu().numpy(), ref) <= b
     assert rel_to_max(qfeat.cpu().numpy(), g[name + "/query_feat"]) < 1e-5
     if ck["fine"]:
         assert vis is None
     else:
-        assert rel_to_max(vis.cpu().numpy(), g[name + "/vis"]) < PRED_BARS[iters - 1] * 10
+        b, ref = bar(g, name, "vis")
+        assert rel_to_max(vis.cpu().numpy(), ref) <= b
 
 
 @pytest.mark.gpu
@@ -128,5 +150,7 @@ def test_dropin_predictor_coarse_shape_uses_tensor_path():
             b = m(query_points=q, fmaps=fmaps, iters=3, down_ratio=2, TRACKorPOSE=False)[0]
         finally:
             os.environ["COMET_B200_DISABLE_TC"] = "0"
+    # two float32 implementations of the same loop: iteration 0 within the spec, later ones bounded by the drift the
+    # reference shows between its own float32 and float64 runs at this size (tracker_full.npz: 2.5e-5, 5.7e-3)
     for i, (x, y) in enumerate(zip(a, b)):
-        assert rel_to_max(x.cpu().numpy(), y.cpu().numpy()) < PRED_BARS[i]
+        assert rel_to_max(x.cpu().numpy(), y.cpu().numpy()) < [1e-4, 1e-3, 5e-2][i]
