@@ -52,3 +52,15 @@ def pad_mode(padding_mode: str) -> int:
     if padding_mode == "border":
         return _lib.PAD_BORDER
     raise ValueError(f"padding_mode {padding_mode!r} is not supported (the reference path uses 'zeros' and 'border')")
+
+
+def require_no_grad(*tensors: torch.Tensor) -> None:
+    """The kernels are forward-only (the reference runs the tracker frozen under ``torch.no_grad()``,
+    E2Epose2.py:176, train_util.py:311-318).  Outputs are written into fresh buffers without an autograd node, so a
+    call that autograd would have to differentiate through is refused instead of silently dropping the gradient."""
+    if torch.is_grad_enabled():
+        for t in tensors:
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                raise RuntimeError(
+                    "comet_pose_estimation_b200 kernels are forward-only: an input requires grad while autograd is "
+                    "enabled. Run the tracker under torch.no_grad() (as COMET.forward_all does) or detach the inputs.")

@@ -17,6 +17,7 @@ PREC_F32, PREC_BF16_AUTOCAST = 0, 1
 PYR_NCHW, PYR_CHANNEL_LAST, PYR_ALL_CHANNEL_LAST = 0, 1, 2
 FMAPS_NCHW, FMAPS_CHANNEL_LAST = 0, 1
 MAX_LEVELS, MAX_RADIUS = 8, 7
+OPT_TENSOR_PATH, OPT_TMA_LOOKUP = 0, 1
 
 _p = C.c_void_p
 _i = C.c_int
@@ -58,7 +59,8 @@ SIGNATURES = {
                                        _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "comet_tc_corr_volume_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "comet_tc_status": (_i, []),
-    "comet_tc_debug_stamps": (None, [_p]),
+    "comet_set_option": (_i, [_i, _i]),
+    "comet_get_option": (_i, [_i]),
 }
 
 
@@ -81,6 +83,13 @@ def _load():
 
 
 lib = _load()
+
+
+def set_option(option: int, value: bool) -> bool:
+    """Library-wide A/B switch (``OPT_TENSOR_PATH``, ``OPT_TMA_LOOKUP``); returns the previous value."""
+    prev = bool(lib.comet_get_option(option))
+    check(lib.comet_set_option(option, int(bool(value))))
+    return prev
 
 
 def last_error() -> str:

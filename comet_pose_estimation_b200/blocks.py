@@ -2,24 +2,28 @@
 (comet/models/track_modules/blocks.py:351-484), computed by the fused sm_100a kernels.
 
 Differences a caller can observe: none in results (parity tests) -- but the correlation volume is never
-materialised by ``corr()``/``sample()``; ``corrs_pyramid`` is produced lazily only if somebody reads it."""
+materialised by ``corr()``/``sample()``; ``corrs_pyramid`` is produced lazily only if somebody reads it.  One
+consequence: ``corr(targets)`` keeps a *reference* to ``targets`` and the fused kernel reads it at ``sample()`` time,
+whereas the reference computes the volume inside ``corr()``.  A caller that mutates ``targets`` in place between the
+two calls would get different numbers, so that case is detected (tensor version counter) and refused.  The kernels
+are forward-only (the reference runs the tracker under ``torch.no_grad()``)."""
 from __future__ import annotations
 
 import ctypes
-import os
 from typing import List, Optional
 
 import torch
 
 from . import _lib
-from ._dev import f32c, inner_contig, pad_mode, prec_mode, require_cuda, stream_ptr
+from ._dev import f32c, inner_contig, pad_mode, prec_mode, require_cuda, require_no_grad, stream_ptr
 
 lib = _lib.lib
 
 
 def tensor_path_enabled() -> bool:
-    """The tcgen05 kernels serve the dense coarse shape; COMET_B200_DISABLE_TC=1 forces the SIMT kernels (A/B runs)."""
-    return os.environ.get("COMET_B200_DISABLE_TC", "0") != "1" and bool(lib.comet_has_tensor_path())
+    """The tcgen05 kernels serve the dense coarse shape; ``_lib.set_option(_lib.OPT_TENSOR_PATH, False)`` forces the
+    SIMT kernels (A/B runs)."""
+    return bool(lib.comet_has_tensor_path())
 
 
 class _Pyramid:
@@ -28,6 +32,7 @@ class _Pyramid:
 
     def __init__(self, fmaps: torch.Tensor, num_levels: int):
         require_cuda(fmaps, "fmaps")
+        require_no_grad(fmaps)
         assert fmaps.dim() == 5, "fmaps must be (B, S, C, H, W)"
         B, S, C, H, W = fmaps.shape
         assert 1 <= num_levels <= _lib.MAX_LEVELS, f"num_levels must be in [1, {_lib.MAX_LEVELS}]"
@@ -64,7 +69,7 @@ class _Pyramid:
                 _lib.check(lib.comet_pyramid_f32(self.fmaps0.data_ptr(), self.pyr.data_ptr(), B * S, C, H, W,
                                                  num_levels, stream_ptr(fmaps.device)))
         self.levels: List[torch.Tensor] = [fmaps]
-        self._ws = None  # scratch of the tensor path (sorted query order + job list), sized for the last N seen
+        self._ws = {}  # scratch of the tensor path (sorted query order + job list) per CUDA stream
         h, w = H, W
         for l in range(1, num_levels):
             h, w = h // 2, w // 2
@@ -77,10 +82,15 @@ class _Pyramid:
 
 
 def _tc_workspace(pyr: "_Pyramid", N: int) -> torch.Tensor:
+    """Scratch of the tensor path, one buffer per CUDA stream (two streams driving the same CorrBlock never share a
+    plan).  It grows only when a larger N arrives: under CUDA-graph capture call once with the largest N first."""
     need = lib.comet_tc_workspace_bytes(pyr.B * pyr.S, N)
-    if pyr._ws is None or pyr._ws.numel() * 4 < need:
-        pyr._ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=pyr.fmaps0.device)
-    return pyr._ws
+    key = stream_ptr(pyr.fmaps0.device)
+    ws = pyr._ws.get(key)
+    if ws is None or ws.numel() * 4 < need:
+        ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=pyr.fmaps0.device)
+        pyr._ws[key] = ws
+    return ws
 
 
 def _use_tc(pyr: "_Pyramid", t: torch.Tensor, radius: int, padding: str, level_stride: int = 0) -> bool:
@@ -93,6 +103,7 @@ def _fused_lookup(pyr: _Pyramid, targets, coords, radius, padding, level_stride=
     assert D == 2
     require_cuda(coords, "coords")
     require_cuda(targets, "targets")
+    require_no_grad(coords, targets)
     t = inner_contig(targets)
     c = inner_contig(coords)
     Wr = 2 * radius + 1
@@ -142,7 +153,15 @@ class CorrBlock:
         assert S == self.S
         require_cuda(targets, "targets")
         self._targets = targets
+        self._targets_version = targets._version
         self._volumes = None
+
+    def _check_targets_unchanged(self):
+        if self._targets._version != self._targets_version:
+            raise RuntimeError(
+                "CorrBlock: `targets` was modified in place after corr(). The reference computes the correlation "
+                "volume inside corr(); this implementation reads `targets` when sample() / corrs_pyramid is "
+                "evaluated. Call corr() again with the updated tensor.")
 
     @property
     def corrs_pyramid(self):
@@ -151,6 +170,7 @@ class CorrBlock:
         if self._targets is None:
             raise AttributeError("'CorrBlock' object has no attribute 'corrs_pyramid' (call corr() first)")
         if self._volumes is None:
+            self._check_targets_unchanged()
             p = self._pyr
             B, S, N, _ = self._targets.shape
             t = f32c(self._targets).view(B * S, N, -1)
@@ -192,6 +212,7 @@ class CorrBlock:
         assert D == 2
         if self._targets is None:
             raise AttributeError("'CorrBlock' object has no attribute 'corrs_pyramid' (call corr() first)")
+        self._check_targets_unchanged()
         return _fused_lookup(self._pyr, self._targets, coords, self.radius, self.padding_mode,
                              self.C if self.multiple_track_feats else 0)
 

@@ -37,13 +37,14 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(PKG, "..", "include", "*.h")) + [__file__]
     have_tc = any(os.path.basename(s) == "corr_tc.cu" for s in srcs)
-    flags = NVCC_FLAGS + (["-DCOMET_HAVE_TC"] if have_tc else [])
+    flags = NVCC_FLAGS + (["-DCOMET_HAVE_TC"] if have_tc else []) + (["-DCOMET_TC_TRACE"] if trace else [])
+    force = force or trace   # a trace build (attribution switches + clock64 stamps in corr_tc.cu) never mixes objects
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
@@ -70,4 +71,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, trace="--trace" in sys.argv))

@@ -10,9 +10,18 @@ char* last_error_buf() {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_options[COMET_OPT_COUNT] = {{1}, {1}};   // every specialised path enabled
+int option(int which) { return (which >= 0 && which < COMET_OPT_COUNT) ? g_options[which].load(std::memory_order_relaxed) : 0; }
 }  // namespace comet
 
-extern "C" int comet_version(void) { return 100; /* 0.1.0, round 1 */ }
+extern "C" int comet_set_option(int option, int value) {
+  COMET_REQUIRE(option >= 0 && option < COMET_OPT_COUNT, "unknown option %d", option);
+  comet::g_options[option].store(value ? 1 : 0, std::memory_order_relaxed);
+  return COMET_OK;
+}
+extern "C" int comet_get_option(int option) { return comet::option(option); }
+
+extern "C" int comet_version(void) { return 200; /* 0.2.0, round 2 */ }
 extern "C" const char* comet_last_error(void) { return comet::last_error_buf(); }
 
 extern "C" long long comet_launch_count(void) { return comet::g_launches.load(std::memory_order_relaxed); }

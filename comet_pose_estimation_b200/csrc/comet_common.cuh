@@ -57,18 +57,23 @@ inline TensorMapEncodeFn tensor_map_encoder() {
   }
   return fn;
 }
-// SM count of the current device if it is compute capability 10.x, else 0 (no device: 0).
+// SM count of the CURRENT device if it is compute capability 10.x, else 0 (no device: 0).  Cached per device ordinal:
+// a process may drive several GPUs.
 inline int device_sm_count_if_sm100() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, major = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  static int cached[64];
+  static bool known[64] = {false};
+  int dev = 0, major = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 0; }
+  if (!known[dev]) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cached = (major == 10 && sms > 0) ? sms : 0;
+    cached[dev] = (major == 10 && sms > 0) ? sms : 0;
+    known[dev] = true;
   }
-  return cached;
+  return cached[dev];
 }
+// Library options (comet_set_option, cabi.cu): explicit A/B switches instead of environment variables on the launch path.
+int option(int which);
 
 // ---- pyramid geometry (host) -------------------------------------------
 struct Levels {

@@ -661,11 +661,7 @@ static int launch_lookup(const LookupParams& p, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) return fail(COMET_ERR_UNSUPPORTED, "too many queries for one launch");
   if (p.C == 32 && p.r >= 1 && p.r <= 3 && p.t_level_stride == 0 && ((uintptr_t)p.pyr % 16) == 0 &&
       (!p.cl0 || ((uintptr_t)p.fmaps % 16) == 0)) {
-    static int use_tma = -1;
-    if (use_tma < 0) {
-      const char* e = getenv("COMET_B200_DISABLE_TMA_LOOKUP");
-      use_tma = (!(e && atoi(e) == 1) && device_sm_count_if_sm100() > 0 && tensor_map_encoder() != nullptr) ? 1 : 0;
-    }
+    const bool use_tma = option(COMET_OPT_TMA_LOOKUP) && device_sm_count_if_sm100() > 0 && tensor_map_encoder() != nullptr;
     if (use_tma && p.cl0 && p.L <= 3 && total < (1LL << 40)) {
       TmaMaps maps;
       memset(&maps, 0, sizeof(maps));

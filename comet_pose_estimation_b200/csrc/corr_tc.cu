@@ -118,9 +118,19 @@ struct Params {
   const JobRec* jobs;   // [njobs]
   float inv_sqrt_c;
   int* status;  // device int: set non-zero by the watchdog
-  int debug;    // COMET_TC_DEBUG bit mask (attribution experiments; 0 in production)
-  long long* stamps;  // optional clock64 trace of CTA 0 (debug aid): [4 roles][64][2]
+#ifdef COMET_TC_TRACE
+  int debug;    // COMET_TC_DEBUG bit mask (attribution experiments)
+  long long* stamps;  // optional clock64 trace of CTA 0: [4 roles][64][2]
+#endif
 };
+
+// Attribution switches and clock64 stamps exist only in -DCOMET_TC_TRACE builds (scripts/gpu_tc_attr.sh); the
+// production kernel has no debug branch in its loops.
+#ifdef COMET_TC_TRACE
+#define TC_DBG(p, bit) (((p).debug & (bit)) != 0)
+#else
+#define TC_DBG(p, bit) false
+#endif
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,13 +166,25 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (fast, visible failure) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (visible failure) instead of hanging the GPU box.  The bound is WALL TIME
+// (10 s of %globaltimer, looked at every 4096 polls), not a poll count, so that compute-sanitizer, a debugger,
+// MPS or time-slicing cannot make it fire on a healthy kernel.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* status, int code) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      if (status) atomicExch(status, code);
-      __trap();
+    if ((++spins & 4095u) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) {
+        if (status) atomicExch(status, code);
+        __trap();
+      }
     }
   }
 }
@@ -248,7 +270,9 @@ __device__ __forceinline__ JobRec load_job(const Params& p, int job) {
 }
 
 __device__ __forceinline__ void stamp(const Params& p, int role, int idx, int which) {
+#ifdef COMET_TC_TRACE
   if (p.stamps && blockIdx.x == 0 && idx < 64) p.stamps[(role * 64 + idx) * 2 + which] = clock64();
+#endif
 }
 
 // Window geometry of one query along y at pyramid level l -- the ONE definition shared by the plan kernel (row
@@ -470,7 +494,7 @@ corr_tc_kernel(const Params p) {
             mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
             stamp(p, 0, tcount++, 0);
             uint8_t* dst = sB + stage * STAGE_BYTES;
-            if (p.debug & 64) {
+            if (TC_DBG(p, 64)) {
               mbar_arrive(&full[stage]);
             } else {
               // autocast mode issues the hi x hi pass only: fetch just the hi half of the stage
@@ -487,7 +511,7 @@ corr_tc_kernel(const Params p) {
     // ===================== MMA issuer =====================
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, ji = 0;
     int tcount = 0;
-    const int npass = (p.debug & 8) ? 0 : p.npass;
+    const int npass = TC_DBG(p, 8) ? 0 : p.npass;
     JobRec nxt = load_job(p, blockIdx.x);
     for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
       const JobRec jr = nxt;
@@ -620,7 +644,7 @@ corr_tc_kernel(const Params p) {
         float hprev[Wr];
 #pragma unroll
         for (int i = 0; i < Wr; ++i) hprev[i] = 0.f;
-        if (!VOLUME && !(p.debug & 1)) {
+        if (!VOLUME && !TC_DBG(p, 1)) {
           // claim a window buffer and clear it cooperatively (entries whose rows are off the map stay 0)
           const uint32_t wbuf = wu % NWIN;
           mbar_wait(&win_empty[wbuf * 4 + wq], ((wu / NWIN) & 1) ^ 1, p.status, 7);
@@ -635,7 +659,7 @@ corr_tc_kernel(const Params p) {
           const TileInfo ti = tile_info(t);
           const int ylast = ti.y_first + ti.rows - 1;
           // does any query of this warp touch the rows of this tile?  (warp-uniform)
-          const bool wneed = VOLUME || ((ti.y_first <= whi && ylast >= wlo) && !(p.debug & 32));
+          const bool wneed = VOLUME || ((ti.y_first <= whi && ylast >= wlo) && !TC_DBG(p, 32));
           mbar_wait(&acc_full[acc], acc_phase, p.status, 5);
           if (warp == 2 && lane == 0) stamp(p, 2, tcount, 0);
           float v[64];
@@ -673,7 +697,7 @@ corr_tc_kernel(const Params p) {
             }
             continue;
           }
-          if ((p.debug & 1) || !wneed) continue;
+          if (TC_DBG(p, 1) || !wneed) continue;
 
           // park the accumulator row in this lane's private smem row (the window columns are indexed dynamically):
           // only queries that touch this tile, and at level 0 only the 16-byte groups under their x window
@@ -721,7 +745,7 @@ corr_tc_kernel(const Params p) {
           }
         }
 
-        if (VOLUME || (p.debug & 1)) continue;
+        if (VOLUME || TC_DBG(p, 1)) continue;
         // ---- end of the level inside this job: finish the window and hand it to the stager warp ----
         {
           const bool last = !is0 || (jr.flags() & JF_LAST0);
@@ -767,7 +791,7 @@ corr_tc_kernel(const Params p) {
       const uint32_t abuf = ji & 1;
       mbar_wait(&a_empty[abuf], ((ji >> 1) & 1) ^ 1, p.status, 6);
       tcgen05_fence_after();
-      if (!(p.debug & 256)) {
+      if (!TC_DBG(p, 256)) {
         const bool rv = nq >= 0;
         const float4* src = reinterpret_cast<const float4*>(p.targets + b * p.t_sb + s * p.t_ss +
                                                             (long long)(rv ? nq : 0) * p.t_sn);
@@ -830,7 +854,7 @@ corr_tc_kernel(const Params p) {
         __syncwarp();
       }
       if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 1, 0);
-      const bool do_windows = !(VOLUME || (p.debug & 1));
+      const bool do_windows = !(VOLUME || TC_DBG(p, 1));
       const int nvalid = min(32, p.N - (jr.mt() * TILE_M + 32 * wq));   // sorted slots: valid first, padding last
       // window units of this job: one per tile run (= one pyramid level)
       for (int sg = 0; do_windows && sg < nseg; ++sg, ++wu) {
@@ -848,12 +872,12 @@ corr_tc_kernel(const Params p) {
         float* obase = p.out + lvl_off + lane;
 #pragma unroll 1
         for (int q16 = 0; q16 < 32; q16 += 16) {
-          if (q16 >= nvalid || (p.debug & 2)) break;
+          if (q16 >= nvalid || TC_DBG(p, 2)) break;
           // unconditional loads (clamped addresses) into their own registers: all 48 in flight before the first store
           float val[16][3];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            if (p.tokens && !(p.debug & 16)) {
+            if (p.tokens && !TC_DBG(p, 16)) {
               const float* pq = pbase + rowoff[32 * wq + q16 + u];
               val[u][0] = __ldg(pq);
               val[u][1] = __ldg(pq + d1);
@@ -960,29 +984,46 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// SM count of the CURRENT device if it is an sm_100 part (0 otherwise); cached per device ordinal -- a process may
+// drive several GPUs, possibly of different kinds.
 static int device_is_sm100() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, major = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  static int cached[64];
+  static bool known[64] = {false};
+  int dev = 0, major = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 0; }
+  if (!known[dev]) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cached = (major == 10 && sms > 0 && encode_fn() != nullptr) ? sms : 0;
+    cached[dev] = (major == 10 && sms > 0 && encode_fn() != nullptr) ? sms : 0;
+    known[dev] = true;
   }
-  return cached;
+  return cached[dev];
 }
 
+#ifdef COMET_TC_TRACE
 static long long* g_stamps = nullptr;
+#endif
 
-static int* status_word() {   // one watchdog word per device (a process may drive several GPUs)
-  static int* d[64] = {nullptr};
+// One watchdog word per device.  Allocated by comet_tc_prepare_f32 (once per tracker call, never inside the
+// per-iteration launches, so nothing is allocated under a CUDA-graph capture of the iteration loop).
+static int* g_status[64] = {nullptr};
+static int* status_word() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return nullptr; }
-  if (!d[dev]) {
-    if (cudaMalloc(&d[dev], sizeof(int)) != cudaSuccess) { cudaGetLastError(); d[dev] = nullptr; return nullptr; }
-    cudaMemset(d[dev], 0, sizeof(int));
-  }
-  return d[dev];
+  return g_status[dev];
+}
+static int ensure_status_word(cudaStream_t stream) {
+  int dev = 0;
+  COMET_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || g_status[dev]) return COMET_OK;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+    return COMET_OK;   // prepare itself is being captured: run without the watchdog word (status == nullptr)
+  int* d = nullptr;
+  COMET_CUDA(cudaMalloc(&d, sizeof(int)));
+  COMET_CUDA(cudaMemsetAsync(d, 0, sizeof(int), stream));
+  g_status[dev] = d;
+  return COMET_OK;
 }
 
 // Work decomposition chosen on the host: `nsplit` level-0 row chunks + `npyr` pyramid jobs per (frame, query tile),
@@ -992,11 +1033,13 @@ static void choose_split(int BS, int mtiles, int L, int sms, int& nsplit, int& n
   npyr = L == 1 ? 0 : (L >= 3 && base * 3 < 4LL * sms) ? 2 : 1;
   long long want = (4LL * sms + base - 1) / (base > 0 ? base : 1) - npyr;
   nsplit = (int)(want < 1 ? 1 : want > MAX_SPLIT ? MAX_SPLIT : want);
+#ifdef COMET_TC_TRACE
   static int env_split = -1, env_pyr = -1;
   if (env_split < 0) { const char* e = getenv("COMET_TC_NSPLIT"); env_split = e ? atoi(e) : 0; }
   if (env_pyr < 0) { const char* e = getenv("COMET_TC_NPYR"); env_pyr = e ? atoi(e) : 0; }
   if (env_split >= 1 && env_split <= MAX_SPLIT) nsplit = env_split;
   if (env_pyr >= 1 && env_pyr <= 2 && L > 1) npyr = (env_pyr == 2 && L < 3) ? 1 : env_pyr;
+#endif
 }
 
 static long long workspace_bytes(int BS, int N) {
@@ -1019,12 +1062,14 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   p.njobs = (int)njobs;
   p.inv_sqrt_c = 1.0f / sqrtf((float)KC);
   p.status = status_word();
+#ifdef COMET_TC_TRACE
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("COMET_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
   p.stamps = g_stamps;
+#endif
   // workspace: [jobs: BS*mtiles*MAX_CHUNK records][perm: BS*npad ints]
   JobRec* jobs = reinterpret_cast<JobRec*>(workspace);
   int* perm = reinterpret_cast<int*>(jobs + (long long)p.BS * p.mtiles * MAX_CHUNK);
@@ -1032,7 +1077,7 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   p.perm = perm;
   p.split = reinterpret_cast<const uint8_t*>(split);
 
-  const int full = (p.volume_mode || (p.debug & 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
+  const int full = (p.volume_mode || TC_DBG(p, 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
   // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
   long long misc = 0;
   if (p.tokens) {
@@ -1082,7 +1127,7 @@ static int check_shape(int C, int H, int W, int L, int r, int pad_mode) {
 
 using namespace comet;
 
-extern "C" int comet_has_tensor_path(void) { return tc::device_is_sm100() > 0; }
+extern "C" int comet_has_tensor_path(void) { return option(COMET_OPT_TENSOR_PATH) && tc::device_is_sm100() > 0; }
 
 extern "C" int comet_tc_supported(int C, int H, int W, int L, int r, int pad_mode) {
   return C == tc::KC && H == tc::MAP && W == tc::MAP && L >= 1 && L <= 5 && r >= 0 && r <= 4 &&
@@ -1102,6 +1147,8 @@ extern "C" int comet_tc_prepare_f32(const float* fmaps, void* split, float* pyr,
   if (rc != COMET_OK) return rc;
   if (BS == 0) return COMET_OK;
   COMET_REQUIRE(fmaps && split, "null pointer");
+  rc = tc::ensure_status_word((cudaStream_t)stream);
+  if (rc != COMET_OK) return rc;
   Levels lv = make_levels(BS, C, H, W, 5);
   tc::tc_prepare_kernel<<<BS * tc::KC, 256, 0, (cudaStream_t)stream>>>(
       fmaps, reinterpret_cast<__nv_bfloat16*>(split), pyr, BS, L, lv.off[1], lv.off[2], lv.off[3], lv.off[4]);
@@ -1172,7 +1219,9 @@ extern "C" int comet_tc_corr_volume_f32(const void* split, const float* targets,
   return tc::launch(p, split, workspace, (cudaStream_t)stream);
 }
 
+#ifdef COMET_TC_TRACE
 extern "C" void comet_tc_debug_stamps(long long* dev_buf) { comet::tc::g_stamps = dev_buf; }
+#endif
 
 extern "C" int comet_tc_status(void) {
   int* d = tc::status_word();

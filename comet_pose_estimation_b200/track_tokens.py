@@ -7,12 +7,13 @@ comet/models/track_modules/base_track_predictor.py:153-224, as ONE kernel launch
 layout (B,N,S,D) -- no (B,S,N,LW) intermediate, no permute/cat copies, no host-side sincos table."""
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Optional, Union
 
 import torch
 
 from . import _lib
-from ._dev import inner_contig, pad_mode, prec_mode, require_cuda, stream_ptr
+from ._dev import inner_contig, pad_mode, prec_mode, require_cuda, require_no_grad, stream_ptr
 from .blocks import CorrBlock, EfficientCorrBlock, _Pyramid, _tc_workspace, _use_tc
 
 lib = _lib.lib
@@ -28,18 +29,30 @@ def transformer_dim(corr_levels: int, corr_radius: int, latent_dim: int, fine: b
     return d
 
 
-_TABLES = {}  # (D, H, W, device) -> channel-last sin/cos table (H, W, D); the reference rebuilds and uploads it per iteration
+# (D, H, W, device) -> (channel-last sin/cos table (H, W, D), event recorded after it was built).  The reference
+# rebuilds and uploads the table every iteration; here it is kept, LRU-bounded (a tracker uses two shapes: coarse 10.9 MB,
+# fine 0.8 MB).
+_TABLES = OrderedDict()
+_TABLES_MAX = 8
 
 
 def _sincos_table_cl(embed_dim: int, H: int, W: int, device) -> torch.Tensor:
     key = (embed_dim, H, W, str(device))
-    t = _TABLES.get(key)
-    if t is None:
+    hit = _TABLES.get(key)
+    if hit is None:
         from .utils import get_2d_sincos_pos_embed
 
         t = get_2d_sincos_pos_embed(embed_dim, (H, W), device=device)[0].permute(1, 2, 0).contiguous()
-        _TABLES[key] = t
-    return t
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        _TABLES[key] = hit = (t, ev)
+        while len(_TABLES) > _TABLES_MAX:
+            _TABLES.popitem(last=False)
+    else:
+        _TABLES.move_to_end(key)
+    # the table may have been built on another stream: order this stream after the build (no-op once complete)
+    torch.cuda.current_stream(device).wait_event(hit[1])
+    return hit[0]
 
 
 def sampled_pos_emb(coords0: torch.Tensor, embed_dim: int, H: int, W: int, cached_table: bool = True) -> torch.Tensor:
@@ -49,6 +62,7 @@ def sampled_pos_emb(coords0: torch.Tensor, embed_dim: int, H: int, W: int, cache
     is one contiguous line) and sampled by one kernel.  ``cached_table=False`` evaluates the four taps on the fly
     instead (no table at all; same values)."""
     require_cuda(coords0, "coords0")
+    require_no_grad(coords0)
     B, N, two = coords0.shape
     assert two == 2
     c = inner_contig(coords0)
@@ -94,6 +108,7 @@ class TrackTokenizer:
         assert S == p.S and B == p.B
         require_cuda(coords, "coords")
         require_cuda(track_feats, "track_feats")
+        require_no_grad(coords, track_feats)
         c = inner_contig(coords)
         t = inner_contig(track_feats)
         if out is None:

@@ -7,7 +7,7 @@ from typing import Tuple, Union
 import torch
 
 from . import _lib
-from ._dev import f32c, inner_contig, pad_mode, require_cuda, stream_ptr
+from ._dev import f32c, inner_contig, pad_mode, require_cuda, require_no_grad, stream_ptr
 
 lib = _lib.lib
 
@@ -27,6 +27,7 @@ def bilinear_sampler(input, coords, align_corners=True, padding_mode="border"):
     assert len(sizes) in [2, 3]
     require_cuda(input, "input")
     require_cuda(coords, "coords")
+    require_no_grad(input, coords)
     x = f32c(input)
     c = f32c(coords)
     pm = pad_mode(padding_mode)
@@ -54,6 +55,7 @@ def sample_features4d(input, coords):
     ``input`` may be a batch-strided view (e.g. ``fmaps[:, 0]``) or batch-expanded (stride 0)."""
     require_cuda(input, "input")
     require_cuda(coords, "coords")
+    require_no_grad(input, coords)
     B, C, H, W = input.shape
     x = input if input.dtype == torch.float32 else input.float()
     c = inner_contig(coords)
@@ -80,6 +82,7 @@ def get_2d_embedding(xy: torch.Tensor, C: int, cat_coords: bool = True) -> torch
     B, N, D = xy.shape
     assert D == 2
     require_cuda(xy, "xy")
+    require_no_grad(xy)
     x = f32c(xy)
     out = torch.empty((B, N, 2 * C + (2 if cat_coords else 0)), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
@@ -146,6 +149,7 @@ def upsample_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
     (ShallowEncoder.forward, blocks.py:176-190) spends 90 % of ``refine_track`` in ATen's kernel for this op at 8192
     patches; this one is HBM-bound."""
     require_cuda(x, "x")
+    require_no_grad(x)
     assert x.dim() == 4
     N, C, Hi, Wi = x.shape
     Ho, Wo = (size, size) if isinstance(size, int) else tuple(size)
@@ -167,6 +171,7 @@ def instance_norm(x: torch.Tensor, relu: bool = False, eps: float = 1e-5) -> tor
     """``nn.InstanceNorm2d(C)(x)`` (affine=False, no running stats; optionally followed by ReLU) for a 4-D float32 CUDA
     tensor, contiguous or channels-last (memory format preserved)."""
     require_cuda(x, "x")
+    require_no_grad(x)
     assert x.dim() == 4
     N, C, H, W = x.shape
     x = x if x.dtype == torch.float32 else x.float()

@@ -57,8 +57,17 @@ typedef void* comet_stream_t;
 /* ---- library ---------------------------------------------------------- */
 int comet_version(void);
 const char* comet_last_error(void);
-/* 1 if the tcgen05/TMEM/TMA correlation kernels were compiled in and the current device is sm_100. */
+/* 1 if the tcgen05/TMEM/TMA correlation kernels were compiled in, the current device is sm_100 and
+ * COMET_OPT_TENSOR_PATH is on. */
 int comet_has_tensor_path(void);
+/* Library-wide switches for A/B measurements (all on by default; no environment variable is read on the launch path):
+ *   COMET_OPT_TENSOR_PATH  the tcgen05 kernels serve the dense coarse shape; off = general SIMT kernels
+ *   COMET_OPT_TMA_LOOKUP   the TMA-staged C=32 lookup serves channel-last small maps; off = register version */
+#define COMET_OPT_TENSOR_PATH 0
+#define COMET_OPT_TMA_LOOKUP 1
+#define COMET_OPT_COUNT 2
+int comet_set_option(int option, int value);
+int comet_get_option(int option);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */
 long long comet_launch_count(void);
 
@@ -188,10 +197,9 @@ int comet_tc_track_tokens_f32(const void* split, const float* track_feats, long 
 int comet_tc_corr_volume_f32(const void* split, const float* targets, long long t_sb, long long t_ss, long long t_sn,
                              float* const* vols, int B, int S, int N, int C, int H, int W, int L, int prec_mode,
                              void* workspace, comet_stream_t stream);
-/* 0 = healthy; non-zero = a pipeline watchdog fired inside the tensor kernel (debug aid). Synchronises. */
+/* 0 = healthy; non-zero = the pipeline watchdog of the tensor kernel fired (a wait exceeded 10 s of wall time; the
+ * kernel trapped and the CUDA context is lost): which wait it was.  Synchronises with the device. */
 int comet_tc_status(void);
-/* debug aid: device buffer of 4*64*2 int64 receiving a clock64 trace of CTA 0 (NULL = off). */
-void comet_tc_debug_stamps(long long* dev_buf);
 
 #ifdef __cplusplus
 }

@@ -2,7 +2,9 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import comet_pose_estimation_b200 as cb
-lib = cb._lib.lib
+lib = cb._lib.lib   # needs a trace build: python -m comet_pose_estimation_b200.build --trace
+import ctypes
+lib.comet_tc_debug_stamps.argtypes = [ctypes.c_void_p]
 dev = torch.device("cuda:0")
 tdim = cb.transformer_dim(5, 4, 128, False)
 fm = torch.randn(1, 16, 128, 64, 64, device=dev); ft = torch.randn(1, 16, 512, 128, device=dev)

@@ -86,3 +86,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_options_are_an_explicit_abi_not_environment_variables(built):
+    """A/B switches go through comet_set_option; the launch path reads no environment variable, and the production
+    header exports no debug entry point (trace hooks exist only in -DCOMET_TC_TRACE builds)."""
+    from comet_pose_estimation_b200 import _lib
+
+    assert _lib.lib.comet_get_option(_lib.OPT_TENSOR_PATH) == 1 and _lib.lib.comet_get_option(_lib.OPT_TMA_LOOKUP) == 1
+    assert _lib.set_option(_lib.OPT_TMA_LOOKUP, False) is True
+    assert _lib.lib.comet_get_option(_lib.OPT_TMA_LOOKUP) == 0
+    _lib.set_option(_lib.OPT_TMA_LOOKUP, True)
+    assert _lib.lib.comet_set_option(99, 1) == _lib.ERR_INVALID
+    assert "comet_tc_debug_stamps" not in _declared()
+    assert not hasattr(ctypes.CDLL(built), "comet_tc_debug_stamps")
+    pkg = os.path.join(ROOT, "comet_pose_estimation_b200")
+    for f in os.listdir(os.path.join(pkg, "csrc")):
+        txt = open(os.path.join(pkg, "csrc", f)).read()
+        txt = re.sub(r"#ifdef COMET_TC_TRACE.*?#endif", "", txt, flags=re.S)
+        assert "getenv" not in txt, f"{f} reads the environment outside a trace build"
+    for f in os.listdir(pkg):
+        if f.endswith(".py") and f not in ("build.py", "launch.py"):   # launch.py reads torchrun's RANK / WORLD_SIZE
+            assert "os.environ" not in open(os.path.join(pkg, f)).read(), f

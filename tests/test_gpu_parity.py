@@ -551,9 +551,9 @@ def test_tensor_path_degenerate_query_sets(cb):
         assert rel_to_max(host(corr_part[ok]), host(got.permute(0, 2, 1, 3)[ok])) < 1e-5, name
 
 
-def test_tensor_path_matches_simt_and_oracle(cb, monkeypatch):
+def test_tensor_path_matches_simt_and_oracle(cb):
     """Coarse COMET shape (C=128, 64x64, L=5, r=4, zero padding) runs on the tcgen05 kernel; the same call with
-    COMET_B200_DISABLE_TC=1 runs the SIMT kernel.  Both must sit inside the fp32 bar against the oracle, for
+    the tensor path switched off (comet_set_option) runs the SIMT kernel.  Both must sit inside the fp32 bar against the oracle, for
     N that is not a multiple of the 128-query tile, for strided targets, and for smaller L / r."""
     if not cb._lib.lib.comet_has_tensor_path():
         pytest.skip("no sm_100 tensor path on this device")
@@ -564,7 +564,7 @@ def test_tensor_path_matches_simt_and_oracle(cb, monkeypatch):
         coords = torch.rand(2, S, N, 2, device="cuda", generator=g) * 80 - 8
         coords[0, 0, 0] = torch.tensor([63.0, 0.0], device="cuda")
         coords[1, 0, 0] = torch.tensor([-30.0, 31.25], device="cuda")
-        monkeypatch.setenv("COMET_B200_DISABLE_TC", "0")
+        cb._lib.set_option(cb._lib.OPT_TENSOR_PATH, True)
         blk = cb.CorrBlock(fmaps, num_levels=L, radius=r)
         assert blk._pyr.split is not None
         blk.corr(feats)
@@ -575,7 +575,7 @@ def test_tensor_path_matches_simt_and_oracle(cb, monkeypatch):
         else:
             x_tc = None
         vols_tc = [v.clone() for v in blk.corrs_pyramid]
-        monkeypatch.setenv("COMET_B200_DISABLE_TC", "1")
+        cb._lib.set_option(cb._lib.OPT_TENSOR_PATH, False)
         blk2 = cb.CorrBlock(fmaps, num_levels=L, radius=r)
         assert blk2._pyr.split is None
         blk2.corr(feats)
@@ -589,8 +589,9 @@ def test_tensor_path_matches_simt_and_oracle(cb, monkeypatch):
         sel = slice(0, N, max(1, N // 9))
         want = O.corr_lookup(host(fmaps), host(feats[:, :, sel]), host(coords[:, :, sel]), L, r)
         assert rel_to_max(host(tc[:, :, sel]), want) < FP32_BAR
+        cb._lib.set_option(cb._lib.OPT_TENSOR_PATH, True)
         assert cb._lib.lib.comet_tc_status() == 0
-    monkeypatch.setenv("COMET_B200_DISABLE_TC", "0")
+    cb._lib.set_option(cb._lib.OPT_TENSOR_PATH, True)
 
 
 def test_tensor_path_bf16_autocast(cb):
@@ -607,3 +608,44 @@ def test_tensor_path_bf16_autocast(cb):
     want = O.corr_lookup_bf16_autocast(host(fmaps), host(feats), host(coords), 5, 4)
     assert rel_to_max(host(out), want) < 8e-3          # same rounding points (reciprocal multiply vs divide)
     assert rel_to_max(host(out), O.corr_lookup(host(fmaps), host(feats), host(coords), 5, 4)) < BF16_BAR
+
+
+def test_forward_only_contract_and_corr_aliasing(cb):
+    """(i) an input that requires grad under enabled autograd is refused (the kernels build no autograd
+    graph; the reference runs the tracker under no_grad); (ii) corr() keeps a reference to `targets`, so an in-place
+    update before sample() -- which the reference, computing the volume inside corr(), would not see -- is detected."""
+    fmaps = torch.randn(1, 2, 16, 12, 12, device="cuda")
+    targets = torch.randn(1, 2, 5, 16, device="cuda")
+    coords = torch.rand(1, 2, 5, 2, device="cuda") * 11
+    blk = cb.CorrBlock(fmaps, num_levels=2, radius=2)
+    blk.corr(targets)
+    want = blk.sample(coords).clone()
+    with torch.enable_grad():
+        with pytest.raises(RuntimeError, match="forward-only"):
+            cb.CorrBlock(fmaps.clone().requires_grad_(True), num_levels=2, radius=2)
+        blk.corr(targets.clone().requires_grad_(True))
+        with pytest.raises(RuntimeError, match="forward-only"):
+            blk.sample(coords)
+        with pytest.raises(RuntimeError, match="forward-only"):
+            cb.sample_features4d(fmaps[:, 0].clone().requires_grad_(True), coords[:, 0])
+    with torch.no_grad():   # the same tensors under no_grad are accepted
+        blk.corr(targets.clone().requires_grad_(True))
+        assert torch.equal(blk.sample(coords), want)
+    blk.corr(targets)
+    targets.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified in place"):
+        blk.sample(coords)
+    blk.corr(targets)
+    assert rel_to_max(host(blk.sample(coords)), host(want) * 2.0) < 1e-5
+
+
+def test_extract_patches_clamps_corners_on_non_square_images(cb):
+    """corners are clamped per axis (x with W, y with H); the reference assumes H == W."""
+    imgs = torch.rand(1, 2, 3, 40, 33, device="cuda")            # H=40, W=33
+    tl = torch.tensor([[[[-5, 38], [10, 3]], [[30, 0], [2, 9]]]], device="cuda", dtype=torch.int32)   # (1,2,2,2) = (x, y)
+    p = cb.extract_patches(imgs, tl, 31)
+    assert p.shape == (4, 3, 31, 31)
+    for n in range(2):
+        for s in range(2):
+            x0 = int(tl[0, s, n, 0].clamp(0, 33 - 31)); y0 = int(tl[0, s, n, 1].clamp(0, 40 - 31))
+            assert torch.equal(p[n * 2 + s], imgs[0, s, :, y0:y0 + 31, x0:x0 + 31])

@@ -135,8 +135,6 @@ def test_dropin_predictor_matches_reference(golden, name):
 @pytest.mark.gpu
 def test_dropin_predictor_coarse_shape_uses_tensor_path():
     """Full coarse configuration (C=128, 64x64, L=5, r=4): tcgen05 path and SIMT path give the same tracks."""
-    import os
-
     import comet_pose_estimation_b200 as cb
 
     torch.manual_seed(0)
@@ -145,11 +143,11 @@ def test_dropin_predictor_coarse_shape_uses_tensor_path():
     q = torch.rand(1, 96, 2, device="cuda") * 480 + 16
     with torch.no_grad():
         a = m(query_points=q, fmaps=fmaps, iters=3, down_ratio=2, TRACKorPOSE=False)[0]
-        os.environ["COMET_B200_DISABLE_TC"] = "1"
+        cb._lib.set_option(cb._lib.OPT_TENSOR_PATH, False)
         try:
             b = m(query_points=q, fmaps=fmaps, iters=3, down_ratio=2, TRACKorPOSE=False)[0]
         finally:
-            os.environ["COMET_B200_DISABLE_TC"] = "0"
+            cb._lib.set_option(cb._lib.OPT_TENSOR_PATH, True)
     # two float32 implementations of the same loop: iteration 0 within the spec, later ones bounded by the drift the
     # reference shows between its own float32 and float64 runs at this size (tracker_full.npz: 2.5e-5, 5.7e-3)
     for i, (x, y) in enumerate(zip(a, b)):
