@@ -18,7 +18,7 @@ All arithmetic runs in hand-written CUDA kernels behind the C ABI of ``include/c
 There is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the kernels are not built)
-from .blocks import CorrBlock, EfficientCorrBlock  # noqa: F401
+from .blocks import CorrBlock, EfficientCorrBlock, Upsampled2x  # noqa: F401
 from .utils import (  # noqa: F401
     bilinear_sampler,
     sample_features4d,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libcomet_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 PAD_ZEROS, PAD_BORDER = 0, 1
 PREC_F32, PREC_BF16_AUTOCAST = 0, 1
-PYR_NCHW, PYR_CHANNEL_LAST, PYR_ALL_CHANNEL_LAST = 0, 1, 2
+PYR_NCHW, PYR_CHANNEL_LAST, PYR_ALL_CHANNEL_LAST, PYR_UP2_SOURCE = 0, 1, 2, 3
 FMAPS_NCHW, FMAPS_CHANNEL_LAST = 0, 1
 MAX_LEVELS, MAX_RADIUS = 8, 7
 OPT_TENSOR_PATH, OPT_TMA_LOOKUP = 0, 1
@@ -34,6 +34,9 @@ SIGNATURES = {
     "comet_pyramid_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "comet_corr_volume_f32": (_i, [_p, _ll, _ll, _p, _p, _i, _i, _i, _i, _i, _p]),
     "comet_pyramid_cl_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_pyramid_up2_elems": (_ll, [_i, _i, _i, _i]),
+    "comet_pyramid_up2_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "comet_up2_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "comet_corr_lookup_f32": (_i, [_p, _p, _p, _ll, _ll, _ll, _i, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
                                    _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "comet_track_tokens_f32": (_i, [_p, _p, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _p,

@@ -15,7 +15,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .blocks import CorrBlock, EfficientCorrBlock
+from .blocks import CorrBlock, EfficientCorrBlock, Upsampled2x
 from .track_tokens import TrackTokenizer, transformer_dim
 from .update_former import EfficientUpdateFormer
 from .utils import sample_features4d
@@ -62,7 +62,11 @@ class BaseTrackerPredictor(nn.Module):
         else:
             coords = query_points.clone().reshape(B, 1, N, 2).repeat(1, S, 1, 1)
 
-        query_track_feat = sample_features4d(fmaps[:, 0], coords[:, 0])
+        if isinstance(fmaps, Upsampled2x):
+            # bilinear sample (border) of the 2x-1 up-sampling at p == bilinear sample of its source at p / 2
+            query_track_feat = sample_features4d(fmaps.src[:, 0], coords[:, 0] * 0.5)
+        else:
+            query_track_feat = sample_features4d(fmaps[:, 0], coords[:, 0])
         track_feats = query_track_feat.unsqueeze(1).repeat(1, S, 1, 1)
         coords_backup = coords.clone()
 

@@ -81,6 +81,89 @@ class _Pyramid:
                 self.levels.append(flat.view(B, S, C, h, w))
 
 
+class Upsampled2x:
+    """A (B, S, C, 2Hs-1, 2Ws-1) feature tensor that is *defined* as
+    ``F.interpolate(src, (2Hs-1, 2Ws-1), mode="bilinear", align_corners=True)`` of a half-resolution map ``src``
+    (B, S, C, Hs, Ws) but never materialised: what ``ShallowEncoder`` computes right before its last resize
+    (blocks.py:176-190).  ``CorrBlock`` / ``BaseTrackerPredictor`` of this package accept it in place of ``fmaps`` and
+    evaluate pyramid levels 0 and 1 from ``src`` inside the fused lookup (COMET_PYR_UP2_SOURCE, csrc/corr_lookup_up2.cu):
+    the 1 GB-per-sequence up-sampled tensor of the fine tracker is neither written nor read.  ``materialize()`` gives
+    the ordinary tensor (any subset of maps) for callers that need values, e.g. ``compute_score_fn``."""
+
+    def __init__(self, src: torch.Tensor):
+        require_cuda(src, "src")
+        require_no_grad(src)
+        assert src.dim() == 5, "src must be (B, S, C, Hs, Ws)"
+        B, S, C, Hs, Ws = src.shape
+        src = src if src.dtype == torch.float32 else src.float()
+        if not (src.permute(0, 1, 3, 4, 2).is_contiguous() and src.data_ptr() % 16 == 0):
+            src = src.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)   # channels-last memory, same shape
+        self.src = src
+        self.shape = torch.Size((B, S, C, 2 * Hs - 1, 2 * Ws - 1))
+        self.device, self.dtype = src.device, torch.float32
+
+    def dim(self) -> int:
+        return 5
+
+    def materialize(self, index=None) -> torch.Tensor:
+        """The up-sampled tensor itself, (B,S,C,H,W), or maps ``index`` of its (B*S) flattening -> (len, C, H, W)."""
+        from .utils import upsample_bilinear_align_corners
+
+        B, S, C, H, W = self.shape
+        flat = self.src.permute(0, 1, 3, 4, 2).reshape(B * S, self.src.shape[3], self.src.shape[4], C).permute(0, 3, 1, 2)
+        if index is not None:
+            return upsample_bilinear_align_corners(flat[index].contiguous(memory_format=torch.channels_last), (H, W))
+        return upsample_bilinear_align_corners(flat, (H, W)).permute(0, 2, 3, 1).reshape(B, S, H, W, C).permute(0, 1, 4, 2, 3)
+
+
+class _PyramidUp2:
+    """Pyramid state of the COMET_PYR_UP2_SOURCE layout: the source map (level 0 and 1 are stencils of it) and the
+    pooled level 2; duck-types ``_Pyramid`` for the fused lookup / token entry points."""
+
+    def __init__(self, up: Upsampled2x, num_levels: int):
+        B, S, C, H, W = up.shape
+        self.B, self.S, self.C, self.H, self.W = B, S, C, H, W
+        self.num_levels = num_levels
+        self.up = up
+        self.fmaps0 = up.src                      # passed as `fmaps`: the half-resolution source
+        self.cl_input = True
+        self.split = None
+        self.layout = _lib.PYR_UP2_SOURCE
+        self._ws = {}
+        Hs, Ws = up.src.shape[-2:]
+        n = lib.comet_pyramid_up2_elems(B * S, C, Hs, Ws)
+        assert n >= 0
+        self.pyr = torch.empty(max(n, 1), dtype=torch.float32, device=up.device)   # level 2 only, channel-last
+        with torch.cuda.device(up.device):
+            if B * S:
+                _lib.check(lib.comet_pyramid_up2_f32(up.src.data_ptr(), self.pyr.data_ptr(), B * S, C, Hs, Ws,
+                                                     stream_ptr(up.device)))
+        self._levels = None
+
+    @property
+    def levels(self) -> List[torch.Tensor]:
+        """``fmaps_pyramid`` as the reference stores it (values only needed by callers that read the attribute)."""
+        if self._levels is None:
+            self._levels = _Pyramid(self.up.materialize(), self.num_levels).levels
+        return self._levels
+
+
+def up2_supported(fmaps, num_levels: int, radius: int, padding_mode: str) -> bool:
+    if not isinstance(fmaps, Upsampled2x):
+        return False
+    B, S, C, H, W = fmaps.shape
+    with torch.cuda.device(fmaps.device):
+        return bool(lib.comet_up2_supported(C, H, W, num_levels, radius, pad_mode(padding_mode)))
+
+
+def _make_pyramid(fmaps, num_levels: int, radius: int, padding_mode: str):
+    if isinstance(fmaps, Upsampled2x):
+        if up2_supported(fmaps, num_levels, radius, padding_mode):
+            return _PyramidUp2(fmaps, num_levels)
+        fmaps = fmaps.materialize()    # shape the specialised kernel does not serve: the ordinary path
+    return _Pyramid(fmaps, num_levels)
+
+
 def _tc_workspace(pyr: "_Pyramid", N: int) -> torch.Tensor:
     """Scratch of the tensor path, one buffer per CUDA stream (two streams driving the same CorrBlock never share a
     plan).  It grows only when a larger N arrives: under CUDA-graph capture call once with the largest N first."""
@@ -140,10 +223,22 @@ class CorrBlock:
         self.multiple_track_feats = multiple_track_feats
         pad_mode(padding_mode)  # validate early
         assert 0 <= radius <= _lib.MAX_RADIUS, f"radius must be in [0, {_lib.MAX_RADIUS}]"
-        self._pyr = _Pyramid(fmaps, num_levels)
-        self.fmaps_pyramid = self._pyr.levels
+        if multiple_track_feats and isinstance(fmaps, Upsampled2x):
+            fmaps = fmaps.materialize()     # per-level targets are served by the general kernel only
+        self._pyr = _make_pyramid(fmaps, num_levels, radius, padding_mode)
         self._targets: Optional[torch.Tensor] = None
         self._volumes: Optional[List[torch.Tensor]] = None
+
+    @classmethod
+    def from_upsampled(cls, src, num_levels=4, radius=4, multiple_track_feats=False, padding_mode="zeros"):
+        """``CorrBlock(F.interpolate(src, (2Hs-1, 2Ws-1), bilinear, align_corners=True), ...)`` without the up-sampled
+        tensor: ``src`` (B,S,C,Hs,Ws) is the patch encoder's half-resolution output (see :class:`Upsampled2x`)."""
+        return cls(src if isinstance(src, Upsampled2x) else Upsampled2x(src), num_levels, radius, multiple_track_feats,
+                   padding_mode)
+
+    @property
+    def fmaps_pyramid(self):
+        return self._pyr.levels
 
     def corr(self, targets):
         B, S, N, C = targets.shape
@@ -172,13 +267,15 @@ class CorrBlock:
         if self._volumes is None:
             self._check_targets_unchanged()
             p = self._pyr
+            if isinstance(p, _PyramidUp2):   # API completeness only: volumes of the materialised pyramid
+                p = _Pyramid(p.up.materialize(), p.num_levels)
             B, S, N, _ = self._targets.shape
             t = f32c(self._targets).view(B * S, N, -1)
             vols = []
             mode = prec_mode()
             with torch.cuda.device(t.device):
                 if B * S * N and not self.multiple_track_feats and _use_tc(p, t.view(B, S, N, -1), 0, "zeros"):
-                    for f in self.fmaps_pyramid:
+                    for f in p.levels:
                         vols.append(torch.empty((B, S, N) + tuple(f.shape[-2:]), dtype=torch.float32,
                                                 device=t.device))
                     ptrs = (ctypes.c_void_p * len(vols))(*[v.data_ptr() for v in vols])
@@ -191,7 +288,7 @@ class CorrBlock:
                         vols = [v.to(torch.bfloat16) for v in vols]
                     self._volumes = vols
                     return self._volumes
-                for l, f in enumerate(self.fmaps_pyramid):
+                for l, f in enumerate(p.levels):
                     h, w = f.shape[-2:]
                     tl = t[..., l * self.C:(l + 1) * self.C] if self.multiple_track_feats else t
                     fl = p.fmaps0 if (l == 0 and not p.cl_input) else f.contiguous()
@@ -224,7 +321,7 @@ class EfficientCorrBlock:
         self.num_levels = num_levels
         self.radius = radius
         assert 0 <= radius <= _lib.MAX_RADIUS, f"radius must be in [0, {_lib.MAX_RADIUS}]"
-        self._pyr = _Pyramid(fmaps, num_levels)
+        self._pyr = _make_pyramid(fmaps, num_levels, radius, "border")
         self.fmaps_pyramid = self._pyr.levels
 
     def sample(self, coords, target):

@@ -13,34 +13,13 @@
 // The volume is never written to global memory.  This is the general path (any C, H, W, L, r<=7, both
 // padding modes, strided views) and the HBM-bound path of the fine tracker (one query per map, GEMV-shaped);
 // the dense coarse shapes go through the tcgen05 kernel in corr_tc.cu when available.
-#include "comet_common.cuh"
+#include "lookup_common.cuh"
 
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
 
 namespace comet {
-
-struct LookupParams {
-  const float* fmaps;
-  const float* pyr;
-  const float* targets;
-  long long t_sb, t_ss, t_sn;
-  int t_level_stride;
-  const float* coords;
-  long long c_sb, c_ss, c_sn;
-  float* out;
-  long long o_sb, o_ss, o_sn;
-  const float* pos;  // TOKENS: (B,N,D_tok)
-  int D_tok;
-  int B, S, N, C, L, r;
-  int pad_border, bf16;
-  int lvlH[COMET_MAX_LEVELS], lvlW[COMET_MAX_LEVELS];
-  long long lvlOff[COMET_MAX_LEVELS];
-  int channel_last;  // levels >= 1 stored (BS, H_l, W_l, C) instead of (BS, C, H_l, W_l)
-  int cl0;           // level 0 (the caller's fmaps) is channel-last too
-  float sqrt_c;
-};
 
 // element strides of level l: channel, row, column
 __device__ __forceinline__ void level_strides(const LookupParams& p, int l, long long& sc, int& sy, int& sx) {
@@ -352,37 +331,6 @@ __global__ void __launch_bounds__(256, 2) corr_lookup_c32_kernel(const LookupPar
 // Then lanes <-> grid positions read "their" 128-byte line (swizzle makes the 8 lanes of a quarter-warp hit 8 different
 // bank groups), dot it with the target vector held in registers, and the blend / token epilogue is the one above.
 // Persistent: 8 warps per SM, each owns 3 box buffers (24 KB at r = 3) and loops over queries.
-namespace tma {
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();  // a protocol bug must fail fast, not hang the device
-  }
-}
-__device__ __forceinline__ void load_box_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-}  // namespace tma
-
-struct TmaMaps { CUtensorMap m[3]; };
 
 template <int R, bool TOKENS, bool BF16, bool CL0>
 __global__ void __launch_bounds__(256, 1) corr_lookup_c32_tma_kernel(const __grid_constant__ TmaMaps maps, const LookupParams p) {
@@ -627,22 +575,6 @@ static int launch_c32_tma(const LookupParams& p, const TmaMaps& maps, int grid, 
   return launch_status("corr_lookup_c32_tma_kernel");
 }
 
-// 4-D tensor map over one channel-last level: dims (fastest first) {32 channels, W_l, H_l, BS}, box {32, G, G, 1},
-// 128-byte swizzle, zero fill outside the map.
-static int encode_level_map(CUtensorMap* tm, const float* base, int BS, int Hl, int Wl, int G) {
-  TensorMapEncodeFn enc = tensor_map_encoder();
-  if (!enc) return fail(COMET_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
-  const cuuint64_t gdim[4] = {32, (cuuint64_t)Wl, (cuuint64_t)Hl, (cuuint64_t)BS};
-  const cuuint64_t gstride[3] = {128, (cuuint64_t)Wl * 128, (cuuint64_t)Hl * Wl * 128};
-  const cuuint32_t box[4] = {32, (cuuint32_t)G, (cuuint32_t)G, 1};
-  const cuuint32_t estride[4] = {1, 1, 1, 1};
-  CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstride, box, estride,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)cr);
-  return COMET_OK;
-}
-
 template <int R, bool TOKENS>
 static void launch_c32(const LookupParams& p, unsigned blocks, cudaStream_t stream) {
   if (p.bf16) corr_lookup_c32_kernel<R, TOKENS, true><<<blocks, 256, 0, stream>>>(p);
@@ -710,7 +642,8 @@ static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, co
   COMET_REQUIRE(pad_mode == COMET_PAD_ZEROS || pad_mode == COMET_PAD_BORDER, "bad pad_mode %d", pad_mode);
   COMET_REQUIRE(prec_mode == COMET_PREC_F32 || prec_mode == COMET_PREC_BF16_AUTOCAST, "bad prec_mode %d", prec_mode);
   COMET_REQUIRE(pyr_layout == COMET_PYR_NCHW || pyr_layout == COMET_PYR_CHANNEL_LAST ||
-                    pyr_layout == COMET_PYR_ALL_CHANNEL_LAST, "bad pyr_layout %d", pyr_layout);
+                    pyr_layout == COMET_PYR_ALL_CHANNEL_LAST || pyr_layout == COMET_PYR_UP2_SOURCE,
+                "bad pyr_layout %d", pyr_layout);
   COMET_REQUIRE((H >> (L - 1)) >= 1 && (W >> (L - 1)) >= 1, "map %dx%d too small for %d levels", H, W, L);
   const long long total = (long long)B * S * N;
   COMET_REQUIRE(total == 0 || (fmaps && targets && coords), "null input pointer");
@@ -730,6 +663,11 @@ static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, co
   return COMET_OK;
 }
 
+// corr_lookup_up2.cu: the fine tracker reading the encoder's half-resolution map (COMET_PYR_UP2_SOURCE)
+int up2_supported(int C, int H, int W, int L, int r, int pad_mode);
+template <bool TOKENS>
+int launch_lookup_up2(LookupParams& p, const float* src, const float* p2, cudaStream_t stream);
+
 }  // namespace comet
 
 using namespace comet;
@@ -746,6 +684,12 @@ extern "C" int comet_corr_lookup_f32(const float* fmaps, const float* pyr, const
   COMET_REQUIRE(t_level_stride == 0 || t_level_stride == C, "t_level_stride must be 0 or C");
   COMET_REQUIRE((long long)B * S * N == 0 || out, "null output pointer");
   p.out = out; p.o_sb = o_sb; p.o_ss = o_ss; p.o_sn = o_sn;
+  if (pyr_layout == COMET_PYR_UP2_SOURCE) {
+    rc = up2_supported(C, H, W, L, r, pad_mode);
+    if (rc != COMET_OK) return rc;
+    COMET_REQUIRE(t_level_stride == 0, "multiple_track_feats is not served by COMET_PYR_UP2_SOURCE");
+    return launch_lookup_up2<false>(p, fmaps, pyr, (cudaStream_t)stream);
+  }
   return launch_lookup<false>(p, (cudaStream_t)stream);
 }
 
@@ -763,5 +707,10 @@ extern "C" int comet_track_tokens_f32(const float* fmaps, const float* pyr, cons
   COMET_REQUIRE(D_tok >= need, "D_tok=%d smaller than the %d token channels", D_tok, need);
   COMET_REQUIRE((long long)B * S * N == 0 || (tokens && pos_emb), "null tokens / pos_emb pointer");
   p.out = tokens; p.pos = pos_emb; p.D_tok = D_tok;
+  if (pyr_layout == COMET_PYR_UP2_SOURCE) {
+    rc = up2_supported(C, H, W, L, r, pad_mode);
+    if (rc != COMET_OK) return rc;
+    return launch_lookup_up2<true>(p, fmaps, pyr, (cudaStream_t)stream);
+  }
   return launch_lookup<true>(p, (cudaStream_t)stream);
 }

@@ -207,9 +207,16 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // a protocol bug must fail visibly, not hang the device: trap after 10 s of WALL time (not a poll count)
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();  // a protocol bug must fail fast, not hang the device
+    if ((++spins & 4095u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -27,9 +27,13 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .blocks import Upsampled2x, up2_supported
+
 
 # False routes the encoder's resizes / instance norms through the ATen ops even on the GPU (A/B timing in bench.py)
 USE_LIBRARY_KERNELS = True
+# False makes refine_track materialise the up-sampled patch features (the reference's data flow; A/B timing and tests)
+DEFER_UPSAMPLE = True
 
 
 def _resize(x: torch.Tensor, size) -> torch.Tensor:
@@ -99,7 +103,9 @@ class ShallowEncoder(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
-    def forward(self, x):
+    def forward(self, x, defer_upsample: bool = False):
+        """``defer_upsample=True`` returns the map *before* the last resize together with the size that resize would
+        produce -- ``(x_half, (Ho, Wo))`` -- for callers that consume the up-sampling lazily (:class:`Upsampled2x`)."""
         _, _, H, W = x.shape
         x = _inorm(self.norm1, self.conv1(x), True)
         tmp = self.layer1(x)
@@ -107,7 +113,10 @@ class ShallowEncoder(nn.Module):
         tmp = self.layer2(tmp)
         x = x + _resize(tmp, x.shape[-2:])
         x = self.conv2(x) + x
-        return _resize(x, (H // self.stride, W // self.stride))
+        size = (H // self.stride, W // self.stride)
+        if defer_upsample:
+            return x, size
+        return _resize(x, size)
 
 
 def extract_patches(images: torch.Tensor, topleft: torch.Tensor, psize: int) -> torch.Tensor:
@@ -160,9 +169,33 @@ def refine_track(images, fine_fnet, fine_tracker, coarse_pred, pradius=15, sradi
 
     with torch.no_grad():
         patch_input = extract_patches(images, topleft, psize)
-    patch_feat = fine_fnet(patch_input)                            # (B*N*S, C_out, p, p), channels-last memory
-    C_out = patch_feat.shape[1]
-    patch_feat = patch_feat.reshape(B * N, S, C_out, psize, psize)  # a view: (b n) s c p q, no rearrange copy
+    patch_feat = None
+    from .base_track_predictor import BaseTrackerPredictor
+
+    if (USE_LIBRARY_KERNELS and DEFER_UPSAMPLE and isinstance(fine_fnet, ShallowEncoder) and patch_input.is_cuda
+            and isinstance(fine_tracker, BaseTrackerPredictor) and not torch.is_grad_enabled()):
+        # The encoder's last op is an exact 2x-1 bilinear up-sampling (16x16 -> 31x31): hand the fine tracker the
+        # half-resolution map and let the fused lookup evaluate the up-sampled pyramid from it (blocks.Upsampled2x) --
+        # the 1 GB-per-sequence patch-feature tensor is never written.
+        half, size = fine_fnet(patch_input, defer_upsample=True)
+        Hs, Ws = half.shape[-2:]
+        if size == (2 * Hs - 1, 2 * Ws - 1) and size == (psize, psize):
+            C_out = half.shape[1]
+            half = half.contiguous(memory_format=torch.channels_last)
+            # (B*N*S, C, Hs, Ws) channels-last memory == (B*N, S, Hs, Ws, C): the (b n) s c p q view, no copy
+            src = half.permute(0, 2, 3, 1).reshape(B * N, S, Hs, Ws, C_out).permute(0, 1, 4, 2, 3)
+            up = Upsampled2x(src)
+            if up2_supported(up, fine_tracker.corr_levels, fine_tracker.corr_radius, "zeros") and not fine_tracker.efficient_corr:
+                patch_feat = up
+            else:
+                patch_feat = _resize(half, size)
+        else:
+            patch_feat = _resize(half, size)
+    if patch_feat is None:
+        patch_feat = fine_fnet(patch_input)                        # (B*N*S, C_out, p, p), channels-last memory
+    if not isinstance(patch_feat, Upsampled2x):
+        C_out = patch_feat.shape[1]
+        patch_feat = patch_feat.reshape(B * N, S, C_out, psize, psize)  # a view: (b n) s c p q, no rearrange copy
 
     patch_query_points = (track_frac[:, 0] + pradius).reshape(B * N, 2).unsqueeze(1)
     fine_pred_track_lists, _, _, query_point_feat, _ = fine_tracker(
@@ -208,7 +241,13 @@ def compute_score_fn(query_point_feat, patch_feat, fine_pred_track, sradius, psi
     ar = torch.arange(ssize, device=patch_feat.device)
     rows = (cy[:, None] + ar)[:, :, None]         # (M, ss, 1)
     cols = (cx[:, None] + ar)[:, None, :]         # (M, 1, ss)
-    win = patch_feat[(mb * N + mn)[:, None, None], ms[:, None, None], :, rows, cols]   # (M, ss, ss, C)
+    if isinstance(patch_feat, Upsampled2x):
+        # only maps number 0..B-1 of the list are ever indexed (the quirk above): up-sample just those
+        idx = [((v // (S * N)) * N + v % N) * S + (v // N) % S for v in range(B)]
+        small = patch_feat.materialize(torch.tensor(idx, device=patch_feat.device))        # (B, C, p, p)
+        win = small[which[:, None, None], :, rows, cols]                                     # (M, ss, ss, C)
+    else:
+        win = patch_feat[(mb * N + mn)[:, None, None], ms[:, None, None], :, rows, cols]   # (M, ss, ss, C)
     win = win.permute(0, 3, 1, 2).reshape(B, S, N, C_out, ssize, ssize)[:, 1:].reshape(B * (S - 1) * N, C_out, ssize * ssize)
 
     sim = torch.einsum("mc,mcr->mr", q, win)

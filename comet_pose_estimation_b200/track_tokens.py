@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 from ._dev import inner_contig, pad_mode, prec_mode, require_cuda, require_no_grad, stream_ptr
-from .blocks import CorrBlock, EfficientCorrBlock, _Pyramid, _tc_workspace, _use_tc
+from .blocks import CorrBlock, EfficientCorrBlock, Upsampled2x, _make_pyramid, _tc_workspace, _use_tc
 
 lib = _lib.lib
 
@@ -85,11 +85,11 @@ class TrackTokenizer:
     def __init__(self, corr: Union[CorrBlock, EfficientCorrBlock, torch.Tensor], coords0: torch.Tensor,
                  tdim: int, num_levels: Optional[int] = None, radius: Optional[int] = None,
                  padding_mode: Optional[str] = None):
-        if isinstance(corr, torch.Tensor):
+        if isinstance(corr, (torch.Tensor, Upsampled2x)):
             assert num_levels is not None and radius is not None
-            self._pyr = _Pyramid(corr, num_levels)
             self.radius = radius
             self.padding_mode = padding_mode or "zeros"
+            self._pyr = _make_pyramid(corr, num_levels, radius, self.padding_mode)
         else:
             self._pyr = corr._pyr
             self.radius = corr.radius

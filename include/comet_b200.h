@@ -45,6 +45,11 @@ extern "C" {
 #define COMET_PYR_NCHW 0         /* pyramid levels 1..L-1 stored (BS, C, H_l, W_l), like the reference */
 #define COMET_PYR_CHANNEL_LAST 1 /* ... stored (BS, H_l, W_l, C): one contiguous line per position (fine tracker) */
 #define COMET_PYR_ALL_CHANNEL_LAST 2 /* as 1, and level 0 (the caller's fmaps) is channel-last (BS, H, W, C) too */
+#define COMET_PYR_UP2_SOURCE 3       /* level 0 is NOT stored: `fmaps` is the half-resolution map S (BS, Hs, Ws, C),
+                                        channel-last, whose bilinear align_corners up-sampling to (H, W) = (2Hs-1, 2Ws-1)
+                                        is the level-0 map (ShallowEncoder's last op, blocks.py:176-190); levels 0 and 1
+                                        are evaluated from S inside the lookup, `pyr` holds level L-1 = 2 only
+                                        (BS, H/4, W/4, C), written by comet_pyramid_up2_f32.  C=32, L=3, r=3, zeros. */
 
 #define COMET_FMAPS_NCHW 0         /* fmaps (BS, C, H, W) contiguous, as the reference's encoders return them */
 #define COMET_FMAPS_CHANNEL_LAST 1 /* fmaps (BS, H, W, C) dense: a torch.channels_last encoder output, used zero-copy */
@@ -84,6 +89,14 @@ int comet_pyramid_f32(const float* fmaps, float* pyr, int BS, int C, int H, int 
  * tracker's patches); COMET_FMAPS_CHANNEL_LAST input requires C % 4 == 0 and 16-byte aligned buffers. */
 int comet_pyramid_cl_f32(const float* fmaps, float* pyr, int BS, int C, int H, int W, int L, int fmaps_layout,
                          comet_stream_t stream);
+
+/* Level 2 of the pyramid of the up-sampled map, straight from the half-resolution source (COMET_PYR_UP2_SOURCE):
+ * src (BS, Hs, Ws, C) channel-last -> p2 (BS, (Hs-1)/2, (Ws-1)/2, C) channel-last.  Replaces, for this package's own
+ * refine_track, the reference's F.interpolate (blocks.py:176-190) + CorrBlock.__init__ pooling (blocks.py:368-374). */
+long long comet_pyramid_up2_elems(int BS, int C, int Hs, int Ws);
+int comet_pyramid_up2_f32(const float* src, float* p2, int BS, int C, int Hs, int Ws, comet_stream_t stream);
+/* 1 if (C, level-0 H x W, L, r, pad_mode) is served by COMET_PYR_UP2_SOURCE on the current device. */
+int comet_up2_supported(int C, int H, int W, int L, int r, int pad_mode);
 
 /* ---- correlation volume: CorrBlock.corr, blocks.py:409-429 -------------
  * vol[bs, n, hw] = (sum_c targets[bs, n, c] * fmap[bs, c, hw]) / sqrt(C) for ONE pyramid level.

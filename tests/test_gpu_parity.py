@@ -649,3 +649,64 @@ def test_extract_patches_clamps_corners_on_non_square_images(cb):
         for s in range(2):
             x0 = int(tl[0, s, n, 0].clamp(0, 33 - 31)); y0 = int(tl[0, s, n, 1].clamp(0, 40 - 31))
             assert torch.equal(p[n * 2 + s], imgs[0, s, :, y0:y0 + 31, x0:x0 + 31])
+
+
+# ------------------------------------------------------------------ fine tracker on the half-resolution source map
+def _cl5(t):
+    """(B,S,C,H,W) tensor re-laid out channels-last (same shape)."""
+    return t.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+
+
+@pytest.mark.parametrize("hs", [16, 9])
+def test_up2_lookup_matches_materialised_upsampling_and_oracle(cb, hs):
+    """COMET_PYR_UP2_SOURCE: CorrBlock.from_upsampled(S) == CorrBlock(F.interpolate(S, 2Hs-1, bilinear, align_corners))
+    -- fcorrs and tokens, queries on, near and off the border (zero padding is applied on each level's own tap grid),
+    against the materialised path (itself held to the reference goldens) and against the oracle."""
+    import torch.nn.functional as F
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    Bp, S, C = 37, 3, 32
+    H = 2 * hs - 1
+    src = _cl5(torch.randn(Bp, S, C, hs, hs, device="cuda", generator=g))
+    full = F.interpolate(src.reshape(Bp * S, C, hs, hs), (H, H), mode="bilinear", align_corners=True).reshape(Bp, S, C, H, H)
+    feats = torch.randn(Bp, S, 1, C, device="cuda", generator=g)
+    coords = torch.rand(Bp, S, 1, 2, device="cuda", generator=g) * (H + 5) - 3
+    coords[0, 0, 0] = torch.tensor([0.0, H - 1.0], device="cuda")
+    coords[1, 0, 0] = torch.tensor([H - 0.5, -0.5], device="cuda")
+    coords[2, 0, 0] = torch.tensor([H - 1.0, H - 1.0], device="cuda")
+    coords[3, 0, 0] = torch.tensor([-50.0, 1e9], device="cuda")
+    up = cb.CorrBlock.from_upsampled(src, num_levels=3, radius=3)
+    assert type(up._pyr).__name__ == "_PyramidUp2"
+    ref = cb.CorrBlock(_cl5(full), num_levels=3, radius=3)
+    up.corr(feats)
+    ref.corr(feats)
+    a, b = up.sample(coords), ref.sample(coords)
+    assert rel_to_max(host(a), host(b)) < 1e-5
+    want = O.corr_lookup(host(full), host(feats), host(coords), 3, 3)
+    assert rel_to_max(host(a), want) < FP32_BAR
+    tdim = cb.transformer_dim(3, 3, C, True)
+    xa = cb.TrackTokenizer(up, coords[:, 0], tdim).tokens(coords, feats)
+    xb = cb.TrackTokenizer(ref, coords[:, 0], tdim).tokens(coords, feats)
+    assert rel_to_max(host(xa), host(xb)) < 1e-5
+    # the attributes the reference exposes still work (materialised lazily)
+    assert [tuple(l.shape[-2:]) for l in up.fmaps_pyramid] == [tuple(l.shape[-2:]) for l in ref.fmaps_pyramid]
+    assert rel_to_max(host(up.fmaps_pyramid[2]), host(ref.fmaps_pyramid[2])) < 1e-6
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ab, bb = up.sample(coords), ref.sample(coords)
+    assert rel_to_max(host(ab), host(bb)) < BF16_BAR
+    # shapes the specialised kernel does not serve fall back to the materialised tensor
+    other = cb.CorrBlock.from_upsampled(src, num_levels=2, radius=2)
+    assert type(other._pyr).__name__ == "_Pyramid"
+    other.corr(feats)
+    assert rel_to_max(host(other.sample(coords)), O.corr_lookup(host(full), host(feats), host(coords), 2, 2)) < FP32_BAR
+
+
+def test_up2_pyramid_level2_matches_pooled_upsampling(cb):
+    import torch.nn.functional as F
+
+    src = _cl5(torch.randn(5, 2, 32, 16, 16, device="cuda"))
+    p = cb.CorrBlock.from_upsampled(src, num_levels=3, radius=3)._pyr
+    got = p.pyr[: 10 * 7 * 7 * 32].view(10, 7, 7, 32).permute(0, 3, 1, 2)
+    full = F.interpolate(src.reshape(10, 32, 16, 16), (31, 31), mode="bilinear", align_corners=True)
+    want = F.avg_pool2d(F.avg_pool2d(full, 2, 2), 2, 2)
+    assert rel_to_max(host(got), host(want)) < 1e-6

@@ -144,9 +144,14 @@ def test_patch_gather_kernel_matches_torch_indexing():
 
 
 @pytest.mark.gpu
-def test_dropin_refine_track_matches_reference(golden):
-    from comet_pose_estimation_b200.refine_track import refine_track
+@pytest.mark.parametrize("defer", [True, False])
+def test_dropin_refine_track_matches_reference(golden, defer):
+    """defer=True: the fine tracker reads the encoder's half-resolution map (blocks.Upsampled2x, the default);
+    defer=False: the up-sampled patch features are materialised and reach the kernels as a channels-last view."""
+    import importlib
 
+    rt = importlib.import_module("comet_pose_estimation_b200.refine_track")
+    refine_track = rt.refine_track
     g = golden("refine")
     fnet, ftr = modules(g)
     fnet = fnet.cuda().to(memory_format=torch.channels_last)
@@ -163,6 +168,14 @@ def test_dropin_refine_track_matches_reference(golden):
         layouts.append(self.cl_input)
 
     blk._Pyramid.__init__ = spy
+    orig_up = blk._PyramidUp2.__init__
+
+    def spy_up(self, up, num_levels):
+        orig_up(self, up, num_levels)
+        layouts.append("up2")
+
+    blk._PyramidUp2.__init__ = spy_up
+    rt.DEFER_UPSAMPLE = defer
     # the golden comes from the reference on CPU (strict fp32); cuDNN would otherwise run the encoder's convolutions
     # in TF32 (PyTorch's default), which is an encoder-precision choice outside the path under test
     tf32 = torch.backends.cudnn.allow_tf32
@@ -174,8 +187,11 @@ def test_dropin_refine_track_matches_reference(golden):
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
         blk._Pyramid.__init__ = orig
+        blk._PyramidUp2.__init__ = orig_up
+        rt.DEFER_UPSAMPLE = True
         h.remove()
-    assert layouts == [True]  # the encoder output reached the kernels as a channels-last view, zero-copy
+    # defer: the half-resolution source reached the kernels; else: the encoder output as a channels-last view, zero-copy
+    assert layouts == (["up2"] if defer else [True])
     assert rel_to_max(toks[0], g[NAME + "/tok0"]) < 1e-4
     for i in range(1, 6):
         assert rel_to_max(toks[i], g[f"{NAME}/tok{i}"]) < TOK_BAR
