@@ -10,7 +10,10 @@ exactly what COMET.forward_all makes the tracker's correlation / lookup / token 
   coarse tracker  fmaps (1,16,128,64,64), N=512 tracks, L=5, r=4:  pyramid + pos-emb once, then 4 iterations of
                   [correlation -> 9x9x5 window lookup -> track tokens (1,512,16,664)]
   fine tracker    patch features (512,16,32,31,31), 1 track/patch, L=3, r=3: pyramid + pos-emb once, then
-                  6 iterations of [correlation -> 7x7x3 lookup -> tokens (512,1,16,216)]
+                  6 iterations of [correlation -> 7x7x3 lookup -> tokens (512,1,16,216)].  The patch features are the
+                  2x-1 bilinear up-sampling of the patch encoder's 16x16 output (blocks.py:176-190); the default
+                  --fine-layout up2 hands the path that 16x16 map, as this package's refine_track does (the up-sampled
+                  tensor is never materialised); cl / nchw hand it the materialised 31x31 tensor (variants).
 
 The update transformer that runs between iterations is outside the path, so every iteration reads its
 own pre-generated coords / track_feats (seeded random walk around the query points) -- the bytes and flops of the
@@ -58,9 +61,27 @@ def tdim(L, r, latent, fine):
 
 
 # --------------------------------------------------------------------------- synthetic inputs (host, seeded)
-def make_inputs(Q, seed, torch, pin, fine_layout="nchw"):
+def upsample_fine(torch, src, layout):
+    """The fine tracker's materialised patch features: F.interpolate(src, 31x31, bilinear, align_corners=True) -- what
+    ShallowEncoder.forward returns (blocks.py:176-190) -- as a channels-last view ("cl") or NCHW-contiguous ("nchw")."""
+    import torch.nn.functional as F
+
+    B, S, C, hs, ws = src.shape
+    H, W = 2 * hs - 1, 2 * ws - 1
+    out = torch.empty(B, S, H, W, C, dtype=torch.float32, device=src.device).permute(0, 1, 4, 2, 3)
+    step = max(1, 4096 // S)
+    for b0 in range(0, B, step):
+        x = src[b0:b0 + step]
+        out[b0:b0 + step] = F.interpolate(x.reshape(-1, C, hs, ws), (H, W), mode="bilinear",
+                                          align_corners=True).reshape(x.shape[0], S, C, H, W)
+    return out if layout == "cl" else out.contiguous()
+
+
+def make_inputs(Q, seed, torch, pin, fine_layout="up2"):
     """Host tensors for Q sequences.  SURVEY 8(d) item 5: fmaps ~ N(0,1); queries U over the map; per-iteration
-    coords = query + small random walk (frame 0 pinned); per-iteration track_feats ~ N(0,1)."""
+    coords = query + small random walk (frame 0 pinned); per-iteration track_feats ~ N(0,1).  The fine tracker's
+    input is generated as the patch encoder's 16x16 output ~ N(0,1) (channels-last memory); for the cl / nchw layouts
+    it is up-sampled to 31x31 here (outside any timed region), so every layout carries the same values."""
     g = torch.Generator().manual_seed(seed)
 
     def alloc(*shape):
@@ -70,13 +91,22 @@ def make_inputs(Q, seed, torch, pin, fine_layout="nchw"):
     out = {}
     for name, cfg, B, N in (("coarse", COARSE, Q, COARSE["N"]), ("fine", FINE, Q * FINE["P"], 1)):
         S, C, H, W, it = cfg["S"], cfg["C"], cfg["H"], cfg["W"], cfg["iters"]
-        if name == "fine" and fine_layout == "cl":
-            # same (B,S,C,H,W) tensor, memory laid out (B,S,H,W,C): the native output layout of a channels-last
-            # patch encoder; the kernels use it zero-copy
-            fm = alloc(B, S, H, W, C).permute(0, 1, 4, 2, 3)
+        if name == "fine":
+            hs, ws = H // 2 + 1, W // 2 + 1
+            src = torch.empty(B, S, hs, ws, C, dtype=torch.float32).permute(0, 1, 4, 2, 3)   # channels-last memory
+            src.normal_(generator=g)
+            if fine_layout == "up2":
+                fm = alloc(B, S, hs, ws, C).permute(0, 1, 4, 2, 3)
+                fm.copy_(src)
+            else:
+                up = upsample_fine(torch, src, fine_layout)
+                fm = (alloc(B, S, H, W, C).permute(0, 1, 4, 2, 3) if fine_layout == "cl" else alloc(B, S, C, H, W))
+                fm.copy_(up)
+                del up
+            del src
         else:
             fm = alloc(B, S, C, H, W)
-        fm.normal_(generator=g)
+            fm.normal_(generator=g)
         q = torch.rand(B, 1, N, 2, generator=g) * torch.tensor([W - 1.0, H - 1.0])
         coords = alloc(it, B, S, N, 2)
         feats = alloc(it, B, S, N, C)
@@ -114,7 +144,10 @@ class HotPath:
         for name, cfg, out in (("coarse", COARSE, self.tok_c), ("fine", FINE, self.tok_f)):
             x = d[name]
             self._mark(None)
-            blk = cb.CorrBlock(x["fmaps"], num_levels=cfg["L"], radius=cfg["r"])
+            if name == "fine" and x["fmaps"].shape[-1] != cfg["W"]:      # the encoder's half-resolution map (up2)
+                blk = cb.CorrBlock.from_upsampled(x["fmaps"], num_levels=cfg["L"], radius=cfg["r"])
+            else:
+                blk = cb.CorrBlock(x["fmaps"], num_levels=cfg["L"], radius=cfg["r"])
             self._mark(name + "_pyramid")
             tk = cb.TrackTokenizer(blk, x["coords"][0][:, 0], out.shape[-1])
             self._mark(name + "_posemb")
@@ -124,26 +157,61 @@ class HotPath:
         return self.tok_c, self.tok_f
 
 
-def algorithmic_bytes(Q):
-    """DESIGN.md section 5.  Per launch of the fused token kernel."""
+def fine_lines_per_query(coords, layout):
+    """Mean number of 128-byte feature lines one fine query must read, from the ACTUAL coordinates: every box of the
+    lookup is clipped to its map (taps off the map are zero padding and cost no traffic -- the TMA unit zero-fills them
+    without fetching).  coords: (..., 2) float tensor in level-0 (31x31) cell units."""
+    f = FINE
+    x, y = coords[..., 0].double(), coords[..., 1].double()
+
+    def inmap(c, scale, r, edge, size):
+        o = (c * scale).floor() - r
+        return ((o + edge).clamp(max=size) - o.clamp(min=0)).clamp(min=0)
+
+    r = f["r"]
+    if layout == "up2":
+        hs = f["H"] // 2 + 1
+        h2 = (hs - 1) // 2
+        n = inmap(x, 0.5, r, 9, hs) * inmap(y, 0.5, r, 9, hs) + inmap(x, 0.25, r, 8, h2) * inmap(y, 0.25, r, 8, h2)
+    else:
+        n, h = 0, f["H"]
+        for l in range(f["L"]):
+            n = n + inmap(x, 0.5 ** l, r, 2 * r + 2, h) * inmap(y, 0.5 ** l, r, 2 * r + 2, h)
+            h //= 2
+    return float(n.mean())
+
+
+def algorithmic_bytes(Q, fine_coords=None, fine_layout="up2"):
+    """bytes one launch has to move.  fine_tokens uses the window-neighbourhood definition (SURVEY
+    8d) with every box clipped to its map per query (round-1's figure counted taps the hardware never fetches)."""
     c, f = COARSE, FINE
     tdc, tdf = tdim(c["L"], c["r"], c["C"], False), tdim(f["L"], f["r"], f["C"], True)
     # coarse: SURVEY 8(d) compulsory traffic (whole level-0 map + targets + coords + tokens)
     coarse = Q * (c["S"] * c["C"] * c["H"] * c["W"] * 4 + c["S"] * c["N"] * c["C"] * 4 + c["S"] * c["N"] * 8
                   + c["N"] * c["S"] * tdc * 4)
-    # fine: window-neighbourhood definition (SURVEY 8d, the 194 MB figure): the (2r+2)^2 taps of every level,
-    # clipped to the level size, + target + coords + token row (+ pos-emb row amortised over S)
-    G = 2 * f["r"] + 2
-    taps, h, w = 0, f["H"], f["W"]
-    for _ in range(f["L"]):
-        taps += min(G, h) * min(G, w)
-        h, w = h // 2, w // 2
-    per_q = taps * f["C"] * 4 + f["C"] * 4 + 8 + tdf * 4 + tdf * 4 / f["S"]
+    if fine_coords is not None:
+        lines = fine_lines_per_query(fine_coords, fine_layout)
+    elif fine_layout == "up2":
+        hs = f["H"] // 2 + 1
+        lines = min(9, hs) ** 2 + min(2 * f["r"] + 2, (hs - 1) // 2) ** 2      # S box + level-2 box, unclipped by position
+    else:
+        G = 2 * f["r"] + 2
+        lines, h = 0, f["H"]
+        for _ in range(f["L"]):
+            lines += min(G, h) ** 2
+            h //= 2
+    per_q = lines * f["C"] * 4 + f["C"] * 4 + 8 + tdf * 4 + tdf * 4 / f["S"]
     fine = Q * f["P"] * f["S"] * per_q
     pyr_c = Q * c["S"] * c["C"] * 4 * (64 * 64 + 2 * (32 * 32 + 16 * 16 + 8 * 8) + 4 * 4)
-    # read the 30x30 positions of level 0 that floor-mode pooling uses, write levels 1-2
-    pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (30 * 30 + 15 * 15 + 7 * 7)
-    return dict(coarse_tokens=coarse, fine_tokens=fine, coarse_pyramid=pyr_c, fine_pyramid=pyr_f)
+    if fine_layout == "up2":
+        hs = f["H"] // 2 + 1
+        # read the 15x15 positions of the 16x16 source that level 2 depends on, write level 2
+        pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * ((hs - 1) ** 2 + ((hs - 1) // 2) ** 2)
+    else:
+        # read the 30x30 positions of level 0 that floor-mode pooling uses, write levels 1-2
+        pyr_f = Q * f["P"] * f["S"] * f["C"] * 4 * (30 * 30 + 15 * 15 + 7 * 7)
+    return dict(coarse_tokens=coarse, fine_tokens=fine, coarse_pyramid=pyr_c, fine_pyramid=pyr_f,
+                fine_lines_per_query=lines)
 
 
 class ClockSampler:
@@ -189,67 +257,74 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_reference_seq_per_s(torch, reps):
-    """Times the CPU port of the same hot path (oracle/torch_port.py: the reference's own ATen calls) on the host
-    cores: ONE sequence per rep (coarse 4 iterations + fine 6 iterations, pyramids included)."""
+def cpu_hot_path(torch, d):
+    """One pass of the SAME hot path on the host cores through oracle/torch_port.py (the reference's own ATen calls):
+    per sequence coarse 4 iterations + fine 6 iterations, pyramids included.  The fine tracker gets the materialised
+    31x31 patch features (what the reference's CorrBlock receives)."""
     from oracle import torch_port as P
 
+    with torch.no_grad():
+        for name, cfg in (("coarse", COARSE), ("fine", FINE)):
+            x = d[name]
+            td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
+            lv = P.pyramid(x["fmaps"], cfg["L"])
+            for i in range(cfg["iters"]):
+                P.hot_path_iteration(lv, x["coords"][i], x["feats"][i], cfg["r"], (cfg["H"], cfg["W"]), td)
+
+
+def cpu_reference_seq_per_s(torch, reps):
+    """cpu_baseline of the GPU arm's line: ONE sequence per rep (bounded sample), best of `reps` after a warm-up."""
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    d = make_inputs(1, 1234, torch, pin=False)
+    d = make_inputs(1, 1234, torch, pin=False, fine_layout="nchw")
     times = []
-    with torch.no_grad():
-        for rep in range(reps + 1):
-            t0 = time.perf_counter()
-            for name, cfg in (("coarse", COARSE), ("fine", FINE)):
-                x = d[name]
-                td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
-                lv = P.pyramid(x["fmaps"], cfg["L"])
-                for i in range(cfg["iters"]):
-                    P.hot_path_iteration(lv, x["coords"][i], x["feats"][i], cfg["r"], (cfg["H"], cfg["W"]), td)
-            dt = time.perf_counter() - t0
-            if rep > 0 or reps == 0:
-                times.append(dt)
+    for rep in range(reps + 1):
+        t0 = time.perf_counter()
+        cpu_hot_path(torch, d)
+        dt = time.perf_counter() - t0
+        if rep > 0 or reps == 0:
+            times.append(dt)
     return 1.0 / min(times), statistics.mean(times), ncores
 
 
+def make_config(Q, world, fine_layout):
+    """`config` of the JSON line -- identical in both arms (the workload, not the implementation)."""
+    return {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
+            "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
+            "fine_input": "patch encoder output 16x16x32 per (track, frame); the fine tracker's 31x31 features are its "
+                          "2x-1 bilinear up-sampling (blocks.py:176-190)",
+            "l2": "inputs per step exceed L2 (fine patch features: %.1f GB at 31x31, %.2f GB at 16x16)"
+                  % (Q * 1.008, Q * 0.268)}
+
+
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (pinned port, kind "port") on all host cores,
+    SAME workload as the GPU arm: `--batch` sequences per step."""
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     t0 = time.perf_counter()
-    # warmup + K steps, each step = one sequence (bounded sample of the batch workload)
-    from oracle import torch_port as P  # noqa: F401
-
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    d = make_inputs(1, 1234, torch, pin=False)
-
-    def one():
-        with torch.no_grad():
-            for name, cfg in (("coarse", COARSE), ("fine", FINE)):
-                x = d[name]
-                td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
-                lv = P.pyramid(x["fmaps"], cfg["L"])
-                for i in range(cfg["iters"]):
-                    P.hot_path_iteration(lv, x["coords"][i], x["feats"][i], cfg["r"], (cfg["H"], cfg["W"]), td)
-
+    Q = args.batch
+    d = make_inputs(Q, 1234, torch, pin=False, fine_layout="nchw")
     for _ in range(args.warmup):
-        one()
+        cpu_hot_path(torch, d)
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        one()
+        cpu_hot_path(torch, d)
     el = time.perf_counter() - t1
-    v = args.steps / el
+    v = Q * args.steps / el
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(1), "note": "CPU: one sequence per step (bounded sample of the batch)"},
+        "config": make_config(Q, max(1, args.gpus), args.fine_layout),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
-                         "sample": "1 sequence/step: coarse 4 it + fine 6 it, pyramids included; torch CPU fp32"},
+                         "sample": f"{Q} sequences/step (the GPU arm's batch): coarse 4 it + fine 6 it, pyramids included; "
+                                   "oracle/torch_port.py (the reference's own ATen calls), torch CPU fp32, rank 0 only"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -275,10 +350,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
-    ap.add_argument("--fine-layout", default="cl", choices=["nchw", "cl"],
-                    help="memory layout of the fine tracker's patch features: cl = channels-last view, what this "
-                         "package's refine_track hands to the path (torch.channels_last encoder, zero-copy); nchw = "
-                         "contiguous (B,S,C,H,W) as the reference's own refine_track would hand over")
+    ap.add_argument("--fine-layout", default="up2", choices=["up2", "cl", "nchw"],
+                    help="what the fine tracker is handed: up2 = the patch encoder's 16x16 output (this package's "
+                         "refine_track: the 31x31 up-sampling is evaluated inside the lookup); cl = materialised 31x31 "
+                         "features as a channels-last view; nchw = contiguous (B,S,C,H,W) as the reference's own "
+                         "refine_track would hand over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -307,7 +383,8 @@ def main():
     prev_affinity = cl.bind_to_gpu_numa_node(local) if world > 1 else None
 
     Q = args.batch
-    host = make_inputs(Q, 1000 + rank, torch, pin=True, fine_layout=args.fine_layout)
+    layout = args.fine_layout
+    host = make_inputs(Q, 1000 + rank, torch, pin=True, fine_layout=layout)
     # empty_like + copy_ keep the strides (a channels-last view stays a channels-last view on the device)
     devin = {k: {n: torch.empty_like(t, device=dev).copy_(t, non_blocking=True) for n, t in v.items()}
              for k, v in host.items()}
@@ -327,35 +404,47 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, steps, warmup, per_class=False):
+        """W warm-ups, barrier, K steps between two events on the launching stream, barrier; max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if per_class:
+            hp.events = []
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ev, hp.events = hp.events, None
+        per = {}
+        if ev:
+            for (t0_, a_), (t1_, b_) in zip(ev[:-1], ev[1:]):
+                if t1_ is not None:
+                    per.setdefault(t1_, []).append(a_.elapsed_time(b_))
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, per
+
     # ---- device-resident arm ------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None   # samples every 20 ms from the warm-up to the end of the timed region
-    for _ in range(args.warmup):
+    launches0 = None
+
+    def step_dev():
         hp.run(devin)
+
+    for _ in range(args.warmup):
+        step_dev()
     barrier()
     launches0 = cb._lib.lib.comet_launch_count()
-    hp.events = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        hp.run(devin)
-    e1.record()
+    ms_step, per = timed(step_dev, args.steps, 0, per_class=True)
     launches = cb._lib.lib.comet_launch_count() - launches0  # counted by the library itself, one per kernel launch
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None
-    events, hp.events = hp.events, None
-    ms_step = ms_total / args.steps
     value = Q * world / (ms_step * 1e-3)
 
-    # per-kernel-class device time from the events recorded inside the timed region
-    per = {}
-    for (t0, a), (t1, b) in zip(events[:-1], events[1:]):
-        if t1 is None:
-            continue
-        per.setdefault(t1, []).append(a.elapsed_time(b))
     kern = {k: {"launch_groups": len(v), "ms_avg": sum(v) / len(v), "ms_per_step": sum(v) / args.steps}
             for k, v in per.items()}
-    ab = algorithmic_bytes(Q)
+    ab = algorithmic_bytes(Q, host["fine"]["coords"], layout)
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
     peak, peak_src = peaks()
     for k in kern:
@@ -366,9 +455,11 @@ def main():
     # HBM-bound; `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this batch size and layout
     # from the committed ncu --set full captures (profiles/traffic.json, written by scripts/ncu_summary.py --traffic).
     KNAME = {
-        "fine_tokens": {"cl": "corr_lookup_c32_tma_kernel<R=3,TOKENS> (fine tracker: TMA-staged corr + lookup + tokens)",
+        "fine_tokens": {"up2": "corr_lookup_c32_up2_kernel<TOKENS> (fine tracker: TMA-staged corr + lookup + tokens on the 16x16 source map)",
+                        "cl": "corr_lookup_c32_tma_kernel<R=3,TOKENS> (fine tracker: TMA-staged corr + lookup + tokens)",
                         "nchw": "corr_lookup_c32_kernel<R=3,TOKENS> (fine tracker: fused corr + lookup + tokens)"},
-        "fine_pyramid": {"cl": "pyramid_cl_in_fine_kernel (fine tracker: channel-last pyramid)",
+        "fine_pyramid": {"up2": "pyramid_up2_kernel (fine tracker: level 2 pooled straight from the 16x16 source map)",
+                         "cl": "pyramid_cl_in_fine_kernel (fine tracker: channel-last pyramid)",
                          "nchw": "pyramid_cl_fine_kernel (fine tracker: NCHW -> channel-last pyramid)"},
         "coarse_tokens": {"cl": "tc_pre_kernel + corr_tc_kernel (coarse tracker: tcgen05 corr + lookup + tokens)"},
         "coarse_pyramid": {"cl": "tc_prepare_kernel (coarse pyramid + bf16 hi/lo split)"},
@@ -381,25 +472,28 @@ def main():
 
     def roofline_of(cls):
         k = kern[cls]
-        tj = tj_all.get(f"{cls}/{args.fine_layout}") or tj_all.get(cls) or {}
+        tj = tj_all.get(f"{cls}/{layout}") or (tj_all.get(cls) if not cls.startswith("fine") else None) or {}
         traffic = tj.get("dram_bytes_per_launch") if tj.get("batch") == Q else None
         names = KNAME.get(cls, {})
-        return {"bound": "hbm", "kernel": names.get(args.fine_layout, names.get("cl", cls)),
-                "achieved": k.get("GBps"), "peak": peak, "unit": "GB/s",
-                "frac": (k["GBps"] / peak) if "GBps" in k else None, "traffic": traffic,
+        gbps = k.get("GBps")
+        return {"bound": "hbm", "kernel": names.get(layout, names.get("cl", cls)),
+                "achieved": gbps, "peak": peak, "unit": "GB/s",
+                "frac": (gbps / peak) if gbps else None, "traffic": traffic,
+                "frac_dram": (traffic / (k["ms_avg"] * 1e-3) / 1e9 / peak) if traffic else None,
                 "traffic_source": tj.get("source") if traffic else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ab.get(cls), "ms_per_launch": k["ms_avg"]}
 
     roof = roofline_of(dom if dom in ab else "fine_tokens")
     roof["dominant_by_time"] = dom
-    roof["note"] = ("algorithmic bytes: fine_tokens = window neighbourhoods + target + coords + token row (SURVEY 8d, the "
-                    "194 MB/sequence definition); fine_pyramid = level 0 read once + levels 1-2 written; coarse_tokens = "
-                    "SURVEY 8d compulsory traffic (fp32 maps + targets + coords + tokens)")
+    roof["note"] = ("algorithmic bytes: fine_tokens = per query the feature lines of its boxes CLIPPED to the maps (from the "
+                    "actual coordinates; %.1f lines of 128 B on average) + target + coords + token row; fine_pyramid = "
+                    "the source positions level 2 depends on read once + level 2 written; coarse_tokens = SURVEY 8d "
+                    "compulsory traffic (fp32 maps + targets + coords + tokens).  frac_dram = measured DRAM bytes "
+                    "(ncu, profiles/traffic.json) / time / peak" % ab["fine_lines_per_query"])
     rooflines = {c: roofline_of(c) for c in kern if c in ab}
     # correlation on the tensor pipe (coarse tracker): FLOPs as the reference defines them (dense, all pyramid levels,
     # one pass).  The kernel issues 3 bf16 passes (fp32 parity) but only for the band of map rows each sorted query
-    # tile touches (~45 % of the tiles at this query distribution), and it is bounded by the HBM read of the packed
-    # pyramid, not by the tensor pipe.
+    # tile touches (~45 % of the tiles at this query distribution).
     ct = kern["coarse_tokens"]
     flop_alg = 2.0 * Q * COARSE["S"] * COARSE["N"] * COARSE["C"] * 5456
     try:
@@ -412,52 +506,78 @@ def main():
               "frac": flop_alg / (ct["ms_avg"] * 1e-3) / 1e12 / tpeak, "ms_per_launch": ct["ms_avg"],
               "note": "reference-defined dense FLOPs / time; ms_per_launch includes the plan + token pre-kernel"}
 
-    # ---- the other memory layout of the fine tracker's patch features, same run (reported, not the headline) ----
     variants = {}
     if not args.no_variants:
-        other = "nchw" if args.fine_layout == "cl" else "cl"
-        f0 = devin["fine"]["fmaps"]
-        if other == "nchw":
-            alt = f0.contiguous()
-        else:
-            alt = f0.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
-        alt_in = {"coarse": devin["coarse"], "fine": dict(devin["fine"], fmaps=alt)}
-        for _ in range(args.warmup):
-            hp.run(alt_in)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            hp.run(alt_in)
-        e1.record()
-        barrier()
-        ms_alt = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        variants["fine_" + other] = {"value": Q * world / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt,
-                                     "what": "same step with the fine tracker's patch features " +
-                                             ("NCHW-contiguous (the reference encoder's own output layout)"
-                                              if other == "nchw" else "as a channels-last view")}
-        del alt, alt_in
+        # ---- the materialised layouts of the fine tracker's patch features, same values, same run ----
+        for other in [l for l in ("up2", "cl", "nchw") if l != layout]:
+            if other == "up2":
+                continue   # (the headline was run with a materialised layout: the source map is not available)
+            alt = upsample_fine(torch, devin["fine"]["fmaps"], other) if layout == "up2" else (
+                devin["fine"]["fmaps"].contiguous() if other == "nchw"
+                else devin["fine"]["fmaps"].permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3))
+            alt_in = {"coarse": devin["coarse"], "fine": dict(devin["fine"], fmaps=alt)}
+            ms_alt, per_alt = timed(lambda: hp.run(alt_in), args.steps, args.warmup, per_class=True)
+            variants["fine_" + other] = {
+                "value": Q * world / (ms_alt * 1e-3), "unit": UNIT, "ms_per_step": ms_alt,
+                "ms_per_step_by_class": {k: sum(v) / args.steps for k, v in per_alt.items()},
+                "what": "same step with the fine tracker handed MATERIALISED 31x31 patch features, " +
+                        ("NCHW-contiguous (the reference encoder's own output layout)" if other == "nchw"
+                         else "as a channels-last view (a torch.channels_last encoder's output, zero-copy)")}
+            del alt, alt_in
         # the reference's shipped configuration runs under torch.autocast(bf16) (mixed_precision: bf16, abl_ours.yaml:102):
         # CorrBlock.corr then rounds operands and volume to bf16.  Same step with that rounding mode selected.
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            for _ in range(args.warmup):
-                hp.run(devin)
-            barrier()
-            hp.events = []
-            e0.record()
-            for _ in range(args.steps):
-                hp.run(devin)
-            e1.record()
-            barrier()
-        ev_bf, hp.events = hp.events, None
-        per_bf = {}
-        for (t0, a), (t1, b) in zip(ev_bf[:-1], ev_bf[1:]):
-            if t1 is not None:
-                per_bf.setdefault(t1, []).append(a.elapsed_time(b))
-        ms_bf = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+            ms_bf, per_bf = timed(step_dev, args.steps, args.warmup, per_class=True)
         variants["autocast_bf16"] = {"value": Q * world / (ms_bf * 1e-3), "unit": UNIT, "ms_per_step": ms_bf,
                                      "ms_per_step_by_class": {k: sum(v) / args.steps for k, v in per_bf.items()},
                                      "what": "same step under torch.autocast(bf16): one tensor-core pass, bf16-rounded "
                                              "operands and volume, fp32 lookup (parity bar 2e-2)"}
+
+        # ---- B=1 (the reference's eval is hard-wired to batch 1): one sequence per step, eager and as ONE CUDA graph
+        # replay of its launches (launch.CudaGraphRunner) ----
+        one = {}
+        for k, v in devin.items():
+            nb = 1 if k == "coarse" else FINE["P"]
+            one[k] = {"fmaps": v["fmaps"][:nb], "coords": v["coords"][:, :nb].contiguous(),
+                      "feats": v["feats"][:, :nb].contiguous()}
+        hp1 = HotPath(cb, torch, 1, dev)
+        l0 = cb._lib.lib.comet_launch_count()
+        hp1.run(one)
+        n_launch1 = cb._lib.lib.comet_launch_count() - l0
+        ms_b1, _ = timed(lambda: hp1.run(one), max(args.steps, 20), args.warmup)
+        runner = cl.CudaGraphRunner(lambda: hp1.run(one))
+        ms_g1, _ = timed(lambda: runner(), max(args.steps, 20), args.warmup)
+        variants["batch1"] = {"value": world / (ms_b1 * 1e-3), "unit": UNIT, "ms_per_sequence": ms_b1,
+                              "launches_per_sequence": int(n_launch1), "what": "one sequence per step, eager launches"}
+        variants["batch1_graph"] = {"value": world / (ms_g1 * 1e-3), "unit": UNIT, "ms_per_sequence": ms_g1,
+                                    "launches_per_sequence": int(n_launch1),
+                                    "what": "one sequence per step, its launches captured once into a CUDA graph "
+                                            "(launch.CudaGraphRunner) and replayed"}
+        del runner, hp1, one
+
+        # ---- config 4 (BASELINE.json configs[3]): long sequence, dense query grid -- S=64, N=4096 (64x64 grid at pixel
+        # centres), coarse tracker only (the part that scales with S*N); per-iteration time and rates ----
+        S4, N4 = 64, 4096
+        g4 = torch.Generator(device=dev).manual_seed(4)
+        fm4 = torch.randn(1, S4, COARSE["C"], 64, 64, device=dev, generator=g4)
+        ys, xs = torch.meshgrid(torch.arange(64, device=dev), torch.arange(64, device=dev), indexing="ij")
+        q4 = torch.stack([xs, ys], -1).reshape(1, 1, N4, 2).float() + 0.5          # pixel centres (8i+4, 8j+4) / 8
+        co4 = (q4 + torch.randn(1, S4, N4, 2, device=dev, generator=g4) * 0.75)
+        co4[:, 0] = q4[:, 0]
+        ft4 = torch.randn(1, S4, N4, COARSE["C"], device=dev, generator=g4)
+        out4 = torch.empty(1, N4, S4, hp.td_c, device=dev)
+        blk4 = cb.CorrBlock(fm4, num_levels=COARSE["L"], radius=COARSE["r"])
+        tk4 = cb.TrackTokenizer(blk4, co4[:, 0], hp.td_c)
+        ms_c4, _ = timed(lambda: tk4.tokens(co4, ft4, out=out4), args.steps, args.warmup)
+        flop4 = 2.0 * S4 * N4 * COARSE["C"] * 5456
+        bytes4 = S4 * COARSE["C"] * 4096 * 4 + S4 * N4 * COARSE["C"] * 4 + S4 * N4 * 8 + N4 * S4 * hp.td_c * 4
+        variants["config4"] = {"ms_per_iteration": ms_c4, "dense_equiv_TFLOPs": flop4 / (ms_c4 * 1e-3) / 1e12,
+                               "frac_tensor_sustained": flop4 / (ms_c4 * 1e-3) / 1e12 / tpeak,
+                               "compulsory_GBps": bytes4 / (ms_c4 * 1e-3) / 1e9, "frac_hbm": bytes4 / (ms_c4 * 1e-3) / 1e9 / peak,
+                               "what": "coarse tracker, ONE sequence of S=64 frames with a dense 64x64 query grid (N=4096): "
+                                       "one fused iteration (plan + tcgen05 corr + lookup + tokens); the reference "
+                                       "materialises a 5.72 GB volume per iteration here"}
+        del fm4, co4, ft4, out4, blk4, tk4
 
     # ---- the producer of the fine tracker's input (outside `value`): patch gather + ShallowEncoder for
     # ONE sequence (8192 patches of a 16-frame 512x512 sequence), with the library's resize / instance-norm kernels and
@@ -471,81 +591,90 @@ def main():
         imgs = torch.rand(1, FINE["S"], 3, 512, 512, device=dev)
         tl = (torch.rand(1, FINE["S"], FINE["P"], 2, device=dev) * (512 - 31)).int()
 
-        def producer():
+        def producer(defer):
             with torch.no_grad():
-                return enc(rt.extract_patches(imgs, tl, 31))
+                return enc(rt.extract_patches(imgs, tl, 31), defer_upsample=defer)
 
         res = {}
-        for tag, flag in (("library_kernels", True), ("aten_ops", False)):
+        for tag, flag, defer in (("library_kernels_half_res", True, True), ("library_kernels", True, False), ("aten_ops", False, False)):
             rt.USE_LIBRARY_KERNELS = flag
-            for _ in range(2):
-                producer()
-            barrier()
-            e0.record()
-            for _ in range(3):
-                producer()
-            e1.record()
-            barrier()
-            res[tag] = max_over_ranks(e0.elapsed_time(e1)) / 3
+            res[tag], _ = timed(lambda: producer(defer), 3, 2)
         rt.USE_LIBRARY_KERNELS = True
-        variants["patch_encoder"] = {"ms_per_sequence": res["library_kernels"], "ms_per_sequence_aten_ops": res["aten_ops"],
-                                     "what": "refine_track's producer of the fine patch features (extract_patches + "
-                                             "ShallowEncoder, channels-last, cuDNN convolutions) for one sequence: "
-                                             "library resize + instance-norm kernels vs the ATen ops"}
+        variants["patch_encoder"] = {"ms_per_sequence_half_res_output": res["library_kernels_half_res"],
+                                     "ms_per_sequence": res["library_kernels"],
+                                     "ms_per_sequence_aten_ops": res["aten_ops"],
+                                     "what": "refine_track's producer of the fine tracker's input (extract_patches + "
+                                             "ShallowEncoder, channels-last, cuDNN convolutions) for one sequence: up to the "
+                                             "16x16 map the up2 layout consumes / with the final 31x31 up-sampling / with "
+                                             "the ATen resize + instance-norm ops"}
         del enc, imgs, tl
 
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------
     e2e = None
     if not args.no_e2e:
-        td_c, td_f = hp.tok_c, hp.tok_f
-        out_c = torch.empty(td_c.shape, dtype=torch.float32).pin_memory()
-        out_f = torch.empty(td_f.shape, dtype=torch.float32).pin_memory()
-        h2d = sum(t.numel() * 4 for v in host.values() for t in v.values())
-        d2h = out_c.numel() * 4 + out_f.numel() * 4
-        # Two device-side staging sets: the H2D copy of step i+1 (copy stream) overlaps the kernels and the D2H of step i
-        # (current stream).  Every step still copies all of its inputs from pinned host memory and reads its result
-        # back; the pipeline fill (first copy) is inside the timed region.
-        stages = [{k: {n: torch.empty_like(t, device=dev) for n, t in v.items()} for k, v in host.items()}
-                  for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
+        def e2e_arm(host_in):
+            out_c = torch.empty(hp.tok_c.shape, dtype=torch.float32).pin_memory()
+            out_f = torch.empty(hp.tok_f.shape, dtype=torch.float32).pin_memory()
+            h2d = sum(t.numel() * 4 for v in host_in.values() for t in v.values())
+            d2h = out_c.numel() * 4 + out_f.numel() * 4
+            # Two device-side staging sets: the H2D copy of step i+1 (copy stream) overlaps the kernels and the D2H of
+            # step i (current stream).  Every step still copies all of its inputs from pinned host memory and reads its
+            # result back; the pipeline fill (first copy) is inside the timed region.
+            stages = [{k: {n: torch.empty_like(t, device=dev) for n, t in v.items()} for k, v in host_in.items()}
+                      for _ in range(2)]
+            copy_stream = torch.cuda.Stream(device=dev)
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
 
-        def issue_copy(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i % 2])       # the kernels of step i-2 are done with this set
-                for k, v in host.items():
-                    for n, t in v.items():
-                        stages[i % 2][k][n].copy_(t, non_blocking=True)
-                copied[i % 2].record(copy_stream)
+            def issue_copy(i):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[i % 2])       # the kernels of step i-2 are done with this set
+                    for k, v in host_in.items():
+                        for n, t in v.items():
+                            stages[i % 2][k][n].copy_(t, non_blocking=True)
+                    copied[i % 2].record(copy_stream)
 
-        def e2e_run(nsteps):
-            cur = torch.cuda.current_stream(dev)
-            for ev in consumed:
-                ev.record(cur)
-            issue_copy(0)
-            for i in range(nsteps):
-                if i + 1 < nsteps:
-                    issue_copy(i + 1)
-                cur.wait_event(copied[i % 2])
-                a, b = hp.run(stages[i % 2])
-                consumed[i % 2].record(cur)
-                out_c.copy_(a, non_blocking=True)
-                out_f.copy_(b, non_blocking=True)
+            def e2e_run(nsteps):
+                cur = torch.cuda.current_stream(dev)
+                for ev in consumed:
+                    ev.record(cur)
+                issue_copy(0)
+                for i in range(nsteps):
+                    if i + 1 < nsteps:
+                        issue_copy(i + 1)
+                    cur.wait_event(copied[i % 2])
+                    a, b = hp.run(stages[i % 2])
+                    consumed[i % 2].record(cur)
+                    out_c.copy_(a, non_blocking=True)
+                    out_f.copy_(b, non_blocking=True)
 
-        n_e2e = max(2, min(args.steps, 10))
-        e2e_run(2)
-        barrier()
-        e0.record()
-        e2e_run(n_e2e)
-        e1.record()
-        barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
-        e2e = {"value": Q * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": n_e2e,
-               "api": "CorrBlock + TrackTokenizer (ctypes -> C ABI), pinned host tensors; H2D of step i+1 overlapped "
-                      "with the kernels / D2H of step i (two staging sets)"}
-        del stages
+            n_e2e = max(2, min(args.steps, 10))
+            e2e_run(2)
+            barrier()
+            e0.record()
+            e2e_run(n_e2e)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+            return {"value": Q * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": n_e2e,
+                    "h2d_GBps_per_gpu": h2d / (ms * 1e-3) / 1e9}
+
+        e2e = e2e_arm(host)
+        e2e["api"] = ("CorrBlock%s + TrackTokenizer (ctypes -> C ABI), pinned host tensors; H2D of step i+1 overlapped "
+                      "with the kernels / D2H of step i (two staging sets)" % (".from_upsampled" if layout == "up2" else ""))
+        e2e["fine_layout"] = layout
+        if layout == "up2" and not args.no_variants:
+            # round-1 definition, kept for continuity: the MATERIALISED channels-last 31x31 patch features cross PCIe
+            host_cl = dict(host, fine=dict(host["fine"]))
+            up = upsample_fine(torch, host["fine"]["fmaps"], "cl")
+            host_cl["fine"]["fmaps"] = torch.empty(up.permute(0, 1, 3, 4, 2).shape, dtype=torch.float32).pin_memory().permute(0, 1, 4, 2, 3)
+            host_cl["fine"]["fmaps"].copy_(up)
+            del up
+            e2e["variants"] = {"fine_cl": e2e_arm(host_cl)}
+            e2e["variants"]["fine_cl"]["what"] = ("round-1 definition: the materialised 31x31 channels-last patch features "
+                                                   "(4x the bytes) are copied from the host every step")
+            del host_cl
 
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)
@@ -557,17 +686,18 @@ def main():
                          f"fp32, {mean_s:.2f} s/sequence mean"}
 
     if rank == 0:
+        config = make_config(Q, world, layout)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
-                       "parallelism": f"dp{world} (sequences sharded across ranks, no collective)",
-                       "numa_bound": prev_affinity is not None,
-                       "fine_layout": args.fine_layout + (" (channels-last view of the patch encoder output, as "
-                                                          "comet_pose_estimation_b200.refine_track produces it)"
-                                                          if args.fine_layout == "cl" else " (contiguous)"),
-                       "l2": "inputs per step exceed L2 (fine patch features: %.1f GB)" % (Q * 1.008)},
+            "config": config,
+            "fine_layout": layout + {"up2": " (the fine tracker reads the patch encoder's 16x16 output; levels 0/1 of the "
+                                            "31x31 pyramid are evaluated inside the lookup, as comet_pose_estimation_b200."
+                                            "refine_track does)",
+                                     "cl": " (materialised 31x31 features, channels-last view)",
+                                     "nchw": " (materialised 31x31 features, contiguous)"}[layout],
+            "numa_bound": prev_affinity is not None,
             "roofline": roof, "rooflines": rooflines, "roofline_tensor": tensor, "variants": variants,
             "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "kernels": kern,

@@ -29,9 +29,9 @@ def transformer_dim(corr_levels: int, corr_radius: int, latent_dim: int, fine: b
     return d
 
 
-# (D, H, W, device) -> (channel-last sin/cos table (H, W, D), event recorded after it was built).  The reference
-# rebuilds and uploads the table every iteration; here it is kept, LRU-bounded (a tracker uses two shapes: coarse 10.9 MB,
-# fine 0.8 MB).
+# (D, H, W, device) -> channel-last sin/cos table (H, W, D).  The reference rebuilds and uploads the table every
+# iteration; here it is kept, LRU-bounded (a tracker uses two shapes: coarse 10.9 MB, fine 0.8 MB).  The building
+# stream is synchronised once, so later readers on any stream (or inside a CUDA-graph capture) need no event.
 _TABLES = OrderedDict()
 _TABLES_MAX = 8
 
@@ -42,17 +42,16 @@ def _sincos_table_cl(embed_dim: int, H: int, W: int, device) -> torch.Tensor:
     if hit is None:
         from .utils import get_2d_sincos_pos_embed
 
-        t = get_2d_sincos_pos_embed(embed_dim, (H, W), device=device)[0].permute(1, 2, 0).contiguous()
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(device))
-        _TABLES[key] = hit = (t, ev)
+        hit = get_2d_sincos_pos_embed(embed_dim, (H, W), device=device)[0].permute(1, 2, 0).contiguous()
+        if torch.cuda.is_current_stream_capturing():
+            return hit          # built inside a capture: valid for this graph only, not cached
+        torch.cuda.current_stream(device).synchronize()
+        _TABLES[key] = hit
         while len(_TABLES) > _TABLES_MAX:
             _TABLES.popitem(last=False)
     else:
         _TABLES.move_to_end(key)
-    # the table may have been built on another stream: order this stream after the build (no-op once complete)
-    torch.cuda.current_stream(device).wait_event(hit[1])
-    return hit[0]
+    return hit
 
 
 def sampled_pos_emb(coords0: torch.Tensor, embed_dim: int, H: int, W: int, cached_table: bool = True) -> torch.Tensor:
