@@ -62,6 +62,11 @@ SIGNATURES = {
                                        _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "comet_tc_corr_volume_f32": (_i, [_p, _p, _ll, _ll, _ll, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "comet_tc_status": (_i, []),
+    "comet_split_planes_f32": (_i, [_p, _ll, _p, _ll, _ll, _ll, _i, _i, _p]),
+    "comet_linear_tc": (_i, [_p, _ll, _ll, _p, _ll, _ll, _i, _p, _p, _ll, _p, _ll, _p, _ll, _ll, _i, _i, _ll, _i, _i, _p]),
+    "comet_layernorm_planes_f32": (_i, [_p, _ll, _p, _p, C.c_float, _p, _ll, _p, _ll, _ll, _i, _ll, _i, _p]),
+    "comet_attention_planes_f32": (_i, [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_add_planes_f32": (_i, [_p, _p, _p, _ll, _i, _ll, _p]),
     "comet_set_option": (_i, [_i, _i]),
     "comet_get_option": (_i, [_i]),
 }

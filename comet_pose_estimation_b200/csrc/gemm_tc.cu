@@ -1,0 +1,437 @@
+// Linear layers of the track-update transformer (EfficientUpdateFormer, comet/models/track_modules/blocks.py:205-348;
+// AttnBlock / CrossAttnBlock / Mlp, comet/models/modules.py:119-154, :248-344) on the 5th-generation tensor cores:
+//
+//     Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] ) (+ residual[M,N])
+//
+// tcgen05.mma (kind::f16, bf16 operands, float32 accumulation in TMEM), operand tiles staged by TMA (2-D tiled loads,
+// 128-byte swizzle, K-major) through an mbarrier ring, accumulator double-buffered in TMEM so that the epilogue of tile i
+// overlaps the MMAs of tile i+1.  Persistent CTAs (one per SM), 6 warps: TMA producer | MMA issuer (one elected thread) |
+// 4 epilogue warps (TMEM lane quarter = warp % 4).
+//
+// Precision.  Operands are "bf16 planes": a float32 tensor x is held as NP bf16 tensors p0 = bf16(x), p1 = bf16(x - p0),
+// p2 = bf16(x - p0 - p1).  NP = 1 is what torch.autocast(bf16) gives the reference's nn.Linear (COMET's shipped
+// mixed_precision: bf16); NP = 3 carries all 24 mantissa bits, and the product is accumulated over the six plane pairs
+// (i, j), i + j <= 2 (the dropped pairs are below 2^-24 relative) -- float32-grade results from bf16 tensor-core passes,
+// which the float32 parity mode of the tracker loop needs (rounding noise is amplified ~200x per refinement iteration).
+// The tensor core adds each K=16 block product to its float32 accumulator with truncation, an error that grows linearly
+// with the number of accumulation steps (measured 4e-9 * K relative with all six pairs in one accumulator), so the five
+// low-order pairs -- 2^-8 and less of the result -- go to a SECOND accumulator and the epilogue adds the two in float32:
+// the main accumulator sees K/16 steps instead of 6K/16 (float32 cuBLAS-level error, measured).
+// The epilogue emits the result as float32 and / or directly as planes for the next GEMM.
+#include "comet_common.cuh"
+
+#include <cuda.h>
+
+namespace comet {
+namespace gemm {
+
+constexpr int BM = 128, BN = 128, BK = 64;       // BK bf16 = one 128-byte swizzle row
+constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB (A tile == B tile)
+constexpr int THREADS = 192;                     // 6 warps
+constexpr int MAX_NP = 3;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct Maps {
+  CUtensorMap a[MAX_NP];   // X planes: {K, M} bf16, box {64, 128}
+  CUtensorMap w[MAX_NP];   // W planes: {K, N} bf16, box {64, 128}
+};
+
+struct Params {
+  int M, N, K;
+  int np;                  // planes per operand (1 or 3)
+  int nstage;              // ring depth: nstage * np * 32 KB <= SMEM_BUDGET
+  int tiles_m, tiles_n, ktiles;
+  const float* bias;       // [N] or null
+  const float* resid;      // [M, resid_ld] float32 or null (added after the activation)
+  long long resid_ld;
+  float* out;              // [M, out_ld] float32 or null
+  long long out_ld;
+  __nv_bfloat16* outp[MAX_NP];   // planes of the result, [M, outp_ld] each, or null
+  long long outp_ld;
+  int out_np;
+  int gelu;                // exact (erf) GELU, nn.GELU() default (modules.py:133)
+};
+
+// ------------------------------------------------------------------ PTX helpers (see corr_tc.cu for the rationale)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded by WALL time (10 s), not by a poll count: a protocol bug traps instead of hanging the box
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 4095u) == 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], both K-major
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); LBO is not used by
+// swizzled K-major layouts (canonical value 1).
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D f32, A/B bf16, both K-major, M=128, N=BN
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int stage_bytes = p.np * 2 * TILE_BYTES;           // [A planes][B planes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * stage_bytes);
+  uint64_t* full = bars;                 // [nstage]  TMA -> MMA
+  uint64_t* empty = full + p.nstage;     // [nstage]  MMA -> TMA
+  uint64_t* acc_full = empty + p.nstage; // [2]       MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;    // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(4 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
+        for (int kb = 0; kb < p.ktiles; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * stage_bytes;
+          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          for (int i = 0; i < p.np; ++i) {
+            tma_load_2d(&maps.a[i], &full[stage], dst + i * TILE_BYTES, kb * BK, mb * BM);
+            tma_load_2d(&maps.w[i], &full[stage], dst + (p.np + i) * TILE_BYTES, kb * BK, nb * BN);
+          }
+          if (++stage == (uint32_t)p.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      // TMEM columns of tile buffer `acc`: [main 128 | low-order pairs 128]
+      const uint32_t d_main = tmem_base + acc * 2 * BN, d_low = d_main + BN;
+      uint32_t accum_main = 0, accum_low = 0;
+      for (int kb = 0; kb < p.ktiles; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + p.np * TILE_BYTES;
+          // plane pairs (i, j), i + j < np: (0,0) into the main accumulator, the low-order ones into their own
+          for (int sum = p.np - 1; sum >= 0; --sum) {
+            for (int i = 0; i <= sum; ++i) {
+              const int j = sum - i;
+              const uint64_t ad = make_desc_kmajor(a0 + i * TILE_BYTES), bd = make_desc_kmajor(b0 + j * TILE_BYTES);
+              if (sum == 0) {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  umma_bf16_ss(d_main, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, accum_main);   // +32 bytes per K=16
+                  accum_main = 1;
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  umma_bf16_ss(d_low, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, accum_low);
+                  accum_low = 1;
+                }
+              }
+            }
+          }
+          tcgen05_commit(&empty[stage]);                       // smem stage free once these MMAs retire
+          if (kb + 1 == p.ktiles) tcgen05_commit(&acc_full[acc]);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)p.nstage) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int wq = warp & 3;                        // TMEM lane quarter this warp may access
+    const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
+    uint32_t acc = 0, acc_phase = 0;
+    const bool vec_out = p.out && (p.out_ld % 4 == 0) && (((uintptr_t)p.out) % 16 == 0);
+    const bool vec_res = p.resid && (p.resid_ld % 4 == 0) && (((uintptr_t)p.resid) % 16 == 0);
+    const bool vec_pl = p.out_np > 0 && (p.outp_ld % 8 == 0);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
+      const int m = mb * BM + 32 * wq + lane;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = nb * BN + 32 * c;
+        if (n0 >= p.N) break;                      // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + 32 * c, v);
+        if (p.np > 1) {
+          float lo[32];
+          tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + BN + 32 * c, lo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += lo[i];
+        } else {
+          tmem_ld_wait();
+        }
+        if (m < p.M) {
+          const bool full_chunk = n0 + 32 <= p.N;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += (full_chunk || n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (p.resid) {
+            const float* r = p.resid + (long long)m * p.resid_ld + n0;
+            if (vec_res && full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(r) + i);
+                v[4 * i] += g.x; v[4 * i + 1] += g.y; v[4 * i + 2] += g.z; v[4 * i + 3] += g.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (n0 + i < p.N) v[i] += __ldg(r + i);
+            }
+          }
+          if (p.out) {
+            float* o = p.out + (long long)m * p.out_ld + n0;
+            if (vec_out && full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (n0 + i < p.N) o[i] = v[i];
+            }
+          }
+          for (int pl = 0; pl < p.out_np; ++pl) {
+            __nv_bfloat16* o = p.outp[pl] + (long long)m * p.outp_ld + n0;
+            if (vec_pl && full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 2 * h], v[8 * i + 2 * h + 1]);
+                  w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+                  v[8 * i + 2 * h] -= __low2float(b2);          // residual for the next plane (exact in float32)
+                  v[8 * i + 2 * h + 1] -= __high2float(b2);
+                }
+                reinterpret_cast<uint4*>(o)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const __nv_bfloat16 b = __float2bfloat16_rn(v[i]);
+                if (n0 + i < p.N) o[i] = b;
+                v[i] -= __bfloat162float(b);
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * BN));
+  }
+}
+
+// 2-D tensor map over a row-major bf16 matrix [rows, ld] (K contiguous): dims {K, rows}, box {64, 128}, 128-byte swizzle,
+// zero fill outside (K tails and row tails of the last tile read as 0).
+static int encode_kmajor(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return fail(COMET_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled (gemm operand) failed with %d", (int)cr);
+  return COMET_OK;
+}
+
+}  // namespace gemm
+
+// ---- float32 -> bf16 planes (the A operand of a GEMM whose producer is not one of the kernels of this file) -------
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long x_ld, __nv_bfloat16* __restrict__ p0,
+                                                            __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2,
+                                                            long long p_ld, long long rows, int cols, int np) {
+  const long long total = rows * (long long)cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    float v = __ldg(x + r * x_ld + c);
+    const __nv_bfloat16 a = __float2bfloat16_rn(v);
+    p0[r * p_ld + c] = a;
+    if (np > 1) {
+      v -= __bfloat162float(a);
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      p1[r * p_ld + c] = b;
+      v -= __bfloat162float(b);
+      p2[r * p_ld + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+}  // namespace comet
+
+using namespace comet;
+
+extern "C" int comet_split_planes_f32(const float* x, long long x_ld, void* planes, long long plane_stride, long long p_ld,
+                                      long long rows, int cols, int np, comet_stream_t stream) {
+  COMET_REQUIRE(rows >= 0 && cols >= 0 && (np == 1 || np == 3), "bad shape (rows=%lld cols=%d np=%d)", rows, cols, np);
+  if (rows * cols == 0) return COMET_OK;
+  COMET_REQUIRE(x && planes, "null pointer");
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(planes);
+  long long blocks = (rows * cols + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  split_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, p, p + plane_stride, p + 2 * plane_stride, p_ld,
+                                                                          rows, cols, np);
+  return launch_status("split_planes_kernel");
+}
+
+// x planes: np bf16 matrices [M, x_ld] spaced x_plane_stride elements apart; w planes likewise [N, w_ld].
+// out (float32, optional), out planes (bf16, optional, out_np in {0, 1, 3}), bias [N] / resid [M, resid_ld] optional.
+extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, long long x_ld, const void* w_planes,
+                               long long w_plane_stride, long long w_ld, int np, const float* bias, const float* resid,
+                               long long resid_ld, float* out, long long out_ld, void* out_planes,
+                               long long out_plane_stride, long long outp_ld, int out_np, int gelu, long long M, int N, int K,
+                               comet_stream_t stream) {
+  COMET_REQUIRE(np == 1 || np == 3, "np must be 1 or 3 (got %d)", np);
+  COMET_REQUIRE(out_np == 0 || out_np == 1 || out_np == 3, "out_np must be 0, 1 or 3 (got %d)", out_np);
+  COMET_REQUIRE(M >= 0 && N >= 1 && K >= 1 && M < (1LL << 31), "bad shape (M=%lld N=%d K=%d)", M, N, K);
+  if (M == 0) return COMET_OK;
+  COMET_REQUIRE(x_planes && w_planes && (out || (out_planes && out_np > 0)), "null pointer");
+  COMET_REQUIRE(x_ld % 8 == 0 && w_ld % 8 == 0 && ((uintptr_t)x_planes % 16) == 0 && ((uintptr_t)w_planes % 16) == 0 &&
+                    x_plane_stride % 8 == 0 && w_plane_stride % 8 == 0,
+                "operand planes must be 16-byte aligned with row pitches that are multiples of 8 elements");
+  const int sms = device_sm_count_if_sm100();
+  if (!sms || !tensor_map_encoder()) return fail(COMET_ERR_UNSUPPORTED, "comet_linear_tc needs an sm_100 device with TMA descriptors");
+  gemm::Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x_planes);
+  const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w_planes);
+  for (int i = 0; i < np; ++i) {
+    int rc = gemm::encode_kmajor(&maps.a[i], xp + i * x_plane_stride, M, K, x_ld);
+    if (rc != COMET_OK) return rc;
+    rc = gemm::encode_kmajor(&maps.w[i], wp + i * w_plane_stride, N, K, w_ld);
+    if (rc != COMET_OK) return rc;
+  }
+  gemm::Params p{};
+  p.M = (int)M; p.N = N; p.K = K; p.np = np;
+  p.nstage = gemm::SMEM_BUDGET / (np * 2 * gemm::TILE_BYTES);
+  if (p.nstage > 8) p.nstage = 8;
+  p.tiles_m = (int)((M + gemm::BM - 1) / gemm::BM);
+  p.tiles_n = (N + gemm::BN - 1) / gemm::BN;
+  p.ktiles = (K + gemm::BK - 1) / gemm::BK;
+  p.bias = bias; p.resid = resid; p.resid_ld = resid_ld; p.out = out; p.out_ld = out_ld;
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out_planes);
+  for (int i = 0; i < out_np; ++i) p.outp[i] = op + i * out_plane_stride;
+  p.outp_ld = outp_ld; p.out_np = out_planes ? out_np : 0; p.gelu = gelu;
+  const int smem = p.nstage * np * 2 * gemm::TILE_BYTES + (2 * p.nstage + 4) * 8 + 16;
+  COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long ntiles = (long long)p.tiles_m * p.tiles_n;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  gemm::gemm_tc_kernel<<<grid, gemm::THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  return launch_status("gemm_tc_kernel");
+}

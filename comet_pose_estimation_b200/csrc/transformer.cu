@@ -1,0 +1,280 @@
+// Row-wise pieces of the track-update transformer between the tensor-core GEMMs of gemm_tc.cu
+// (EfficientUpdateFormer, comet/models/track_modules/blocks.py:298-348; AttnBlock / CrossAttnBlock,
+// comet/models/modules.py:248-344):
+//
+//   layernorm_planes_kernel   nn.LayerNorm over the last dimension (with or without affine), result written as float32
+//                             (the reference's blocks add the attention output to the NORMALISED input, so it is needed
+//                             as a residual) and / or as bf16 planes = the A operand of the next GEMM;
+//   attention_kernel          softmax(q k^T / sqrt(dh)) v per (batch item, head) of nn.MultiheadAttention for the short
+//                             sequences of this model: T = 16 frames (time blocks), 64 virtual tracks x N point tracks
+//                             (space blocks).  Arbitrary batch / position strides, so neither the "(b n) t c" nor the
+//                             "(b t) n c" rearrangement of the reference is ever materialised; float32 arithmetic on the
+//                             CUDA cores (0.2 - 0.8 GFLOP per block: not tensor-core work); output directly as bf16
+//                             planes for the out-projection GEMM.
+#include "comet_common.cuh"
+
+namespace comet {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// store v as np bf16 planes at index idx of planes p0 + k * plane_stride
+__device__ __forceinline__ void store_planes(__nv_bfloat16* p0, long long plane_stride, long long idx, float v, int np) {
+  for (int k = 0; k < np; ++k) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    p0[k * plane_stride + idx] = b;
+    v -= __bfloat162float(b);
+  }
+}
+
+// One warp per row; D <= 32 * KPL (KPL values per lane, compile time).
+constexpr int LN_MAX_PER_LANE = 32;
+template <int KPL>
+__global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __restrict__ x, long long x_ld,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float eps, float* __restrict__ out, long long out_ld,
+                                                                __nv_bfloat16* __restrict__ planes, long long plane_stride,
+                                                                long long p_ld, int np, long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + r * x_ld;
+    float v[KPL];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = c < D ? __ldg(xr + c) : 0.f;
+      s += v[k];
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int c = lane + 32 * k;
+      const float d = c < D ? v[k] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int c = lane + 32 * k;
+      if (c < D) {
+        float y = (v[k] - mean) * rstd;
+        if (gamma) y = y * __ldg(gamma + c) + __ldg(beta + c);
+        if (out) out[r * out_ld + c] = y;
+        if (planes) store_planes(planes, plane_stride, r * p_ld + c, y, np);
+      }
+    }
+  }
+}
+
+// q/k/v element (batch b, position i, head h, dim d) at ptr + b * sb + i * si + h * dh + d  (float32).
+// One warp per (batch, head, query position); scores of a query live in shared memory (Lk floats per warp).
+struct AttnParams {
+  const float* q; long long q_sb, q_si;
+  const float* k; long long k_sb, k_si;
+  const float* v; long long v_sb, v_si;
+  __nv_bfloat16* out; long long o_plane_stride, o_sb, o_si;   // planes, element (b, i, h*dh + d) at b*o_sb + i*o_si + ...
+  int np;
+  int B, H, Lq, Lk, dh;
+  float scale;
+};
+// One CTA per (batch item, head, chunk of ATT_QB queries): the query chunk and one tile of ATT_KT keys / values are staged
+// in shared memory (coalesced 128-bit loads, rows padded by 4 floats so that lanes <-> keys read conflict-free
+// LDS.128), every warp walks its queries over the tile with an online softmax (running max / sum / output, rescaled per
+// tile), so K and V are read from L2 once per CTA instead of once per query (the first version of this kernel did the
+// latter and was L2-bound: 215 us per launch on the 64 x 512 space attention, 4.5 of the 8 ms of a coarse forward).
+constexpr int ATT_QB = 64, ATT_KT = 64, ATT_WARPS = 8;
+template <int DH4>   // dh / 4 (dh <= 4 * DH4)
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnParams p) {
+  constexpr int DH = 4 * DH4, KLD = DH + 4;
+  constexpr int QPW = ATT_QB / ATT_WARPS;   // queries per warp
+  extern __shared__ __align__(16) float att_smem[];
+  float* const Qs = att_smem;                       // [ATT_QB][DH]
+  float* const Ks = Qs + ATT_QB * DH;               // [ATT_KT][KLD]
+  float* const Vs = Ks + ATT_KT * KLD;              // [ATT_KT][DH]
+  float (*Ps)[ATT_KT] = reinterpret_cast<float (*)[ATT_KT]>(Vs + ATT_KT * DH);   // [ATT_WARPS][ATT_KT], 16-byte aligned rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qchunks = (p.Lq + ATT_QB - 1) / ATT_QB;
+  const long long nblocks = (long long)p.B * p.H * qchunks;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int qc = (int)(blk % qchunks);
+    const int h = (int)((blk / qchunks) % p.H);
+    const int b = (int)(blk / ((long long)qchunks * p.H));
+    const int q0 = qc * ATT_QB, nq = min(ATT_QB, p.Lq - q0);
+    const float* qp = p.q + b * p.q_sb + h * p.dh;
+    const float* kp = p.k + b * p.k_sb + h * p.dh;
+    const float* vp = p.v + b * p.v_sb + h * p.dh;
+    const int dh4 = p.dh >> 2;
+    __syncthreads();                       // previous chunk fully consumed
+    for (int e = threadIdx.x; e < nq * DH4; e += blockDim.x) {
+      const int r = e / DH4, t = e - r * DH4;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < dh4) g = __ldg(reinterpret_cast<const float4*>(qp + (long long)(q0 + r) * p.q_si) + t);
+      g.x *= p.scale; g.y *= p.scale; g.z *= p.scale; g.w *= p.scale;     // MHA scales q before q k^T
+      reinterpret_cast<float4*>(Qs)[r * DH4 + t] = g;
+    }
+    float m[QPW], l[QPW], acc0[QPW], acc1[QPW];
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) { m[u] = -INFINITY; l[u] = 0.f; acc0[u] = 0.f; acc1[u] = 0.f; }
+
+    for (int k0 = 0; k0 < p.Lk; k0 += ATT_KT) {
+      const int nk = min(ATT_KT, p.Lk - k0);
+      __syncthreads();                     // Q staged / previous tile consumed
+      for (int e = threadIdx.x; e < ATT_KT * DH4; e += blockDim.x) {
+        const int r = e / DH4, t = e - r * DH4;
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (r < nk && t < dh4) {
+          kk = __ldg(reinterpret_cast<const float4*>(kp + (long long)(k0 + r) * p.k_si) + t);
+          vv = __ldg(reinterpret_cast<const float4*>(vp + (long long)(k0 + r) * p.v_si) + t);
+        }
+        *reinterpret_cast<float4*>(Ks + r * KLD + 4 * t) = kk;
+        *reinterpret_cast<float4*>(Vs + r * DH + 4 * t) = vv;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < QPW; ++u) {
+        const int qi = u * ATT_WARPS + warp;     // warp-uniform; interleaved so that short chunks still use every warp
+        if (qi >= nq) break;
+        // scores of keys lane and lane + 32
+        float s0 = 0.f, s1 = 0.f;
+        const float4* qr = reinterpret_cast<const float4*>(Qs + qi * DH);
+        const float4* ka = reinterpret_cast<const float4*>(Ks + lane * KLD);
+        const float4* kb = reinterpret_cast<const float4*>(Ks + (lane + 32) * KLD);
+#pragma unroll
+        for (int t = 0; t < DH4; ++t) {
+          const float4 qv = qr[t], x = ka[t], y = kb[t];
+          s0 = fmaf(qv.x, x.x, s0); s0 = fmaf(qv.y, x.y, s0); s0 = fmaf(qv.z, x.z, s0); s0 = fmaf(qv.w, x.w, s0);
+          s1 = fmaf(qv.x, y.x, s1); s1 = fmaf(qv.y, y.y, s1); s1 = fmaf(qv.z, y.z, s1); s1 = fmaf(qv.w, y.w, s1);
+        }
+        if (lane >= nk) s0 = -INFINITY;
+        if (lane + 32 >= nk) s1 = -INFINITY;
+        const float mn = fmaxf(m[u], warp_max(fmaxf(s0, s1)));
+        const float e0 = expf(s0 - mn), e1 = expf(s1 - mn);      // exp(-inf) = 0 for the padded keys
+        const float corr = expf(m[u] - mn);                       // 0 on the first tile (m = -inf)
+        l[u] = l[u] * corr + warp_sum(e0 + e1);
+        m[u] = mn;
+        __syncwarp();
+        Ps[warp][lane] = e0;
+        Ps[warp][lane + 32] = e1;
+        __syncwarp();
+        // output dims lane and lane + 32: V rows read conflict-free, probabilities broadcast
+        float a0 = acc0[u] * corr, a1 = acc1[u] * corr;
+        const bool two = DH > 32;
+        const int nk4 = (nk + 3) & ~3;          // padded keys carry probability 0 and zero V rows
+        const float* v0 = Vs + (lane < DH ? lane : 0);
+        const float* v1 = Vs + (lane + 32 < DH ? lane + 32 : 0);
+#pragma unroll 2
+        for (int j = 0; j < nk4; j += 4) {
+          const float4 pj = *reinterpret_cast<const float4*>(&Ps[warp][j]);
+          a0 = fmaf(pj.x, v0[j * DH], a0); a0 = fmaf(pj.y, v0[(j + 1) * DH], a0);
+          a0 = fmaf(pj.z, v0[(j + 2) * DH], a0); a0 = fmaf(pj.w, v0[(j + 3) * DH], a0);
+          if (two) {
+            a1 = fmaf(pj.x, v1[j * DH], a1); a1 = fmaf(pj.y, v1[(j + 1) * DH], a1);
+            a1 = fmaf(pj.z, v1[(j + 2) * DH], a1); a1 = fmaf(pj.w, v1[(j + 3) * DH], a1);
+          }
+        }
+        acc0[u] = a0; acc1[u] = a1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+      const int qi = u * ATT_WARPS + warp;
+      if (qi >= nq) break;
+      const float inv = 1.f / l[u];
+      const long long base = b * p.o_sb + (long long)(q0 + qi) * p.o_si + h * p.dh;
+      if (lane < p.dh) store_planes(p.out, p.o_plane_stride, base + lane, acc0[u] * inv, p.np);
+      if (lane + 32 < p.dh) store_planes(p.out, p.o_plane_stride, base + lane + 32, acc1[u] * inv, p.np);
+    }
+  }
+}
+
+// y = a + b (elementwise, float32, contiguous) -- the "tokens + init_tokens" before the flow head, written as planes
+__global__ void __launch_bounds__(256) add_planes_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          __nv_bfloat16* __restrict__ planes, long long plane_stride, int np,
+                                                          long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    store_planes(planes, plane_stride, i, __ldg(a + i) + __ldg(b + i), np);
+}
+
+}  // namespace comet
+
+using namespace comet;
+
+extern "C" int comet_layernorm_planes_f32(const float* x, long long x_ld, const float* gamma, const float* beta, float eps,
+                                          float* out, long long out_ld, void* planes, long long plane_stride, long long p_ld,
+                                          int np, long long rows, int D, comet_stream_t stream) {
+  COMET_REQUIRE(rows >= 0 && D >= 1 && D <= 32 * LN_MAX_PER_LANE, "LayerNorm width %d outside [1, %d]", D, 32 * LN_MAX_PER_LANE);
+  COMET_REQUIRE(np == 0 || np == 1 || np == 3, "np must be 0, 1 or 3");
+  COMET_REQUIRE((gamma == nullptr) == (beta == nullptr), "gamma and beta must be given together");
+  if (rows == 0) return COMET_OK;
+  COMET_REQUIRE(x && (out || (planes && np > 0)), "null pointer");
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  __nv_bfloat16* pl = np > 0 ? reinterpret_cast<__nv_bfloat16*>(planes) : nullptr;
+#define COMET_LN_LAUNCH(KPL)                                                                                        \
+  layernorm_planes_kernel<KPL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, gamma, beta, eps, out, out_ld, pl, \
+                                                                                  plane_stride, p_ld, np, rows, D)
+  if (D <= 32) COMET_LN_LAUNCH(1);
+  else if (D <= 128) COMET_LN_LAUNCH(4);
+  else if (D <= 256) COMET_LN_LAUNCH(8);
+  else if (D <= 384) COMET_LN_LAUNCH(12);
+  else if (D <= 512) COMET_LN_LAUNCH(16);
+  else COMET_LN_LAUNCH(32);
+#undef COMET_LN_LAUNCH
+  return launch_status("layernorm_planes_kernel");
+}
+
+extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long long q_si, const float* k, long long k_sb,
+                                          long long k_si, const float* v, long long v_sb, long long v_si, void* out_planes,
+                                          long long o_plane_stride, long long o_sb, long long o_si, int np, int B, int H,
+                                          int Lq, int Lk, int dh, comet_stream_t stream) {
+  COMET_REQUIRE(B >= 0 && H >= 1 && Lq >= 0 && Lk >= 1 && dh >= 4 && dh <= 64 && dh % 4 == 0,
+                "bad attention shape (B=%d H=%d Lq=%d Lk=%d dh=%d)", B, H, Lq, Lk, dh);
+  COMET_REQUIRE(np == 1 || np == 3, "np must be 1 or 3");
+  const long long total = (long long)B * H * Lq;
+  if (total == 0) return COMET_OK;
+  COMET_REQUIRE(q && k && v && out_planes, "null pointer");
+  COMET_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && q_sb % 4 == 0 && q_si % 4 == 0 && k_sb % 4 == 0 &&
+                    k_si % 4 == 0, "q / k rows must be 16-byte aligned");
+  COMET_REQUIRE(((uintptr_t)v % 16) == 0 && v_sb % 4 == 0 && v_si % 4 == 0, "v rows must be 16-byte aligned");
+  AttnParams p{q, q_sb, q_si, k, k_sb, k_si, v, v_sb, v_si, reinterpret_cast<__nv_bfloat16*>(out_planes),
+               o_plane_stride, o_sb, o_si, np, B, H, Lq, Lk, dh, 1.0f / sqrtf((float)dh)};
+  long long blocks = (long long)B * H * ((Lq + ATT_QB - 1) / ATT_QB);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+#define COMET_ATTN_LAUNCH(D4)                                                                                       \
+  do {                                                                                                              \
+    const int smem = (ATT_QB * 4 * D4 + ATT_KT * (4 * D4 + 4) + ATT_KT * 4 * D4 + ATT_WARPS * ATT_KT) * (int)sizeof(float); \
+    if (smem > 48 * 1024)                                                                                           \
+      COMET_CUDA(cudaFuncSetAttribute(attention_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+    attention_kernel<D4><<<(unsigned)blocks, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);                      \
+  } while (0)
+  if (dh <= 4) COMET_ATTN_LAUNCH(1);
+  else if (dh <= 16) COMET_ATTN_LAUNCH(4);
+  else if (dh <= 32) COMET_ATTN_LAUNCH(8);
+  else if (dh <= 48) COMET_ATTN_LAUNCH(12);
+  else COMET_ATTN_LAUNCH(16);
+#undef COMET_ATTN_LAUNCH
+  return launch_status("attention_kernel");
+}
+
+extern "C" int comet_add_planes_f32(const float* a, const float* b, void* planes, long long plane_stride, int np, long long n,
+                                    comet_stream_t stream) {
+  COMET_REQUIRE(n >= 0 && (np == 1 || np == 3), "bad arguments");
+  if (n == 0) return COMET_OK;
+  COMET_REQUIRE(a && b && planes, "null pointer");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  add_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, b, reinterpret_cast<__nv_bfloat16*>(planes), plane_stride, np, n);
+  return launch_status("add_planes_kernel");
+}

@@ -1,11 +1,11 @@
-"""Track-update transformer used between hot-path iterations.
+"""Track-update transformer used between hot-path iterations (SURVEY.md 8f, rank 1).
 
-This is *host plumbing*, not a kernel: plain ``torch.nn`` modules whose parameter names and arithmetic mirror the
-reference's ``EfficientUpdateFormer`` (comet/models/track_modules/blocks.py:205-348) and its attention blocks
-(comet/models/modules.py:248-344) so that reference checkpoints (``track_predictor.*.updateformer.*`` keys) load
-unchanged.  Inside the reference tree the drop-in predictor can equally be handed the reference's own class; this
-implementation exists so that the package is self-contained and the parity tests can run the full refinement loop.
-It is SURVEY.md 8(f) "next" item 1 for kernel work.
+``EfficientUpdateFormer`` owns the parameters under the reference's names (comet/models/track_modules/blocks.py:205-348,
+attention blocks comet/models/modules.py:248-344), so reference checkpoints (``track_predictor.*.updateformer.*`` keys)
+load unchanged.  CUDA inference runs on this package's own sm_100a kernels (:mod:`.update_former_tc`: tcgen05 GEMMs
+with fused bias / GELU / residual epilogues, LayerNorm and attention kernels); the plain ``torch.nn`` forward below is
+the definition those kernels are tested against, and what runs on CPU tensors (host-logic tests), under autograd, and
+for shapes the kernels do not serve (head_dim not a multiple of 4).
 
 Quirks preserved (they change numerics): both block types add the attention output to the *normalised* input
 (``x = norm1(x); x = x + attn(x)``), the virtual-track parameter is spelled ``virual_tracks``, and the initial
@@ -15,6 +15,9 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+
+# False keeps CUDA inference on the torch.nn forward as well (A/B timing in bench.py, parity tests)
+USE_TC_KERNELS = True
 
 
 class _FeedForward(nn.Module):
@@ -91,6 +94,15 @@ class EfficientUpdateFormer(nn.Module):
             assert len(self.time_blocks) >= len(self.space_virtual2point_blocks)
 
     def forward(self, input_tensor, mask=None):
+        if (USE_TC_KERNELS and mask is None and input_tensor.is_cuda and not torch.is_grad_enabled()):
+            from . import update_former_tc as tc
+
+            if tc.supported(self, input_tensor):
+                autocast = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+                return tc.forward(self, input_tensor.float(), 1 if autocast else 3)
+        return self._forward_torch(input_tensor, mask)
+
+    def _forward_torch(self, input_tensor, mask=None):
         tokens = self.input_transform(input_tensor)
         skip = tokens
         B, _, T, _ = tokens.shape

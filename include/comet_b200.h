@@ -214,6 +214,37 @@ int comet_tc_corr_volume_f32(const void* split, const float* targets, long long 
  * kernel trapped and the CUDA context is lost): which wait it was.  Synchronises with the device. */
 int comet_tc_status(void);
 
+/* ---- track-update transformer: EfficientUpdateFormer (comet/models/track_modules/blocks.py:205-348) and its
+ *      AttnBlock / CrossAttnBlock / Mlp (comet/models/modules.py:119-154, :248-344) --------------------------------------
+ * Activations that feed a GEMM are held as "bf16 planes": np bf16 matrices p0 = bf16(x), p1 = bf16(x - p0),
+ * p2 = bf16(x - p0 - p1), spaced plane_stride ELEMENTS apart.  np = 1 is torch.autocast(bf16) precision (COMET's shipped
+ * mixed_precision), np = 3 is float32-grade (six tensor-core passes over the plane pairs i + j <= 2). */
+/* x (rows, cols) float32 with row pitch x_ld -> np planes with row pitch p_ld. */
+int comet_split_planes_f32(const float* x, long long x_ld, void* planes, long long plane_stride, long long p_ld,
+                           long long rows, int cols, int np, comet_stream_t stream);
+/* nn.Linear on tcgen05: Y[M,N] = act(X[M,K] . W[N,K]^T + bias) (+ resid).  X / W as np planes (row pitches x_ld / w_ld
+ * elements, multiples of 8); result as float32 `out` (may be NULL) and / or out_np planes (out_np = 0: none);
+ * gelu != 0 applies the exact (erf) GELU before the residual is added.  bias, resid may be NULL. */
+int comet_linear_tc(const void* x_planes, long long x_plane_stride, long long x_ld, const void* w_planes,
+                    long long w_plane_stride, long long w_ld, int np, const float* bias, const float* resid,
+                    long long resid_ld, float* out, long long out_ld, void* out_planes, long long out_plane_stride,
+                    long long outp_ld, int out_np, int gelu, long long M, int N, int K, comet_stream_t stream);
+/* nn.LayerNorm over the last dimension (gamma / beta NULL: elementwise_affine=False), written as float32 `out` (may be
+ * NULL) and / or np planes (np = 0: none). */
+int comet_layernorm_planes_f32(const float* x, long long x_ld, const float* gamma, const float* beta, float eps, float* out,
+                               long long out_ld, void* planes, long long plane_stride, long long p_ld, int np,
+                               long long rows, int D, comet_stream_t stream);
+/* softmax(q k^T / sqrt(dh)) v of nn.MultiheadAttention per (batch item, head); element (b, i, h, d) of q / k / v at
+ * ptr + b*sb + i*si + h*dh + d (float32; any batch / position strides: no rearrange copies); output as np planes with
+ * element (b, i, h*dh + d) at b*o_sb + i*o_si + h*dh + d. */
+int comet_attention_planes_f32(const float* q, long long q_sb, long long q_si, const float* k, long long k_sb, long long k_si,
+                               const float* v, long long v_sb, long long v_si, void* out_planes, long long o_plane_stride,
+                               long long o_sb, long long o_si, int np, int B, int H, int Lq, int Lk, int dh,
+                               comet_stream_t stream);
+/* planes of a + b (contiguous float32 vectors of n elements): `tokens + init_tokens` before the flow head (blocks.py:344). */
+int comet_add_planes_f32(const float* a, const float* b, void* planes, long long plane_stride, int np, long long n,
+                         comet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
