@@ -287,6 +287,52 @@ def cpu_reference_seq_per_s(torch, reps):
     return 1.0 / min(times), statistics.mean(times), ncores
 
 
+TRACKER = dict(coarse=dict(stride=4, corr_levels=5, corr_radius=4, latent_dim=128, hidden_size=384, depth=6, use_spaceatt=True, fine=False),
+               fine=dict(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=256, depth=4, use_spaceatt=False, fine=True))
+
+
+def cpu_tracker_loop_s(torch, reps=1):
+    """CPU baseline scope (ii) of BASELINE.md section 4: coarse (4 it) + fine (6 it) tracker loops of ONE sequence WITH the
+    update transformer -- hot path through oracle/torch_port.py (the reference's ATen calls), transformer and state update
+    through torch.nn on the host cores (the same module definition the reference uses, update_former._forward_torch)."""
+    from oracle import torch_port as P
+    import importlib
+
+    uf = importlib.import_module("comet_pose_estimation_b200.update_former")
+    torch.manual_seed(0)
+    d = make_inputs(1, 4321, torch, pin=False, fine_layout="nchw")
+    mods = {}
+    for name, cfg in (("coarse", COARSE), ("fine", FINE)):
+        t = TRACKER[name]
+        td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
+        mods[name] = (uf.EfficientUpdateFormer(space_depth=t["depth"] if t["use_spaceatt"] else 0, time_depth=t["depth"], input_dim=td,
+                                               hidden_size=t["hidden_size"], output_dim=t["latent_dim"] + 2,
+                                               add_space_attn=t["use_spaceatt"]).eval(),
+                      torch.nn.GroupNorm(1, t["latent_dim"]), torch.nn.Sequential(torch.nn.Linear(t["latent_dim"], t["latent_dim"]), torch.nn.GELU()))
+    best = None
+    with torch.no_grad():
+        for rep in range(reps + 1):
+            t0 = time.perf_counter()
+            for name, cfg in (("coarse", COARSE), ("fine", FINE)):
+                x = d[name]
+                former, norm, upd = mods[name]
+                td = tdim(cfg["L"], cfg["r"], cfg["C"], cfg["fine"])
+                lv = P.pyramid(x["fmaps"], cfg["L"])
+                coords, feats = x["coords"][0].clone(), x["feats"][0].clone()
+                B, S, N, C = feats.shape
+                for _ in range(cfg["iters"]):
+                    tok = P.hot_path_iteration(lv, coords, feats, cfg["r"], (cfg["H"], cfg["W"]), td)
+                    delta = former._forward_torch(tok).reshape(B * N, S, C + 2)
+                    f_ = feats.permute(0, 2, 1, 3).reshape(B * N * S, C)
+                    f_ = upd(norm(delta[:, :, 2:].reshape(B * N * S, C))) + f_
+                    feats = f_.reshape(B, N, S, C).permute(0, 2, 1, 3)
+                    coords = coords + delta[:, :, :2].reshape(B, N, S, 2).permute(0, 2, 1, 3) * 0.01
+            dt = time.perf_counter() - t0
+            if rep > 0 or reps == 0:
+                best = dt if best is None else min(best, dt)
+    return best
+
+
 def make_config(Q, world, fine_layout):
     """`config` of the JSON line -- identical in both arms (the workload, not the implementation)."""
     return {"workload": workload_name(Q), "sequences_per_gpu_per_step": Q, "seqlen": 16,
@@ -579,6 +625,50 @@ def main():
                                        "materialises a 5.72 GB volume per iteration here"}
         del fm4, co4, ft4, out4, blk4, tk4
 
+    # ---- the tracker loops WITH the update transformer (outside `value`): drop-in BaseTrackerPredictor,
+    # coarse (hidden 384, depth 6, 4 it, N=512) + fine (hidden 256, depth 4, 6 it, 512 patches on the 16x16 source map) of
+    # ONE sequence, random-init weights; this package's sm_100a transformer kernels vs the torch.nn (cuBLAS / ATen)
+    # definition of the same module, in float32 and under autocast(bf16) ----
+    if not args.no_variants:
+        from types import SimpleNamespace as NS
+        import importlib
+
+        ufm = importlib.import_module("comet_pose_estimation_b200.update_former")
+        tcfg = NS(track_conf=False, MODEL=NS(TRACK=NS(efficient_corr=False)))
+        torch.manual_seed(0)
+        coarse_m = cb.BaseTrackerPredictor(cfg=tcfg, **TRACKER["coarse"]).eval().to(dev)
+        fine_m = cb.BaseTrackerPredictor(cfg=tcfg, **TRACKER["fine"]).eval().to(dev)
+        for mm in (coarse_m, fine_m):                      # small updates, as a trained tracker makes
+            for prm in mm.updateformer.flow_head.parameters():
+                prm.data.mul_(0.05)
+        fm_c = devin["coarse"]["fmaps"][:1]
+        qp_c = devin["coarse"]["coords"][0][:1, 0] * 8.0                      # pixels (stride 4 x down_ratio 2)
+        src_f = devin["fine"]["fmaps"][:FINE["P"]]
+        up_f = cb.Upsampled2x(src_f) if layout == "up2" else src_f
+        qp_f = devin["fine"]["coords"][0][:FINE["P"], 0]
+
+        def tracker_loops():
+            with torch.no_grad():
+                coarse_m(query_points=qp_c, fmaps=fm_c, iters=COARSE["iters"], down_ratio=2, TRACKorPOSE=False)
+                fine_m(query_points=qp_f, fmaps=up_f, iters=FINE["iters"], TRACKorPOSE=False)
+
+        tl = {}
+        for tag, native, bf in (("sm100_kernels_fp32", True, False), ("torch_nn_fp32", False, False),
+                                ("sm100_kernels_autocast_bf16", True, True), ("torch_nn_autocast_bf16", False, True)):
+            ufm.USE_TC_KERNELS = native
+            if bf:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    tl[tag], _ = timed(tracker_loops, 5, 2)
+            else:
+                tl[tag], _ = timed(tracker_loops, 5, 2)
+        ufm.USE_TC_KERNELS = True
+        variants["tracker_loop"] = {"ms_per_sequence": tl,
+                                    "what": "coarse 4 it + fine 6 it of one 16-frame sequence through the drop-in "
+                                            "BaseTrackerPredictor INCLUDING the update transformer and state updates: "
+                                            "transformer on this package's tcgen05 / attention / LayerNorm kernels vs its "
+                                            "torch.nn definition (cuBLAS / ATen); TF32 off for the float32 arms"}
+        del coarse_m, fine_m
+
     # ---- the producer of the fine tracker's input (outside `value`): patch gather + ShallowEncoder for
     # ONE sequence (8192 patches of a 16-frame 512x512 sequence), with the library's resize / instance-norm kernels and
     # with the ATen ops the reference calls (F.interpolate, InstanceNorm2d) ----------------------------------------
@@ -684,6 +774,11 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": ncores, "kind": "port",
                "sample": f"1 sequence x {args.cpu_reps} reps (best), oracle/torch_port.py (reference's ATen calls), "
                          f"fp32, {mean_s:.2f} s/sequence mean"}
+        if not args.no_variants:
+            # BASELINE.md section 4 scope (ii): the tracker loops with the update transformer, one sequence, one rep
+            cpu["tracker_loop_s_per_sequence"] = cpu_tracker_loop_s(torch, reps=1)
+            cpu["tracker_loop_sample"] = ("scope (ii): coarse 4 it + fine 6 it of one sequence incl. the update transformer "
+                                          "(torch.nn on the host cores) and state updates, best of 1 after a warm-up")
 
     if rank == 0:
         config = make_config(Q, world, layout)

@@ -657,6 +657,7 @@ static int fill_params(LookupParams& p, const float* fmaps, const float* pyr, co
   Levels lv = make_levels(B * S, C, H, W, L);
   for (int l = 0; l < L; ++l) { p.lvlH[l] = lv.H[l]; p.lvlW[l] = lv.W[l]; p.lvlOff[l] = lv.off[l]; }
   p.sqrt_c = sqrtf((float)C);
+  p.inv_sqrt_c = 1.0f / p.sqrt_c;
   p.channel_last = pyr_layout != COMET_PYR_NCHW;
   p.cl0 = pyr_layout == COMET_PYR_ALL_CHANNEL_LAST;
   p.pos = nullptr; p.D_tok = 0;

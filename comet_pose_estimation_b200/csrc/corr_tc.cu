@@ -28,6 +28,18 @@
 // row (the window columns are indexed dynamically), horizontal lerp at the query's x window, vertical lerp with the
 // previous row, write the staged window | warps 6-9 stager: every global access -- stage the next job's targets into
 // TMEM (hi/lo split, tcgen05.st), and write the staged windows + position embedding with coalesced stores.
+// The two launches are chained with programmatic dependent launch: the tensor kernel's prologue (barrier init, TMEM
+// allocation) overlaps the drain of tc_pre_kernel and it waits (griddepcontrol.wait) before touching the plan.
+//
+// Measured and rejected in round 2 (scripts/variant_bench.sh, B200, batch of 4 sequences, ms per iteration): EIGHT
+// epilogue warps, two per TMEM lane quarter, each producing half of the window's x entries (no synchronisation between
+// the halves): 0.170 vs 0.118 -- with 14 warps one scheduler hosts 4 of them, which caps the kernel at 128 registers per
+// thread (16384 per scheduler) and spills the epilogue's accumulator row, and a 2-stage operand ring is all that fits
+// beside two sets of private rows.  The stall samples of the 4-warp kernel (profiles/r02_coarse_tc_stalls.md) show why
+// the split does not pay: the epilogue warps spend 21 % of their time WAITING for accumulators -- the MMA warp in turn
+// waits for the target tile of the next job, which the stager warps stage (~5700 clk) only after they have stored the
+// previous job's windows (~6000 clk per level): the roles starve one another in turn rather than one role being the
+// limiter.
 #include "comet_common.cuh"
 
 #include <cuda.h>
@@ -45,6 +57,9 @@ constexpr int NACC = 4;        // accumulator ring (4 x 64 TMEM columns)
 constexpr int P_TOTAL = 5504;  // packed positions per (frame, channel)
 constexpr int NTILES = 86;     // P_TOTAL / TILE_N tiles of 64 positions per frame
 constexpr int MAX_WR = 9;      // 2*4+1
+#ifndef COMET_TC_PDL
+#define COMET_TC_PDL 1
+#endif
 constexpr int THREADS = 320;   // 10 warps: TMA | MMA | 4 epilogue | 4 stager
 
 // tensor-memory map (all 512 columns of the SM are allocated, so the base address is 0)
@@ -432,6 +447,11 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
     const long long nw = (long long)(gridDim.x - p.BS) * 8;
     token_misc_rows(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
   }
+  // programmatic dependent launch: once every CTA of this grid got here the tensor kernel may be scheduled, so its
+  // prologue overlaps this grid's drain; it waits for this grid's completion (griddepcontrol.wait) before it reads
+  // perm / jobs / the token rows.  (Triggering at the START of this kernel instead lets the dependent's 218 KB CTAs occupy
+  // every SM that falls idle and starve the remaining CTAs of this grid.)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -478,6 +498,7 @@ corr_tc_kernel(const Params p) {
     if (threadIdx.x == 0 && p.status) atomicExch(p.status, 9);
     __trap();
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // plan + token rows of tc_pre_kernel are complete and visible
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1092,7 +1113,14 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   do {                                                                                                            \
     COMET_CUDA(cudaFuncSetAttribute(corr_tc_kernel<RR, BF, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                     SMEM_BYTES));                                                                 \
-    corr_tc_kernel<RR, BF, VOL><<<grid, THREADS, SMEM_BYTES, stream>>>(p);                                  \
+    cudaLaunchConfig_t cfg__{};                                                                                   \
+    cfg__.gridDim = dim3(grid); cfg__.blockDim = dim3(THREADS); cfg__.dynamicSmemBytes = SMEM_BYTES;              \
+    cfg__.stream = stream;                                                                                        \
+    cudaLaunchAttribute at__[1];                                                                                  \
+    at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                              \
+    at__[0].val.programmaticStreamSerializationAllowed = COMET_TC_PDL;                                            \
+    cfg__.attrs = at__; cfg__.numAttrs = 1;                                                                       \
+    COMET_CUDA(cudaLaunchKernelEx(&cfg__, corr_tc_kernel<RR, BF, VOL>, p));                                      \
   } while (0)
 #define COMET_TC_LAUNCH_R(RR)                                                                                     \
   do {                                                                                                            \

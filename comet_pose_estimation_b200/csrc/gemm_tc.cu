@@ -5,8 +5,10 @@
 //
 // tcgen05.mma (kind::f16, bf16 operands, float32 accumulation in TMEM), operand tiles staged by TMA (2-D tiled loads,
 // 128-byte swizzle, K-major) through an mbarrier ring, accumulator double-buffered in TMEM so that the epilogue of tile i
-// overlaps the MMAs of tile i+1.  Persistent CTAs (one per SM), 6 warps: TMA producer | MMA issuer (one elected thread) |
-// 4 epilogue warps (TMEM lane quarter = warp % 4).
+// overlaps the MMAs of tile i+1.  Persistent CTAs (one per SM), 10 warps: TMA producer | MMA issuer (one elected thread) |
+// 8 epilogue warps (TMEM lane quarter = warp % 4, two warps per quarter, each owning 64 of the tile's 128 columns: the
+// exact-erf GELU of fc1 costs ~25 instructions per element, and with one warp per quarter the epilogue took twice as long
+// as the tile's MMAs).
 //
 // Precision.  Operands are "bf16 planes": a float32 tensor x is held as NP bf16 tensors p0 = bf16(x), p1 = bf16(x - p0),
 // p2 = bf16(x - p0 - p1).  NP = 1 is what torch.autocast(bf16) gives the reference's nn.Linear (COMET's shipped
@@ -27,7 +29,7 @@ namespace gemm {
 
 constexpr int BM = 128, BN = 128, BK = 64;       // BK bf16 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB (A tile == B tile)
-constexpr int THREADS = 192;                     // 6 warps
+constexpr int THREADS = 320;                     // 10 warps: TMA | MMA | 8 epilogue
 constexpr int MAX_NP = 3;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -233,8 +235,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     const int wq = warp & 3;                        // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;              // which 64 columns of the tile this warp owns
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
     uint32_t acc = 0, acc_phase = 0;
     const bool vec_out = p.out && (p.out_ld % 4 == 0) && (((uintptr_t)p.out) % 16 == 0);
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       mbar_wait(&acc_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
         const int n0 = nb * BN + 32 * c;
         if (n0 >= p.N) break;                      // warp-uniform
         float v[32];

@@ -27,6 +27,7 @@ struct LookupParams {
   int channel_last;  // levels >= 1 stored (BS, H_l, W_l, C) instead of (BS, C, H_l, W_l)
   int cl0;           // level 0 (the caller's fmaps) is channel-last too
   float sqrt_c;
+  float inv_sqrt_c;
 };
 
 namespace tma {
