@@ -27,7 +27,8 @@
 namespace comet {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 64;       // BK bf16 = one 128-byte swizzle row
+constexpr int BM = 128, BN = 128, BK = 64;       // BN: widest tile (TMEM spacing); the tile actually used is Params::bn
+                                                 // BK bf16 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB (A tile == B tile)
 constexpr int THREADS = 320;                     // 10 warps: TMA | MMA | 8 epilogue
 constexpr int MAX_NP = 3;
@@ -35,7 +36,7 @@ constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct Maps {
   CUtensorMap a[MAX_NP];   // X planes: {K, M} bf16, box {64, 128}
-  CUtensorMap w[MAX_NP];   // W planes: {K, N} bf16, box {64, 128}
+  CUtensorMap w[MAX_NP];   // W planes: {K, N} bf16, box {64, bn}
 };
 
 struct Params {
@@ -43,6 +44,7 @@ struct Params {
   int np;                  // planes per operand (1 or 3)
   int nstage;              // ring depth: nstage * np * 32 KB <= SMEM_BUDGET
   int tiles_m, tiles_n, ktiles;
+  int bn;                  // output tile width: 128, or 64 / 32 when 128 would leave most SMs without a tile (small M)
   const float* bias;       // [N] or null
   const float* resid;      // [M, resid_ld] float32 or null (added after the activation)
   long long resid_ld;
@@ -126,9 +128,8 @@ __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D f32, A/B bf16, both K-major, M=128, N=BN
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D f32, A/B bf16, both K-major, M=128; N = Params::bn goes to bits 17-22 at run time
+constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -145,11 +146,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// Same function with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the special-function unit: used when the
+// result is rounded to ONE bf16 plane anyway (autocast mode), where the epilogue, not the tensor pipe, bounds the fc1
+// GEMM (ncu r02: tensor pipe 13 %, issue slots 50 % busy with erff's ~25 instructions per element).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int stage_bytes = p.np * 2 * TILE_BYTES;           // [A planes][B planes]
+  const int b_tile_bytes = p.bn * BK * 2;
+  const int stage_bytes = p.np * (TILE_BYTES + b_tile_bytes);   // [A planes][B planes]
+  const uint32_t idesc = IDESC_BASE | ((uint32_t)(p.bn >> 3) << 17);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * stage_bytes);
   uint64_t* full = bars;                 // [nstage]  TMA -> MMA
   uint64_t* empty = full + p.nstage;     // [nstage]  MMA -> TMA
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
           for (int i = 0; i < p.np; ++i) {
             tma_load_2d(&maps.a[i], &full[stage], dst + i * TILE_BYTES, kb * BK, mb * BM);
-            tma_load_2d(&maps.w[i], &full[stage], dst + (p.np + i) * TILE_BYTES, kb * BK, nb * BN);
+            tma_load_2d(&maps.w[i], &full[stage], dst + p.np * TILE_BYTES + i * b_tile_bytes, kb * BK, nb * p.bn);
           }
           if (++stage == (uint32_t)p.nstage) { stage = 0; phase ^= 1; }
         }
@@ -210,17 +226,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           for (int sum = p.np - 1; sum >= 0; --sum) {
             for (int i = 0; i <= sum; ++i) {
               const int j = sum - i;
-              const uint64_t ad = make_desc_kmajor(a0 + i * TILE_BYTES), bd = make_desc_kmajor(b0 + j * TILE_BYTES);
+              const uint64_t ad = make_desc_kmajor(a0 + i * TILE_BYTES), bd = make_desc_kmajor(b0 + j * b_tile_bytes);
               if (sum == 0) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                  umma_bf16_ss(d_main, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, accum_main);   // +32 bytes per K=16
+                  umma_bf16_ss(d_main, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum_main);   // +32 bytes per K=16
                   accum_main = 1;
                 }
               } else {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                  umma_bf16_ss(d_low, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, accum_low);
+                  umma_bf16_ss(d_low, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum_low);
                   accum_low = 1;
                 }
               }
@@ -249,8 +265,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       mbar_wait(&acc_full[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 2 * chalf; c < 2 * chalf + 2; ++c) {
-        const int n0 = nb * BN + 32 * c;
+      const int cph = p.bn >= 64 ? p.bn / 64 : 1;      // 32-column chunks per epilogue half
+      for (int c = cph * chalf; c < cph * (chalf + 1) && 32 * c < p.bn; ++c) {
+        const int n0 = nb * p.bn + 32 * c;
         if (n0 >= p.N) break;                      // warp-uniform
         float v[32];
         tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + 32 * c, v);
@@ -270,8 +287,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             for (int i = 0; i < 32; ++i) v[i] += (full_chunk || n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
           }
           if (p.gelu) {
+            if (p.np == 1 && !p.out) {     // autocast mode, planes-only output (fc1): bf16 rounding dominates
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
           }
           if (p.resid) {
             const float* r = p.resid + (long long)m * p.resid_ld + n0;
@@ -339,12 +361,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 
 // 2-D tensor map over a row-major bf16 matrix [rows, ld] (K contiguous): dims {K, rows}, box {64, 128}, 128-byte swizzle,
 // zero fill outside (K tails and row tails of the last tile read as 0).
-static int encode_kmajor(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld) {
+static int encode_kmajor(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc) return fail(COMET_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -414,24 +436,29 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
   memset(&maps, 0, sizeof(maps));
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x_planes);
   const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(w_planes);
-  for (int i = 0; i < np; ++i) {
-    int rc = gemm::encode_kmajor(&maps.a[i], xp + i * x_plane_stride, M, K, x_ld);
-    if (rc != COMET_OK) return rc;
-    rc = gemm::encode_kmajor(&maps.w[i], wp + i * w_plane_stride, N, K, w_ld);
-    if (rc != COMET_OK) return rc;
-  }
   gemm::Params p{};
   p.M = (int)M; p.N = N; p.K = K; p.np = np;
-  p.nstage = gemm::SMEM_BUDGET / (np * 2 * gemm::TILE_BYTES);
-  if (p.nstage > 8) p.nstage = 8;
   p.tiles_m = (int)((M + gemm::BM - 1) / gemm::BM);
-  p.tiles_n = (N + gemm::BN - 1) / gemm::BN;
+  // output tile width: 128 unless that leaves most SMs without a tile (the virtual-track GEMMs have M = 1024 rows: 24
+  // tiles of 128x128 on 148 SMs, each MMA-bound for its whole K -- measured 27.6 us against 7 us of work per SM)
+  p.bn = 128;
+  while (p.bn > 32 && (long long)p.tiles_m * ((N + p.bn - 1) / p.bn) * 10 < 7LL * sms) p.bn >>= 1;
+  for (int i = 0; i < np; ++i) {
+    int rc = gemm::encode_kmajor(&maps.a[i], xp + i * x_plane_stride, M, K, x_ld, gemm::BM);
+    if (rc != COMET_OK) return rc;
+    rc = gemm::encode_kmajor(&maps.w[i], wp + i * w_plane_stride, N, K, w_ld, p.bn);
+    if (rc != COMET_OK) return rc;
+  }
+  const int stage_bytes = np * (gemm::TILE_BYTES + p.bn * gemm::BK * 2);
+  p.nstage = gemm::SMEM_BUDGET / stage_bytes;
+  if (p.nstage > 8) p.nstage = 8;
+  p.tiles_n = (N + p.bn - 1) / p.bn;
   p.ktiles = (K + gemm::BK - 1) / gemm::BK;
   p.bias = bias; p.resid = resid; p.resid_ld = resid_ld; p.out = out; p.out_ld = out_ld;
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out_planes);
   for (int i = 0; i < out_np; ++i) p.outp[i] = op + i * out_plane_stride;
   p.outp_ld = outp_ld; p.out_np = out_planes ? out_np : 0; p.gelu = gelu;
-  const int smem = p.nstage * np * 2 * gemm::TILE_BYTES + (2 * p.nstage + 4) * 8 + 16;
+  const int smem = p.nstage * stage_bytes + (2 * p.nstage + 4) * 8 + 16;
   COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long ntiles = (long long)p.tiles_m * p.tiles_n;
   const int grid = (int)(ntiles < sms ? ntiles : sms);

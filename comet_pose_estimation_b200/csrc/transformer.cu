@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnPar
   float* const Qs = att_smem;                       // [ATT_QB][DH]
   float* const Ks = Qs + ATT_QB * DH;               // [ATT_KT][KLD]
   float* const Vs = Ks + ATT_KT * KLD;              // [ATT_KT][DH]
-  float (*Ps)[ATT_KT] = reinterpret_cast<float (*)[ATT_KT]>(Vs + ATT_KT * DH);   // [ATT_WARPS][ATT_KT], 16-byte aligned rows
+  float (*Ps)[ATT_KT] = reinterpret_cast<float (*)[ATT_KT]>(Vs + ATT_KT * DH);   // [ATT_QB][ATT_KT]: one row per query of the chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qchunks = (p.Lq + ATT_QB - 1) / ATT_QB;
   const long long nblocks = (long long)p.B * p.H * qchunks;
@@ -127,6 +127,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnPar
     float m[QPW], l[QPW], acc0[QPW], acc1[QPW];
 #pragma unroll
     for (int u = 0; u < QPW; ++u) { m[u] = -INFINITY; l[u] = 0.f; acc0[u] = 0.f; acc1[u] = 0.f; }
+    // the QPW queries of a warp (qi = u * ATT_WARPS + warp) are processed TOGETHER per key tile: a K / V value is loaded
+    // from shared memory once and used by all of them, and the QPW independent softmax / accumulation chains give the
+    // scheduler instruction-level parallelism (one query at a time: 132 us on the 64 x 512 space attention, ncu r02).
+    const int nmine = nq > warp ? (nq - warp + ATT_WARPS - 1) / ATT_WARPS : 0;     // warp-uniform
 
     for (int k0 = 0; k0 < p.Lk; k0 += ATT_KT) {
       const int nk = min(ATT_KT, p.Lk - k0);
@@ -142,49 +146,65 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnPar
         *reinterpret_cast<float4*>(Vs + r * DH + 4 * t) = vv;
       }
       __syncthreads();
+      if (nmine > 0) {
+        // scores of keys lane and lane + 32 for all queries of this warp
+        float s0[QPW], s1[QPW];
 #pragma unroll
-      for (int u = 0; u < QPW; ++u) {
-        const int qi = u * ATT_WARPS + warp;     // warp-uniform; interleaved so that short chunks still use every warp
-        if (qi >= nq) break;
-        // scores of keys lane and lane + 32
-        float s0 = 0.f, s1 = 0.f;
-        const float4* qr = reinterpret_cast<const float4*>(Qs + qi * DH);
+        for (int u = 0; u < QPW; ++u) { s0[u] = 0.f; s1[u] = 0.f; }
         const float4* ka = reinterpret_cast<const float4*>(Ks + lane * KLD);
         const float4* kb = reinterpret_cast<const float4*>(Ks + (lane + 32) * KLD);
 #pragma unroll
         for (int t = 0; t < DH4; ++t) {
-          const float4 qv = qr[t], x = ka[t], y = kb[t];
-          s0 = fmaf(qv.x, x.x, s0); s0 = fmaf(qv.y, x.y, s0); s0 = fmaf(qv.z, x.z, s0); s0 = fmaf(qv.w, x.w, s0);
-          s1 = fmaf(qv.x, y.x, s1); s1 = fmaf(qv.y, y.y, s1); s1 = fmaf(qv.z, y.z, s1); s1 = fmaf(qv.w, y.w, s1);
-        }
-        if (lane >= nk) s0 = -INFINITY;
-        if (lane + 32 >= nk) s1 = -INFINITY;
-        const float mn = fmaxf(m[u], warp_max(fmaxf(s0, s1)));
-        const float e0 = expf(s0 - mn), e1 = expf(s1 - mn);      // exp(-inf) = 0 for the padded keys
-        const float corr = expf(m[u] - mn);                       // 0 on the first tile (m = -inf)
-        l[u] = l[u] * corr + warp_sum(e0 + e1);
-        m[u] = mn;
-        __syncwarp();
-        Ps[warp][lane] = e0;
-        Ps[warp][lane + 32] = e1;
-        __syncwarp();
-        // output dims lane and lane + 32: V rows read conflict-free, probabilities broadcast
-        float a0 = acc0[u] * corr, a1 = acc1[u] * corr;
-        const bool two = DH > 32;
-        const int nk4 = (nk + 3) & ~3;          // padded keys carry probability 0 and zero V rows
-        const float* v0 = Vs + (lane < DH ? lane : 0);
-        const float* v1 = Vs + (lane + 32 < DH ? lane + 32 : 0);
-#pragma unroll 2
-        for (int j = 0; j < nk4; j += 4) {
-          const float4 pj = *reinterpret_cast<const float4*>(&Ps[warp][j]);
-          a0 = fmaf(pj.x, v0[j * DH], a0); a0 = fmaf(pj.y, v0[(j + 1) * DH], a0);
-          a0 = fmaf(pj.z, v0[(j + 2) * DH], a0); a0 = fmaf(pj.w, v0[(j + 3) * DH], a0);
-          if (two) {
-            a1 = fmaf(pj.x, v1[j * DH], a1); a1 = fmaf(pj.y, v1[(j + 1) * DH], a1);
-            a1 = fmaf(pj.z, v1[(j + 2) * DH], a1); a1 = fmaf(pj.w, v1[(j + 3) * DH], a1);
+          const float4 x = ka[t], y = kb[t];
+#pragma unroll
+          for (int u = 0; u < QPW; ++u) {
+            if (u < nmine) {
+              const float4 qv = reinterpret_cast<const float4*>(Qs + (u * ATT_WARPS + warp) * DH)[t];   // broadcast
+              s0[u] = fmaf(qv.x, x.x, s0[u]); s0[u] = fmaf(qv.y, x.y, s0[u]); s0[u] = fmaf(qv.z, x.z, s0[u]); s0[u] = fmaf(qv.w, x.w, s0[u]);
+              s1[u] = fmaf(qv.x, y.x, s1[u]); s1[u] = fmaf(qv.y, y.y, s1[u]); s1[u] = fmaf(qv.z, y.z, s1[u]); s1[u] = fmaf(qv.w, y.w, s1[u]);
+            }
           }
         }
-        acc0[u] = a0; acc1[u] = a1;
+        __syncwarp();                      // previous tile's probabilities fully consumed
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+          if (u < nmine) {
+            if (lane >= nk) s0[u] = -INFINITY;
+            if (lane + 32 >= nk) s1[u] = -INFINITY;
+            const float mn = fmaxf(m[u], warp_max(fmaxf(s0[u], s1[u])));
+            const float e0 = expf(s0[u] - mn), e1 = expf(s1[u] - mn);      // exp(-inf) = 0 for the padded keys
+            const float corr = expf(m[u] - mn);                             // 0 on the first tile (m = -inf)
+            l[u] = l[u] * corr + warp_sum(e0 + e1);
+            m[u] = mn;
+            acc0[u] *= corr; acc1[u] *= corr;
+            Ps[warp * QPW + u][lane] = e0;
+            Ps[warp * QPW + u][lane + 32] = e1;
+          }
+        }
+        __syncwarp();
+        // output dims lane and lane + 32: one V load serves all queries, probabilities are broadcast reads
+        const int nk4 = (nk + 3) & ~3;      // padded keys carry probability 0 and zero V rows
+        const float* v0 = Vs + (lane < DH ? lane : 0);
+        const float* v1 = Vs + (lane + 32 < DH ? lane + 32 : 0);
+        constexpr bool two = DH > 32;
+#pragma unroll 1
+        for (int j = 0; j < nk4; j += 4) {
+          const float a0 = v0[j * DH], a1 = v0[(j + 1) * DH], a2 = v0[(j + 2) * DH], a3 = v0[(j + 3) * DH];
+          float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+          if (two) { b0 = v1[j * DH]; b1 = v1[(j + 1) * DH]; b2 = v1[(j + 2) * DH]; b3 = v1[(j + 3) * DH]; }
+#pragma unroll
+          for (int u = 0; u < QPW; ++u) {
+            if (u < nmine) {
+              const float4 pj = *reinterpret_cast<const float4*>(&Ps[warp * QPW + u][j]);
+              acc0[u] = fmaf(pj.x, a0, acc0[u]); acc0[u] = fmaf(pj.y, a1, acc0[u]);
+              acc0[u] = fmaf(pj.z, a2, acc0[u]); acc0[u] = fmaf(pj.w, a3, acc0[u]);
+              if (two) {
+                acc1[u] = fmaf(pj.x, b0, acc1[u]); acc1[u] = fmaf(pj.y, b1, acc1[u]);
+                acc1[u] = fmaf(pj.z, b2, acc1[u]); acc1[u] = fmaf(pj.w, b3, acc1[u]);
+              }
+            }
+          }
+        }
       }
     }
 #pragma unroll
@@ -195,6 +215,92 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnPar
       const long long base = b * p.o_sb + (long long)(q0 + qi) * p.o_si + h * p.dh;
       if (lane < p.dh) store_planes(p.out, p.o_plane_stride, base + lane, acc0[u] * inv, p.np);
       if (lane + 32 < p.dh) store_planes(p.out, p.o_plane_stride, base + lane + 32, acc1[u] * inv, p.np);
+    }
+  }
+}
+
+// Short sequences (Lq, Lk <= 32: the time attention, T = 16 frames per track): ONE WARP per (batch item, head), lane =
+// query.  K and V of the (batch, head) are staged in the warp's shared-memory slice, every lane keeps its query row in
+// registers, computes its Lk scores (K rows are broadcast reads), a softmax without any cross-lane traffic, and its
+// output row; outputs go back through shared memory so that the plane stores are coalesced.  (The tiled kernel above
+// spends a CTA with two block-wide barriers per (batch, head) on 16 x 16 scores: 113 us per launch for 4608 of them.)
+constexpr int ATS_WARPS = 4;
+template <int DH4>
+__global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const AttnParams p) {
+  constexpr int DH = 4 * DH4;
+  extern __shared__ __align__(16) float ats_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int OLD = DH + 4;                                       // output row pitch: conflict-free 128-bit stores
+  float* Ks = ats_smem + (size_t)warp * (32 * DH + 32 * OLD + 32 * 33);   // [32][DH]
+  float* Vs = Ks + 32 * DH;                                         // [32][DH]; the region (32 x OLD) is reused for the output rows
+  float* Ss = Vs + 32 * OLD;                                        // [Lk][33]: scores, one column per query lane
+  const int dh4 = p.dh >> 2;
+  const long long total = (long long)p.B * p.H;
+  for (long long w = (long long)blockIdx.x * ATS_WARPS + warp; w < total; w += (long long)gridDim.x * ATS_WARPS) {
+    const int h = (int)(w % p.H);
+    const int b = (int)(w / p.H);
+    const float* qp = p.q + b * p.q_sb + h * p.dh;
+    const float* kp = p.k + b * p.k_sb + h * p.dh;
+    const float* vp = p.v + b * p.v_sb + h * p.dh;
+    __syncwarp();
+    for (int e = lane; e < p.Lk * DH4; e += 32) {
+      const int r = e / DH4, t = e - r * DH4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (t < dh4) {
+        kk = __ldg(reinterpret_cast<const float4*>(kp + (long long)r * p.k_si) + t);
+        vv = __ldg(reinterpret_cast<const float4*>(vp + (long long)r * p.v_si) + t);
+      }
+      reinterpret_cast<float4*>(Ks)[e] = kk;
+      reinterpret_cast<float4*>(Vs)[e] = vv;
+    }
+    float4 q4[DH4];
+    const bool active = lane < p.Lq;
+#pragma unroll
+    for (int t = 0; t < DH4; ++t) {
+      q4[t] = (active && t < dh4) ? __ldg(reinterpret_cast<const float4*>(qp + (long long)lane * p.q_si) + t)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      q4[t].x *= p.scale; q4[t].y *= p.scale; q4[t].z *= p.scale; q4[t].w *= p.scale;   // MHA scales q before q k^T
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = 0; j < p.Lk; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
+      float sc = 0.f;
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) {
+        const float4 kk = kr[t];
+        sc = fmaf(q4[t].x, kk.x, sc); sc = fmaf(q4[t].y, kk.y, sc); sc = fmaf(q4[t].z, kk.z, sc); sc = fmaf(q4[t].w, kk.w, sc);
+      }
+      Ss[j * 33 + lane] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    float4 acc[DH4];
+#pragma unroll
+    for (int t = 0; t < DH4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum = 0.f;
+    for (int j = 0; j < p.Lk; ++j) {
+      const float pj = expf(Ss[j * 33 + lane] - mx);
+      sum += pj;
+      const float4* vr = reinterpret_cast<const float4*>(Vs + j * DH);
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) {
+        const float4 vv = vr[t];
+        acc[t].x = fmaf(pj, vv.x, acc[t].x); acc[t].y = fmaf(pj, vv.y, acc[t].y);
+        acc[t].z = fmaf(pj, vv.z, acc[t].z); acc[t].w = fmaf(pj, vv.w, acc[t].w);
+      }
+    }
+    const float inv = 1.f / sum;
+    __syncwarp();                          // every lane is done reading V before its rows are overwritten
+    float* Os = Vs;                        // [32][OLD]
+    if (active) {
+#pragma unroll
+      for (int t = 0; t < DH4; ++t)
+        *reinterpret_cast<float4*>(Os + lane * OLD + 4 * t) = make_float4(acc[t].x * inv, acc[t].y * inv, acc[t].z * inv, acc[t].w * inv);
+    }
+    __syncwarp();
+    for (int e = lane; e < p.Lq * p.dh; e += 32) {
+      const int i = e / p.dh, d = e - i * p.dh;
+      store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)i * p.o_si + h * p.dh + d, Os[i * OLD + d], p.np);
     }
   }
 }
@@ -250,11 +356,29 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
   COMET_REQUIRE(((uintptr_t)v % 16) == 0 && v_sb % 4 == 0 && v_si % 4 == 0, "v rows must be 16-byte aligned");
   AttnParams p{q, q_sb, q_si, k, k_sb, k_si, v, v_sb, v_si, reinterpret_cast<__nv_bfloat16*>(out_planes),
                o_plane_stride, o_sb, o_si, np, B, H, Lq, Lk, dh, 1.0f / sqrtf((float)dh)};
+  if (Lq <= 32 && Lk <= 32) {
+    long long nb = ((long long)B * H + ATS_WARPS - 1) / ATS_WARPS;
+    if (nb > 148LL * 16) nb = 148LL * 16;
+#define COMET_ATS_LAUNCH(D4)                                                                                       \
+  do {                                                                                                             \
+    const int smem = ATS_WARPS * (32 * 4 * D4 + 32 * (4 * D4 + 4) + 32 * 33) * (int)sizeof(float);                 \
+    if (smem > 48 * 1024)                                                                                          \
+      COMET_CUDA(cudaFuncSetAttribute(attention_small_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    attention_small_kernel<D4><<<(unsigned)nb, ATS_WARPS * 32, smem, (cudaStream_t)stream>>>(p);                   \
+  } while (0)
+    if (dh <= 4) COMET_ATS_LAUNCH(1);
+    else if (dh <= 16) COMET_ATS_LAUNCH(4);
+    else if (dh <= 32) COMET_ATS_LAUNCH(8);
+    else if (dh <= 48) COMET_ATS_LAUNCH(12);
+    else COMET_ATS_LAUNCH(16);
+#undef COMET_ATS_LAUNCH
+    return launch_status("attention_small_kernel");
+  }
   long long blocks = (long long)B * H * ((Lq + ATT_QB - 1) / ATT_QB);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
 #define COMET_ATTN_LAUNCH(D4)                                                                                       \
   do {                                                                                                              \
-    const int smem = (ATT_QB * 4 * D4 + ATT_KT * (4 * D4 + 4) + ATT_KT * 4 * D4 + ATT_WARPS * ATT_KT) * (int)sizeof(float); \
+    const int smem = (ATT_QB * 4 * D4 + ATT_KT * (4 * D4 + 4) + ATT_KT * 4 * D4 + ATT_QB * ATT_KT) * (int)sizeof(float); \
     if (smem > 48 * 1024)                                                                                           \
       COMET_CUDA(cudaFuncSetAttribute(attention_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
     attention_kernel<D4><<<(unsigned)blocks, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(p);                      \

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Round-2 profiling visit: ncu launch list of the bench step + one `ncu --set full` capture per hot kernel
+# (each only after the same command has exited 0 without ncu).  usage: TAG=r02 bash scripts/gpu_round2.sh
+set -u
+TAG=${TAG:-r02}
+mkdir -p gpurun_out
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-variants"
+timeout 600 $B > gpurun_out/plain.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $B > gpurun_out/ncu_list.log 2>&1
+echo "ncu list rc=$?"
+cap() {  # name regex skip count cmd...
+  local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+  timeout 600 "$@" > gpurun_out/plain_$name.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -f -o gpurun_out/${TAG}_$name "$@" > gpurun_out/ncu_$name.log 2>&1
+  echo "ncu $name rc=$?"
+}
+cap fine_tokens_up2 corr_lookup_c32_up2 8 1 $B
+cap fine_pyramid_up2 pyramid_up2 2 1 $B
+cap coarse_tc corr_tc_kernel 6 1 $B
+cap coarse_pre tc_pre_kernel 6 1 $B
+# update transformer: 4th forward of scripts/former_profile.py; gemm launches per forward = 110 -> skip 3*110 + 3 = fc1 (GELU, planes out) and fc2 of time block 0
+cap gemm_np3 gemm_tc_kernel 333 2 python scripts/former_profile.py coarse 3
+cap gemm_np1 gemm_tc_kernel 333 2 python scripts/former_profile.py coarse 1
+cap attention attention_kernel 73 2 python scripts/former_profile.py coarse 3
+ls -la gpurun_out/${TAG}_*

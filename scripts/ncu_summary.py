@@ -5,10 +5,11 @@ import csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-name = os.path.splitext(os.path.basename(rep))[0]
+name = os.path.splitext(os.path.basename(rep))[0] + (("_" + sys.argv[sys.argv.index("--suffix") + 1]) if "--suffix" in sys.argv else "")
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+idx = int(sys.argv[sys.argv.index("--index") + 1]) if "--index" in sys.argv else 0
+hdr, units, vals = rows[0], rows[1], rows[2 + idx]
 KEYS = [
     "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
