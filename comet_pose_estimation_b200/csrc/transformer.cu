@@ -265,12 +265,13 @@ __global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const A
     float mx = -INFINITY;
     for (int j = 0; j < p.Lk; ++j) {
       const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
-      float sc = 0.f;
+      float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;      // four independent chains: one serial chain of dh FMAs is latency-bound
 #pragma unroll
       for (int t = 0; t < DH4; ++t) {
         const float4 kk = kr[t];
-        sc = fmaf(q4[t].x, kk.x, sc); sc = fmaf(q4[t].y, kk.y, sc); sc = fmaf(q4[t].z, kk.z, sc); sc = fmaf(q4[t].w, kk.w, sc);
+        sx = fmaf(q4[t].x, kk.x, sx); sy = fmaf(q4[t].y, kk.y, sy); sz = fmaf(q4[t].z, kk.z, sz); sw = fmaf(q4[t].w, kk.w, sw);
       }
+      const float sc = (sx + sy) + (sz + sw);
       Ss[j * 33 + lane] = sc;
       mx = fmaxf(mx, sc);
     }
@@ -302,6 +303,95 @@ __global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const A
       const int i = e / p.dh, d = e - i * p.dh;
       store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)i * p.o_si + h * p.dh + d, Os[i * OLD + d], p.np);
     }
+  }
+}
+
+// Few keys, many queries (Lk <= 64: points attending to the 64 virtual tracks, the virtual tracks' self attention):
+// one CTA per (batch item, head, 128 queries); K and V of the (batch, head) are staged once per CTA, lane = query as in
+// attention_small_kernel -- no cross-lane reductions, K / V rows are broadcast reads.  (The tiled kernel needs ~500
+// instructions per query here, half of them warp reductions and probability traffic: 85 us per launch for the 512 x 64
+// point -> virtual attention; this formulation needs ~250.)
+constexpr int ATR_WARPS = 4, ATR_KMAX = 64;
+template <int DH4>
+__global__ void __launch_bounds__(ATR_WARPS * 32) attention_rows_kernel(const AttnParams p) {
+  constexpr int DH = 4 * DH4, OLD = DH + 4;
+  extern __shared__ __align__(16) float atr_smem[];
+  float* Ks = atr_smem;                         // [ATR_KMAX][DH]
+  float* Vs = Ks + ATR_KMAX * DH;               // [ATR_KMAX][DH]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Ss = Vs + ATR_KMAX * DH + (size_t)warp * (ATR_KMAX * 33 + 32 * OLD);   // [Lk][33] scores of this warp's queries
+  float* Os = Ss + ATR_KMAX * 33;               // [32][OLD] output rows of this warp
+  const int dh4 = p.dh >> 2;
+  const int qchunks = (p.Lq + ATR_WARPS * 32 - 1) / (ATR_WARPS * 32);
+  const long long nblocks = (long long)p.B * p.H * qchunks;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int qc = (int)(blk % qchunks);
+    const int h = (int)((blk / qchunks) % p.H);
+    const int b = (int)(blk / ((long long)qchunks * p.H));
+    const float* qp = p.q + b * p.q_sb + h * p.dh;
+    const float* kp = p.k + b * p.k_sb + h * p.dh;
+    const float* vp = p.v + b * p.v_sb + h * p.dh;
+    __syncthreads();                            // previous chunk's K / V fully consumed
+    for (int e = threadIdx.x; e < p.Lk * DH4; e += blockDim.x) {
+      const int r = e / DH4, t = e - r * DH4;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (t < dh4) {
+        kk = __ldg(reinterpret_cast<const float4*>(kp + (long long)r * p.k_si) + t);
+        vv = __ldg(reinterpret_cast<const float4*>(vp + (long long)r * p.v_si) + t);
+      }
+      reinterpret_cast<float4*>(Ks)[e] = kk;
+      reinterpret_cast<float4*>(Vs)[e] = vv;
+    }
+    const int qi = qc * (ATR_WARPS * 32) + warp * 32 + lane;
+    const bool active = qi < p.Lq;
+    float4 q4[DH4];
+#pragma unroll
+    for (int t = 0; t < DH4; ++t) {
+      q4[t] = (active && t < dh4) ? __ldg(reinterpret_cast<const float4*>(qp + (long long)qi * p.q_si) + t)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      q4[t].x *= p.scale; q4[t].y *= p.scale; q4[t].z *= p.scale; q4[t].w *= p.scale;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int j = 0; j < p.Lk; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
+      float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;      // four independent chains: one serial chain of dh FMAs is latency-bound
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) {
+        const float4 kk = kr[t];
+        sx = fmaf(q4[t].x, kk.x, sx); sy = fmaf(q4[t].y, kk.y, sy); sz = fmaf(q4[t].z, kk.z, sz); sw = fmaf(q4[t].w, kk.w, sw);
+      }
+      const float sc = (sx + sy) + (sz + sw);
+      Ss[j * 33 + lane] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    float4 acc[DH4];
+#pragma unroll
+    for (int t = 0; t < DH4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum = 0.f;
+    for (int j = 0; j < p.Lk; ++j) {
+      const float pj = expf(Ss[j * 33 + lane] - mx);
+      sum += pj;
+      const float4* vr = reinterpret_cast<const float4*>(Vs + j * DH);
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) {
+        const float4 vv = vr[t];
+        acc[t].x = fmaf(pj, vv.x, acc[t].x); acc[t].y = fmaf(pj, vv.y, acc[t].y);
+        acc[t].z = fmaf(pj, vv.z, acc[t].z); acc[t].w = fmaf(pj, vv.w, acc[t].w);
+      }
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int t = 0; t < DH4; ++t)
+      *reinterpret_cast<float4*>(Os + lane * OLD + 4 * t) = make_float4(acc[t].x * inv, acc[t].y * inv, acc[t].z * inv, acc[t].w * inv);
+    __syncwarp();
+    const int q0w = qc * (ATR_WARPS * 32) + warp * 32;
+    const int nqw = min(32, p.Lq - q0w);
+    for (int e = lane; e < nqw * p.dh; e += 32) {
+      const int i = e / p.dh, d = e - i * p.dh;
+      store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)(q0w + i) * p.o_si + h * p.dh + d, Os[i * OLD + d], p.np);
+    }
+    __syncwarp();
   }
 }
 
@@ -373,6 +463,24 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
     else COMET_ATS_LAUNCH(16);
 #undef COMET_ATS_LAUNCH
     return launch_status("attention_small_kernel");
+  }
+  if (Lk <= ATR_KMAX && Lq >= 64) {
+    long long nb = (long long)B * H * ((Lq + ATR_WARPS * 32 - 1) / (ATR_WARPS * 32));
+    if (nb > 148LL * 16) nb = 148LL * 16;
+#define COMET_ATR_LAUNCH(D4)                                                                                       \
+  do {                                                                                                             \
+    const int smem = (2 * ATR_KMAX * 4 * D4 + ATR_WARPS * (ATR_KMAX * 33 + 32 * (4 * D4 + 4))) * (int)sizeof(float); \
+    if (smem > 48 * 1024)                                                                                          \
+      COMET_CUDA(cudaFuncSetAttribute(attention_rows_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    attention_rows_kernel<D4><<<(unsigned)nb, ATR_WARPS * 32, smem, (cudaStream_t)stream>>>(p);                    \
+  } while (0)
+    if (dh <= 4) COMET_ATR_LAUNCH(1);
+    else if (dh <= 16) COMET_ATR_LAUNCH(4);
+    else if (dh <= 32) COMET_ATR_LAUNCH(8);
+    else if (dh <= 48) COMET_ATR_LAUNCH(12);
+    else COMET_ATR_LAUNCH(16);
+#undef COMET_ATR_LAUNCH
+    return launch_status("attention_rows_kernel");
   }
   long long blocks = (long long)B * H * ((Lq + ATT_QB - 1) / ATT_QB);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
