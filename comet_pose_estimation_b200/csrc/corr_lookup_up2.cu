@@ -18,7 +18,7 @@
 // (81 + 64 lines of 128 B) instead of 22.6 KB.  The up-sampled tensor is what the reference's CorrBlock receives;
 // CorrBlock.from_upsampled() takes S and is used by this package's refine_track only.
 //
-// One warp per (patch, frame) query, persistent, 8 warps per SM; per query two 4-D TMA boxes land in shared memory with
+// One warp per (patch, frame) query, persistent, 11 warps per SM (what shared memory holds); per query two 4-D TMA boxes land in shared memory with
 // the 128-byte swizzle (off-map positions zero-filled); structure otherwise as corr_lookup_c32_tma_kernel.
 #include "lookup_common.cuh"
 
@@ -30,7 +30,13 @@ constexpr int UP2_BOXS = UP2_SB * UP2_SB * 128;            // 10368 B landed
 constexpr int UP2_BOXS_PAD = (UP2_BOXS + 1023) & ~1023;    // 11264
 constexpr int UP2_BOX2 = UP2_GG * 128;                     // 8192
 constexpr int UP2_WARP_BYTES = UP2_BOXS_PAD + UP2_BOX2;
-constexpr int UP2_SMEM = 8 * UP2_WARP_BYTES + 8 * 32 * 4 + 8 * 96 * 4 + 8 * 64 * 4 + 8 * 8;
+// Warps per CTA (= per SM): as many as shared memory holds.  The kernel is latency-bound at low occupancy (ncu r02 with
+// 8 warps: issue slots 39 % busy, 1.9 fixed-latency stall cycles per issue), so every extra warp in flight pays.
+#ifndef COMET_UP2_WARPS
+#define COMET_UP2_WARPS 11
+#endif
+constexpr int UP2_WARPS = COMET_UP2_WARPS;
+constexpr int UP2_SMEM = UP2_WARPS * UP2_WARP_BYTES + UP2_WARPS * 32 * 4 + UP2_WARPS * 96 * 4 + UP2_WARPS * 64 * 4 + UP2_WARPS * 8;
 
 struct Up2Maps { CUtensorMap s, p2; };
 
@@ -44,17 +50,18 @@ __device__ __forceinline__ void up2_stencil0(int i, int& k, float& w0, float& w1
 }
 
 template <bool TOKENS, bool BF16>
-__global__ void __launch_bounds__(256, 1) corr_lookup_c32_up2_kernel(const __grid_constant__ Up2Maps maps, const LookupParams p) {
+__global__ void __launch_bounds__(UP2_WARPS * 32, 1) corr_lookup_c32_up2_kernel(const __grid_constant__ Up2Maps maps, const LookupParams p) {
   constexpr int R = UP2_R, G = UP2_G, Wr = UP2_WR, WW = UP2_WW, GG = UP2_GG;
   extern __shared__ __align__(1024) uint8_t smem_up2[];
   uint8_t* const smem = smem_up2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* boxS = smem + warp * UP2_WARP_BYTES;
   uint8_t* box2 = boxS + UP2_BOXS_PAD;
-  float* Ts = reinterpret_cast<float*>(smem + 8 * UP2_WARP_BYTES) + warp * 32;
-  float* V16 = reinterpret_cast<float*>(smem + 8 * UP2_WARP_BYTES + 8 * 32 * 4) + warp * 96;   // 9 x 9 correlations with S
-  float* Vs = reinterpret_cast<float*>(smem + 8 * UP2_WARP_BYTES + 8 * 32 * 4 + 8 * 96 * 4) + warp * 64;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8 * UP2_WARP_BYTES + 8 * 32 * 4 + 8 * 96 * 4 + 8 * 64 * 4) + warp;
+  constexpr int NW = UP2_WARPS;
+  float* Ts = reinterpret_cast<float*>(smem + NW * UP2_WARP_BYTES) + warp * 32;
+  float* V16 = reinterpret_cast<float*>(smem + NW * UP2_WARP_BYTES + NW * 32 * 4) + warp * 96;   // 9 x 9 correlations with S
+  float* Vs = reinterpret_cast<float*>(smem + NW * UP2_WARP_BYTES + NW * 32 * 4 + NW * 96 * 4) + warp * 64;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + NW * UP2_WARP_BYTES + NW * 32 * 4 + NW * 96 * 4 + NW * 64 * 4) + warp;
   if (lane == 0) {
     tma::mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -62,7 +69,7 @@ __global__ void __launch_bounds__(256, 1) corr_lookup_c32_up2_kernel(const __gri
   __syncwarp();
   uint32_t phase = 0;
   const long long total = (long long)p.B * p.S * p.N;
-  const long long nwarps = (long long)gridDim.x * 8;
+  const long long nwarps = (long long)gridDim.x * NW;
   // level sizes: lvl 0 = (2Hs-1, 2Ws-1) virtual, lvl 1 = (Hs-1, Ws-1) virtual, lvl 2 stored; source map = lvlH/W[0]/2+1
   const int Hs = p.lvlH[0] / 2 + 1, Ws = p.lvlW[0] / 2 + 1;
 
@@ -82,9 +89,9 @@ __global__ void __launch_bounds__(256, 1) corr_lookup_c32_up2_kernel(const __gri
     }
   };
   float cx, cy, cx0, cy0, tl;
-  fetch((long long)blockIdx.x * 8 + warp, cx, cy, cx0, cy0, tl);
+  fetch((long long)blockIdx.x * NW + warp, cx, cy, cx0, cy0, tl);
 
-  for (long long q = (long long)blockIdx.x * 8 + warp; q < total; q += nwarps) {
+  for (long long q = (long long)blockIdx.x * NW + warp; q < total; q += nwarps) {
     const int n = (int)(q % p.N);
     const int s = (int)((q / p.N) % p.S);
     const int b = (int)(q / ((long long)p.N * p.S));
@@ -348,13 +355,13 @@ int launch_lookup_up2(LookupParams& p, const float* src, const float* p2, cudaSt
   rc = encode_level_map(&maps.p2, p2, p.B * p.S, p.lvlH[2], p.lvlW[2], UP2_G);
   if (rc != COMET_OK) return rc;
   const int sms = device_sm_count_if_sm100();
-  const long long want = (total + 7) / 8;
+  const long long want = (total + UP2_WARPS - 1) / UP2_WARPS;
   const int grid = (int)(want < sms ? want : sms);
 #define COMET_UP2_LAUNCH(BF)                                                                                       \
   do {                                                                                                             \
     COMET_CUDA(cudaFuncSetAttribute(corr_lookup_c32_up2_kernel<TOKENS, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     UP2_SMEM));                                                                    \
-    corr_lookup_c32_up2_kernel<TOKENS, BF><<<grid, 256, UP2_SMEM, stream>>>(maps, p);                              \
+    corr_lookup_c32_up2_kernel<TOKENS, BF><<<grid, UP2_WARPS * 32, UP2_SMEM, stream>>>(maps, p);                              \
   } while (0)
   if (p.bf16) COMET_UP2_LAUNCH(true); else COMET_UP2_LAUNCH(false);
 #undef COMET_UP2_LAUNCH

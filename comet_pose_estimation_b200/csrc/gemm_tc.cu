@@ -44,6 +44,8 @@ struct Params {
   int np;                  // planes per operand (1 or 3)
   int nstage;              // ring depth: nstage * np * 32 KB <= SMEM_BUDGET
   int tiles_m, tiles_n, ktiles;
+  int bk;                  // K elements per pipeline stage: 64 (128-byte swizzle rows) or 32 (64-byte rows: half-size
+                           // stages, twice as many of them in flight -- the float32-grade mode moves 96 KB per K=64 block)
   int bn;                  // output tile width: 128, or 64 / 32 when 128 would leave most SMs without a tile (small M)
   const float* bias;       // [N] or null
   const float* resid;      // [M, resid_ld] float32 or null (added after the activation)
@@ -117,15 +119,16 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-// K-major SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); LBO is not used by
+// K-major swizzled operand tile: rows of `row_bytes`, 8-row groups 8 * row_bytes apart (SBO); LBO is not used by
 // swizzled K-major layouts (canonical value 1).
-__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr) {
+// `row_bytes` = 128 (SWIZZLE_128B, layout type 2) or 64 (SWIZZLE_64B, layout type 4); SBO = 8 rows.
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t saddr, uint32_t row_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)(((8 * row_bytes) >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
   return d;
 }
 // kind::f16 instruction descriptor: D f32, A/B bf16, both K-major, M=128; N = Params::bn goes to bits 17-22 at run time
@@ -163,8 +166,10 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int b_tile_bytes = p.bn * BK * 2;
-  const int stage_bytes = p.np * (TILE_BYTES + b_tile_bytes);   // [A planes][B planes]
+  const int a_tile_bytes = BM * p.bk * 2, b_tile_bytes = p.bn * p.bk * 2;
+  const uint32_t row_bytes = (uint32_t)p.bk * 2;
+  const int ksteps = p.bk / 16;
+  const int stage_bytes = p.np * (a_tile_bytes + b_tile_bytes);   // [A planes][B planes]
   const uint32_t idesc = IDESC_BASE | ((uint32_t)(p.bn >> 3) << 17);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * stage_bytes);
   uint64_t* full = bars;                 // [nstage]  TMA -> MMA
@@ -201,8 +206,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           uint8_t* dst = smem + stage * stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
           for (int i = 0; i < p.np; ++i) {
-            tma_load_2d(&maps.a[i], &full[stage], dst + i * TILE_BYTES, kb * BK, mb * BM);
-            tma_load_2d(&maps.w[i], &full[stage], dst + p.np * TILE_BYTES + i * b_tile_bytes, kb * BK, nb * p.bn);
+            tma_load_2d(&maps.a[i], &full[stage], dst + i * a_tile_bytes, kb * p.bk, mb * BM);
+            tma_load_2d(&maps.w[i], &full[stage], dst + p.np * a_tile_bytes + i * b_tile_bytes, kb * p.bk, nb * p.bn);
           }
           if (++stage == (uint32_t)p.nstage) { stage = 0; phase ^= 1; }
         }
@@ -221,23 +226,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         mbar_wait(&full[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + p.np * TILE_BYTES;
+          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + p.np * a_tile_bytes;
           // plane pairs (i, j), i + j < np: (0,0) into the main accumulator, the low-order ones into their own
           for (int sum = p.np - 1; sum >= 0; --sum) {
             for (int i = 0; i <= sum; ++i) {
               const int j = sum - i;
-              const uint64_t ad = make_desc_kmajor(a0 + i * TILE_BYTES), bd = make_desc_kmajor(b0 + j * b_tile_bytes);
+              const uint64_t ad = make_desc_kmajor(a0 + i * a_tile_bytes, row_bytes), bd = make_desc_kmajor(b0 + j * b_tile_bytes, row_bytes);
               if (sum == 0) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                  umma_bf16_ss(d_main, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum_main);   // +32 bytes per K=16
-                  accum_main = 1;
+                  if (k < ksteps) {
+                    umma_bf16_ss(d_main, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum_main);   // +32 bytes per K=16
+                    accum_main = 1;
+                  }
                 }
               } else {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
-                  umma_bf16_ss(d_low, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum_low);
-                  accum_low = 1;
+                  if (k < ksteps) {
+                    umma_bf16_ss(d_low, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, accum_low);
+                    accum_low = 1;
+                  }
                 }
               }
             }
@@ -361,15 +370,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 
 // 2-D tensor map over a row-major bf16 matrix [rows, ld] (K contiguous): dims {K, rows}, box {64, 128}, 128-byte swizzle,
 // zero fill outside (K tails and row tails of the last tile read as 0).
-static int encode_kmajor(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows) {
+static int encode_kmajor(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows, int bk) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc) return fail(COMET_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
   const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled (gemm operand) failed with %d", (int)cr);
   return COMET_OK;
@@ -442,18 +452,19 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
   // output tile width: 128 unless that leaves most SMs without a tile (the virtual-track GEMMs have M = 1024 rows: 24
   // tiles of 128x128 on 148 SMs, each MMA-bound for its whole K -- measured 27.6 us against 7 us of work per SM)
   p.bn = 128;
+  p.bk = (np == 3 && option(COMET_OPT_GEMM_BK32)) ? 32 : 64;
   while (p.bn > 32 && (long long)p.tiles_m * ((N + p.bn - 1) / p.bn) * 10 < 7LL * sms) p.bn >>= 1;
   for (int i = 0; i < np; ++i) {
-    int rc = gemm::encode_kmajor(&maps.a[i], xp + i * x_plane_stride, M, K, x_ld, gemm::BM);
+    int rc = gemm::encode_kmajor(&maps.a[i], xp + i * x_plane_stride, M, K, x_ld, gemm::BM, p.bk);
     if (rc != COMET_OK) return rc;
-    rc = gemm::encode_kmajor(&maps.w[i], wp + i * w_plane_stride, N, K, w_ld, p.bn);
+    rc = gemm::encode_kmajor(&maps.w[i], wp + i * w_plane_stride, N, K, w_ld, p.bn, p.bk);
     if (rc != COMET_OK) return rc;
   }
-  const int stage_bytes = np * (gemm::TILE_BYTES + p.bn * gemm::BK * 2);
+  const int stage_bytes = np * (gemm::BM + p.bn) * p.bk * 2;
   p.nstage = gemm::SMEM_BUDGET / stage_bytes;
-  if (p.nstage > 8) p.nstage = 8;
+  if (p.nstage > 12) p.nstage = 12;
   p.tiles_n = (N + p.bn - 1) / p.bn;
-  p.ktiles = (K + gemm::BK - 1) / gemm::BK;
+  p.ktiles = (K + p.bk - 1) / p.bk;
   p.bias = bias; p.resid = resid; p.resid_ld = resid_ld; p.out = out; p.out_ld = out_ld;
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out_planes);
   for (int i = 0; i < out_np; ++i) p.outp[i] = op + i * out_plane_stride;

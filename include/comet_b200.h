@@ -70,7 +70,8 @@ int comet_has_tensor_path(void);
  *   COMET_OPT_TMA_LOOKUP   the TMA-staged C=32 lookup serves channel-last small maps; off = register version */
 #define COMET_OPT_TENSOR_PATH 0
 #define COMET_OPT_TMA_LOOKUP 1
-#define COMET_OPT_COUNT 2
+#define COMET_OPT_GEMM_BK32 2   /* float32-grade GEMM: K=32 pipeline stages (64-byte swizzle); off = K=64 stages */
+#define COMET_OPT_COUNT 3
 int comet_set_option(int option, int value);
 int comet_get_option(int option);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */
