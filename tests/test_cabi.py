@@ -94,6 +94,7 @@ def test_options_are_an_explicit_abi_not_environment_variables(built):
     from comet_pose_estimation_b200 import _lib
 
     assert _lib.lib.comet_get_option(_lib.OPT_TENSOR_PATH) == 1 and _lib.lib.comet_get_option(_lib.OPT_TMA_LOOKUP) == 1
+    assert _lib.lib.comet_get_option(_lib.OPT_GEMM_BK32) == 0          # measured slower: off unless asked for
     assert _lib.set_option(_lib.OPT_TMA_LOOKUP, False) is True
     assert _lib.lib.comet_get_option(_lib.OPT_TMA_LOOKUP) == 0
     _lib.set_option(_lib.OPT_TMA_LOOKUP, True)
