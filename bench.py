@@ -531,6 +531,20 @@ def main():
 
     roof = roofline_of(dom if dom in ab else "fine_tokens")
     roof["dominant_by_time"] = dom
+    if dom == "coarse_tokens":
+        # the coarse class is the tcgen05 correlation kernel: its roof is the tensor pipe (north_star), FLOPs as the
+        # reference defines them (dense, all pyramid levels); the HBM view of the same launches stays in `rooflines`
+        k_ = kern["coarse_tokens"]
+        flop_ = 2.0 * Q * COARSE["S"] * COARSE["N"] * COARSE["C"] * 5456
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f_:
+                tp_ = float(json.load(f_)["bf16_tflops_sustained"])
+        except Exception:
+            tp_ = 1400.0
+        roof.update({"bound": "tensor", "achieved": flop_ / (k_["ms_avg"] * 1e-3) / 1e12, "peak": tp_, "unit": "TFLOP/s",
+                     "frac": flop_ / (k_["ms_avg"] * 1e-3) / 1e12 / tp_, "frac_dram": None,
+                     "algorithmic_flops_per_launch": flop_,
+                     "peak_source": "measured (MEASURED_PEAKS.json, sustained bf16)"})
     roof["note"] = ("algorithmic bytes: fine_tokens = per query the feature lines of its boxes CLIPPED to the maps (from the "
                     "actual coordinates; %.1f lines of 128 B on average) + target + coords + token row; fine_pyramid = "
                     "the source positions level 2 depends on read once + level 2 written; coarse_tokens = SURVEY 8d "
@@ -667,7 +681,38 @@ def main():
                                             "BaseTrackerPredictor INCLUDING the update transformer and state updates: "
                                             "transformer on this package's tcgen05 / attention / LayerNorm kernels vs its "
                                             "torch.nn definition (cuBLAS / ATen); TF32 off for the float32 arms"}
-        del coarse_m, fine_m
+        # ---- the whole tracker from IMAGES (process_images_to_fmaps -> coarse -> refine_track -> inverted score: the
+        # tracker part of COMET.forward_all, E2Epose2.py:176-239) through TrackerPredictor.track, one 16-frame 512x512
+        # sequence, device-resident and end to end from pinned host images (50 MB H2D, tracks + confidence D2H) ----
+        tp = cb.TrackerPredictor(coarse_predictor=coarse_m, fine_predictor=fine_m, cfg=tcfg).eval().to(dev)
+        tp.fine_fnet.to(memory_format=torch.channels_last)
+        tp.coarse_fnet.to(memory_format=torch.channels_last)
+        img_h = torch.rand(1, COARSE["S"], 3, 512, 512).pin_memory()
+        q_h = (torch.rand(1, COARSE["N"], 2) * 480 + 16).pin_memory()
+        img_d, q_d = img_h.to(dev), q_h.to(dev)
+        res_h = torch.empty(1, COARSE["S"], COARSE["N"], 3).pin_memory()
+
+        def from_images_dev():
+            return tp.track(img_d, q_d, coarse_iters=COARSE["iters"])
+
+        def from_images_host():
+            o = tp.track(img_h.to(dev, non_blocking=True), q_h.to(dev, non_blocking=True), coarse_iters=COARSE["iters"])
+            res_h[..., :2].copy_(o["refine_pred_track"], non_blocking=True)
+            res_h[..., 2].copy_(o["pred_score"], non_blocking=True)
+
+        fi = {}
+        fi["ms_per_sequence"], _ = timed(from_images_dev, 5, 2)
+        fi["ms_per_sequence_e2e_host_images"], _ = timed(from_images_host, 5, 2)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            fi["ms_per_sequence_autocast_bf16"], _ = timed(from_images_dev, 5, 2)
+        fi["sequences_per_s"] = world / (fi["ms_per_sequence"] * 1e-3)
+        fi["h2d_bytes"] = img_h.numel() * 4 + q_h.numel() * 4
+        fi["d2h_bytes"] = res_h.numel() * 4
+        fi["what"] = ("TrackerPredictor.track on one sequence of 16 512x512 frames, 512 query points: BasicEncoder (cuDNN convs, "
+                      "library resize / instance-norm kernels) -> coarse tracker 4 it -> patch encoder -> fine tracker 6 it -> "
+                      "score; random-init weights")
+        variants["tracker_from_images"] = fi
+        del coarse_m, fine_m, tp, img_d
 
     # ---- the producer of the fine tracker's input (outside `value`): patch gather + ShallowEncoder for
     # ONE sequence (8192 patches of a 16-frame 512x512 sequence), with the library's resize / instance-norm kernels and

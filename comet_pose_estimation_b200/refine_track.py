@@ -36,24 +36,34 @@ USE_LIBRARY_KERNELS = True
 DEFER_UPSAMPLE = True
 
 
+def _library_ok(x: torch.Tensor) -> bool:
+    return (USE_LIBRARY_KERNELS and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16, torch.float16)
+            and not (torch.is_grad_enabled() and x.requires_grad))
+
+
 def _resize(x: torch.Tensor, size) -> torch.Tensor:
-    """``F.interpolate(x, size, mode="bilinear", align_corners=True)``.  On the GPU (inference, float32) this is the
-    library's own kernel: ATen's up-sampling kernel walks batch x channels inside every thread and, at 8192 patches,
-    is 90 % of ``refine_track`` (192-314 ms per sequence on B200 against ~1 ms here).  Anything else (CPU tensors in
-    the host-logic tests, autograd) takes the torch op."""
-    if USE_LIBRARY_KERNELS and x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+    """``F.interpolate(x, size, mode="bilinear", align_corners=True)``.  On the GPU (inference) this is the library's own
+    kernel: ATen's up-sampling kernel walks batch x channels inside every thread and, at 8192 patches, is 90 % of
+    ``refine_track`` (192-314 ms per sequence on B200 against ~1 ms here).  bf16 / fp16 activations (the encoder under
+    ``torch.autocast``) are resized in float32 and cast back -- ATen's path for them is the same slow kernel.  Anything
+    else (CPU tensors in the host-logic tests, autograd) takes the torch op."""
+    if _library_ok(x):
         from .utils import upsample_bilinear_align_corners
 
+        if x.dtype != torch.float32:
+            return upsample_bilinear_align_corners(x.float(), size).to(x.dtype)
         return upsample_bilinear_align_corners(x, size)
     return F.interpolate(x, size, mode="bilinear", align_corners=True)
 
 
 def _inorm(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool) -> torch.Tensor:
-    """``relu(norm(x))`` / ``norm(x)``: the library's instance-norm kernel for float32 CUDA inference (ATen routes
+    """``relu(norm(x))`` / ``norm(x)``: the library's instance-norm kernel for CUDA inference (ATen routes
     InstanceNorm2d through batch_norm over N*C channels: 8.6 ms per sequence at 8192 patches), torch otherwise."""
-    if USE_LIBRARY_KERNELS and x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+    if _library_ok(x):
         from .utils import instance_norm
 
+        if x.dtype != torch.float32:
+            return instance_norm(x.float(), relu=relu, eps=norm.eps).to(x.dtype)
         return instance_norm(x, relu=relu, eps=norm.eps)
     y = norm(x)
     return F.relu(y) if relu else y

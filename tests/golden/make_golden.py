@@ -262,6 +262,24 @@ def main():
             out[f"{name}/ftr/{k}"] = v.numpy()
     save("refine", **out)
 
+    # ---- BasicEncoder / process_images_to_fmaps (the step before the path) ---------------------------
+    out = {}
+    enc = blocks.BasicEncoder(input_dim=3, output_dim=128, stride=4).eval()
+    sd = cases.seeded_state_dict({k: tuple(v.shape) for k, v in enc.state_dict().items()}, 91)
+    enc.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    img = np.random.default_rng(92).random((1, 2, 3, 96, 80)).astype(np.float32)       # H != W, not multiples of 8
+    out["basic/images"] = img
+    out["basic/keys"] = np.array(sorted(sd), dtype=object).astype(str)
+    x = F_interp(torch, t(img).reshape(2, 3, 96, 80))
+    out["basic/fmaps"] = enc(x).reshape(1, 2, 128, x.shape[-2] // 4, x.shape[-1] // 4).numpy()
+    out["basic/encoder_only"] = enc(t(img).reshape(2, 3, 96, 80)).numpy()
+    save("encoders", **out)
+
+
+def F_interp(torch, x):
+    """track_predictor.py:136-145 with down_ratio 2."""
+    return torch.nn.functional.interpolate(x, scale_factor=0.5, mode="bilinear", align_corners=True)
+
 
 if __name__ == "__main__":
     main()
