@@ -454,6 +454,19 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// The correlation-independent token channels as their own launch, AFTER the tensor kernel in stream order and chained to
+// it with programmatic dependent launch: the tensor kernel triggers its dependents as soon as its CTAs are resident, so
+// these (128 threads, no shared memory, <= 64 registers: they fit beside the 218 KB tensor CTAs) run in the issue slots
+// and HBM bandwidth the tensor kernel leaves idle (29 % / 30 % busy).  They write channels the tensor kernel never
+// touches; the wait at the END makes this grid's completion imply the tensor kernel's.  COMET_OPT_TC_OVERLAP_MISC, off by
+// default: measured 0.155 vs 0.112 ms per iteration -- beside a tensor CTA (53.7 K registers) only 4 such warps fit on an
+// SM, and the 56 MB these rows move then take longer than the tensor kernel itself.
+__global__ void __launch_bounds__(128, 1) tc_misc_kernel(const Params p) {
+  const long long nw = (long long)gridDim.x * 4;
+  token_misc_rows(p, (long long)blockIdx.x * 4 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ the kernel
 template <int R, bool BF16, bool VOLUME>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -498,7 +511,8 @@ corr_tc_kernel(const Params p) {
     if (threadIdx.x == 0 && p.status) atomicExch(p.status, 9);
     __trap();
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // plan + token rows of tc_pre_kernel are complete and visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // tc_misc_kernel may run beside this grid
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // plan (+ token rows) of tc_pre_kernel are complete and visible
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -1101,7 +1115,8 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   const int full = (p.volume_mode || TC_DBG(p, 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
   // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
   long long misc = 0;
-  if (p.tokens) {
+  const bool overlap_misc = p.tokens && COMET_TC_PDL && option(COMET_OPT_TC_OVERLAP_MISC);
+  if (p.tokens && !overlap_misc) {
     misc = ((long long)p.B * p.N * p.S + 7) / 8;
     if (misc > 64LL * sms) misc = 64LL * sms;
   }
@@ -1139,7 +1154,18 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   }
 #undef COMET_TC_LAUNCH_R
 #undef COMET_TC_LAUNCH
-  return launch_status("corr_tc_kernel");
+  rc = launch_status("corr_tc_kernel");
+  if (rc != COMET_OK || !overlap_misc) return rc;
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * sms)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    COMET_CUDA(cudaLaunchKernelEx(&cfg, tc_misc_kernel, p));
+  }
+  return launch_status("tc_misc_kernel");
 }
 
 static int check_shape(int C, int H, int W, int L, int r, int pad_mode) {

@@ -72,7 +72,11 @@ int comet_has_tensor_path(void);
 #define COMET_OPT_TMA_LOOKUP 1
 #define COMET_OPT_GEMM_BK32 2   /* float32-grade GEMM: K=32 pipeline stages (64-byte swizzle, 4 in flight) instead of K=64 (2 in
                                    flight).  OFF by default: measured 7.28 vs 6.16 ms per coarse forward (scripts/gemm_ab.py) */
-#define COMET_OPT_COUNT 3
+#define COMET_OPT_TC_OVERLAP_MISC 3 /* coarse tokens: the correlation-independent channels as a third launch that runs BESIDE the
+                                      tensor kernel (programmatic dependent launch) instead of before it.  OFF by default:
+                                      measured 0.155 vs 0.112 ms per iteration (scripts/coarse_ab.py) -- the tensor CTAs leave
+                                      room for 4 warps per SM, too few for a bandwidth kernel */
+#define COMET_OPT_COUNT 4
 int comet_set_option(int option, int value);
 int comet_get_option(int option);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */
