@@ -686,7 +686,6 @@ def main():
         # sequence, device-resident and end to end from pinned host images (50 MB H2D, tracks + confidence D2H) ----
         tp = cb.TrackerPredictor(coarse_predictor=coarse_m, fine_predictor=fine_m, cfg=tcfg).eval().to(dev)
         tp.fine_fnet.to(memory_format=torch.channels_last)
-        tp.coarse_fnet.to(memory_format=torch.channels_last)
         img_h = torch.rand(1, COARSE["S"], 3, 512, 512).pin_memory()
         q_h = (torch.rand(1, COARSE["N"], 2) * 480 + 16).pin_memory()
         img_d, q_d = img_h.to(dev), q_h.to(dev)

@@ -429,7 +429,9 @@ __device__ __forceinline__ void token_misc_rows(const Params& p, long long warp_
       const int e = lane + 32 * k;
       const int axis = e / Ce, w = e - axis * Ce;
       const float arg = __fmul_rn(axis ? fly : flx, (float)(w & ~1) * step);
-      o[e] = ((w & 1) ? cosf(arg) : sinf(arg)) + pe[k];
+      float sv, cv;
+      sincosf(arg, &sv, &cv);      // one range reduction, no divergence between the sin and the cos lanes
+      o[e] = ((w & 1) ? cv : sv) + pe[k];
     }
     if (lane < 2) o[KC + lane] = (lane ? fly : flx) + __ldg(pq + KC + lane);
 #pragma unroll

@@ -176,6 +176,10 @@ def instance_norm(x: torch.Tensor, relu: bool = False, eps: float = 1e-5) -> tor
     N, C, H, W = x.shape
     x = x if x.dtype == torch.float32 else x.float()
     cl = C > 1 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+    if cl and H * W > 4096 and N * C < 148 * 256:
+        # few large planes: the channels-last kernel (one thread per (sample, channel), built for the patch encoder's
+        # 262144 planes of <= 256 positions) would serialise over H*W; the NCHW kernel (one warp per plane) does not
+        cl = False
     if not cl:
         x = x.contiguous()
     out = torch.empty_like(x)
