@@ -395,6 +395,140 @@ __global__ void __launch_bounds__(ATR_WARPS * 32) attention_rows_kernel(const At
   }
 }
 
+// Few queries, many keys (the 64 virtual tracks attending to all N point tracks): one CTA per (batch item, head,
+// 64-query chunk), 8 warps = 2 query groups of 32 (lane = query, as in attention_rows_kernel) x 4 KEY SPLITS.  Every split
+// walks its quarter of the keys in 64-key tiles (4 tiles staged at a time) with a per-lane online softmax; the four partial
+// results (running max, sum, output row) of a query are merged through shared memory at the end.  (The tiled kernel gives
+// this shape 128 CTAs of dependent warp reductions: 108 us per launch at N = 512.)
+constexpr int AKS_SPLITS = 4, AKS_KT = 64;
+template <int DH4>
+__global__ void __launch_bounds__(256) attention_ksplit_kernel(const AttnParams p) {
+  constexpr int DH = 4 * DH4, MP = DH + 8;       // merge row pitch: DH outputs, max, sum; a multiple of 4 floats (float4 rows)
+  extern __shared__ __align__(16) float aks_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp & 1, split = warp >> 1;
+  float* Ks = aks_smem + (size_t)split * (2 * AKS_KT * DH);       // [AKS_KT][DH] of this split
+  float* Vs = Ks + AKS_KT * DH;                                    // [AKS_KT][DH]
+  float* Ss = aks_smem + (size_t)AKS_SPLITS * (2 * AKS_KT * DH) + (size_t)warp * (AKS_KT * 33);   // [AKS_KT][33]
+  float* Mg = aks_smem;                                            // merge area (reuses the K / V tiles): [split][64][MP]
+  const int dh4 = p.dh >> 2;
+  const int qchunks = (p.Lq + 63) / 64;
+  const int per_split = (((p.Lk + AKS_SPLITS - 1) / AKS_SPLITS) + AKS_KT - 1) / AKS_KT * AKS_KT;   // keys per split, tile multiple
+  const long long nblocks = (long long)p.B * p.H * qchunks;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int qc = (int)(blk % qchunks);
+    const int h = (int)((blk / qchunks) % p.H);
+    const int b = (int)(blk / ((long long)qchunks * p.H));
+    const float* qp = p.q + b * p.q_sb + h * p.dh;
+    const float* kp = p.k + b * p.k_sb + h * p.dh;
+    const float* vp = p.v + b * p.v_sb + h * p.dh;
+    const int qi = qc * 64 + grp * 32 + lane;
+    const bool active = qi < p.Lq;
+    float4 q4[DH4];
+#pragma unroll
+    for (int t = 0; t < DH4; ++t) {
+      q4[t] = (active && t < dh4) ? __ldg(reinterpret_cast<const float4*>(qp + (long long)qi * p.q_si) + t)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      q4[t].x *= p.scale; q4[t].y *= p.scale; q4[t].z *= p.scale; q4[t].w *= p.scale;
+    }
+    float4 acc[DH4];
+#pragma unroll
+    for (int t = 0; t < DH4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float mrun = -INFINITY, lrun = 0.f;
+    for (int t0 = 0; t0 < per_split; t0 += AKS_KT) {
+      __syncthreads();                                 // previous tiles (or the previous block's merge area) consumed
+      // stage tile t0 of every split: 4 x [AKS_KT][DH] of K and of V, all 256 threads
+      for (int e = threadIdx.x; e < AKS_SPLITS * AKS_KT * DH4; e += blockDim.x) {
+        const int sp = e / (AKS_KT * DH4), r = (e / DH4) % AKS_KT, t = e % DH4;
+        const int key = sp * per_split + t0 + r;
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (key < p.Lk && key < (sp + 1) * per_split && t < dh4) {
+          kk = __ldg(reinterpret_cast<const float4*>(kp + (long long)key * p.k_si) + t);
+          vv = __ldg(reinterpret_cast<const float4*>(vp + (long long)key * p.v_si) + t);
+        }
+        float* dstk = aks_smem + (size_t)sp * (2 * AKS_KT * DH);
+        reinterpret_cast<float4*>(dstk)[r * DH4 + t] = kk;
+        reinterpret_cast<float4*>(dstk + AKS_KT * DH)[r * DH4 + t] = vv;
+      }
+      __syncthreads();
+      const int nk = max(0, min(AKS_KT, min(p.Lk, (split + 1) * per_split) - (split * per_split + t0)));   // warp-uniform
+      if (nk > 0) {
+        float mx = mrun;
+        for (int j = 0; j < nk; ++j) {
+          const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
+          float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;
+#pragma unroll
+          for (int t = 0; t < DH4; ++t) {
+            const float4 kk = kr[t];
+            sx = fmaf(q4[t].x, kk.x, sx); sy = fmaf(q4[t].y, kk.y, sy); sz = fmaf(q4[t].z, kk.z, sz); sw = fmaf(q4[t].w, kk.w, sw);
+          }
+          const float sc = (sx + sy) + (sz + sw);
+          Ss[j * 33 + lane] = sc;
+          mx = fmaxf(mx, sc);
+        }
+        const float corr = expf(mrun - mx);            // 0 on the first tile (mrun = -inf)
+        lrun *= corr;
+#pragma unroll
+        for (int t = 0; t < DH4; ++t) { acc[t].x *= corr; acc[t].y *= corr; acc[t].z *= corr; acc[t].w *= corr; }
+        mrun = mx;
+        for (int j = 0; j < nk; ++j) {
+          const float pj = expf(Ss[j * 33 + lane] - mx);
+          lrun += pj;
+          const float4* vr = reinterpret_cast<const float4*>(Vs + j * DH);
+#pragma unroll
+          for (int t = 0; t < DH4; ++t) {
+            const float4 vv = vr[t];
+            acc[t].x = fmaf(pj, vv.x, acc[t].x); acc[t].y = fmaf(pj, vv.y, acc[t].y);
+            acc[t].z = fmaf(pj, vv.z, acc[t].z); acc[t].w = fmaf(pj, vv.w, acc[t].w);
+          }
+        }
+      }
+    }
+    __syncthreads();                                   // all tiles consumed: the K / V area becomes the merge area
+    {
+      float* mine = Mg + ((size_t)split * 64 + grp * 32 + lane) * MP;
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) *reinterpret_cast<float4*>(mine + 4 * t) = acc[t];
+      mine[DH] = mrun;
+      mine[DH + 1] = lrun;
+    }
+    __syncthreads();
+    if (split == 0) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int sp = 0; sp < AKS_SPLITS; ++sp) M = fmaxf(M, Mg[((size_t)sp * 64 + grp * 32 + lane) * MP + DH]);
+      float L = 0.f;
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int sp = 0; sp < AKS_SPLITS; ++sp) {
+        const float* o = Mg + ((size_t)sp * 64 + grp * 32 + lane) * MP;
+        const float w = expf(o[DH] - M);              // 0 for a split that saw no key (m = -inf)
+        L = fmaf(o[DH + 1], w, L);
+#pragma unroll
+        for (int t = 0; t < DH4; ++t) {
+          const float4 a = *reinterpret_cast<const float4*>(o + 4 * t);
+          acc[t].x = fmaf(a.x, w, acc[t].x); acc[t].y = fmaf(a.y, w, acc[t].y);
+          acc[t].z = fmaf(a.z, w, acc[t].z); acc[t].w = fmaf(a.w, w, acc[t].w);
+        }
+      }
+      const float inv = 1.f / L;
+      __syncwarp();
+      float* Os = Mg + ((size_t)grp * 32) * MP;     // this group's split-0 rows, now free: output staging
+#pragma unroll
+      for (int t = 0; t < DH4; ++t)
+        *reinterpret_cast<float4*>(Os + lane * MP + 4 * t) = make_float4(acc[t].x * inv, acc[t].y * inv, acc[t].z * inv, acc[t].w * inv);
+      __syncwarp();
+      const int q0w = qc * 64 + grp * 32;
+      const int nqw = min(32, p.Lq - q0w);
+      for (int e = lane; e < nqw * p.dh; e += 32) {
+        const int i = e / p.dh, d = e - i * p.dh;
+        store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)(q0w + i) * p.o_si + h * p.dh + d, Os[i * MP + d], p.np);
+      }
+    }
+  }
+}
+
 // y = a + b (elementwise, float32, contiguous) -- the "tokens + init_tokens" before the flow head, written as planes
 __global__ void __launch_bounds__(256) add_planes_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                           __nv_bfloat16* __restrict__ planes, long long plane_stride, int np,
@@ -481,6 +615,23 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
     else COMET_ATR_LAUNCH(16);
 #undef COMET_ATR_LAUNCH
     return launch_status("attention_rows_kernel");
+  }
+  if (Lk > ATR_KMAX && (long long)B * H * ((Lq + 63) / 64) <= 148LL * 4) {
+    long long nb = (long long)B * H * ((Lq + 63) / 64);
+#define COMET_AKS_LAUNCH(D4)                                                                                       \
+  do {                                                                                                             \
+    const int smem = (AKS_SPLITS * 2 * AKS_KT * 4 * D4 + 8 * AKS_KT * 33) * (int)sizeof(float);                    \
+    if (smem > 48 * 1024)                                                                                          \
+      COMET_CUDA(cudaFuncSetAttribute(attention_ksplit_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    attention_ksplit_kernel<D4><<<(unsigned)nb, 256, smem, (cudaStream_t)stream>>>(p);                             \
+  } while (0)
+    if (dh <= 4) COMET_AKS_LAUNCH(1);
+    else if (dh <= 16) COMET_AKS_LAUNCH(4);
+    else if (dh <= 32) COMET_AKS_LAUNCH(8);
+    else if (dh <= 48) COMET_AKS_LAUNCH(12);
+    else COMET_AKS_LAUNCH(16);
+#undef COMET_AKS_LAUNCH
+    return launch_status("attention_ksplit_kernel");
   }
   long long blocks = (long long)B * H * ((Lq + ATT_QB - 1) / ATT_QB);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
