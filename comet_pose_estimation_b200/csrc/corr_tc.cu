@@ -60,6 +60,9 @@ constexpr int MAX_WR = 9;      // 2*4+1
 #ifndef COMET_TC_PDL
 #define COMET_TC_PDL 1
 #endif
+#ifndef COMET_TC_L2PF
+#define COMET_TC_L2PF 0        // tiles the producer's L2 prefetch runs ahead of the operand ring (0: off)
+#endif
 constexpr int THREADS = 320;   // 10 warps: TMA | MMA | 4 epilogue | 4 stager
 
 // tensor-memory map (all 512 columns of the SM are allocated, so the base address is 0)
@@ -79,7 +82,9 @@ constexpr int WIN_WARP = 2740;                  // 83 * 33 = 2739 floats, rounde
 constexpr int WIN_BYTES = 4 * WIN_WARP * 4;
 constexpr int NWIN = 2;                         // window buffers (epilogue -> stager hand-off)
 constexpr int ROWOFF_BYTES = 2 * TILE_M * 8;      // per query: element offset of its pos_emb row and of its output row
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + DUMP_BYTES + NWIN * WIN_BYTES + ROWOFF_BYTES + 512;
+constexpr int META_JOB = TILE_M + 8;                 // int4 per prefetched job: one slot per query + the record, one copy per warp
+constexpr int META_BYTES = 2 * META_JOB * 16;        // epilogue prefetch, two jobs deep
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + DUMP_BYTES + NWIN * WIN_BYTES + ROWOFF_BYTES + META_BYTES + 512;
 
 __host__ __device__ inline int level_offset(int l) { return l == 0 ? 0 : l == 1 ? 4096 : l == 2 ? 5120 : l == 3 ? 5376 : 5440; }
 __host__ __device__ inline int num_tiles(int L) { return L == 1 ? 64 : L == 2 ? 80 : L == 3 ? 84 : L == 4 ? 85 : 86; }
@@ -125,17 +130,20 @@ struct Params {
   const float* coords;  long long c_sb, c_ss, c_sn;
   float* out;           long long o_sb, o_ss, o_sn;   // lookup layout (B,S,N,L*Wr*Wr) when !tokens
   const float* pos; int D_tok; int tokens;            // token layout (B,N,S,D_tok) when tokens
+  int vec4;                                           // tokens: rows of out / pos are 16-byte aligned (float4 token_misc path)
+  int red;                                            // tokens: windows are ADDED to the rows (MODE_REDUCE); tc_pre_kernel writes pos_emb there
   float* vol[5]; int volume_mode;                      // volume mode: per-level (BS,N,H_l,W_l)
   int B, S, N, L, r, npass, bf16;
   int BS, mtiles, npad, nsplit, npyr, nchunk, njobs;
   const uint8_t* split; // packed pyramid (tile-major, pre-swizzled bf16 hi/lo), written by tc_prepare_kernel
   const int* perm;      // [BS][npad]: query index of sorted slot (or -1), written by tc_plan_kernel
+  const int4* slots;    // [BS][npad]: {query index or -1, bits of x, bits of y, 0} of the sorted slot (epilogue prefetch)
   const JobRec* jobs;   // [njobs]
   float inv_sqrt_c;
   int* status;  // device int: set non-zero by the watchdog
 #ifdef COMET_TC_TRACE
   int debug;    // COMET_TC_DEBUG bit mask (attribution experiments)
-  long long* stamps;  // optional clock64 trace of CTA 0: [4 roles][64][2]
+  long long* stamps;  // optional clock64 trace of CTA 0: [3 roles][64][2] + stager [8 jobs][16][2]
 #endif
 };
 
@@ -177,6 +185,15 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P1;\n\t}"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
@@ -271,13 +288,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf16_resid(float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); }
 
+// Loads whose ISSUE POINT matters (software prefetch across an mbarrier wait): `__ldg` is an invariant load that the
+// compiler may sink to its first use -- i.e. behind the wait it was meant to overlap; a volatile asm statement keeps its
+// order relative to the other volatile asm statements (the mbarrier waits and arrives).
+__device__ __forceinline__ float ldg_pin(const float* ptr) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ int ldg_pin(const int* ptr) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ int4 ldg_pin(const int4* ptr) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
+// Shared-memory accesses by 32-bit address.  The "memory" clobber orders them against the plain C++ accesses of the
+// same buffers; volatile keeps the loads of one row together, ahead of the arithmetic that consumes them.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "@p st.shared.f32 [%0], %1;\n\t}"
+      ::"r"(addr), "f"(v), "r"(pred) : "memory");
+}
+
 __device__ __forceinline__ JobRec load_job(const Params& p, int job) {
   JobRec r;
   if (job < p.njobs) {
     const int4* s = reinterpret_cast<const int4*>(p.jobs + job);
     int4* d = reinterpret_cast<int4*>(&r);
-    d[0] = __ldg(s);
-    d[1] = __ldg(s + 1);
+    d[0] = ldg_pin(s);
+    d[1] = ldg_pin(s + 1);
   } else {
     r.bs = 0; r.mnf = 0; r.t0p = 0; r.t1p = 0; r.own_lo = 0; r.own_hi = 0; r.pad0 = 0; r.pad1 = 0;
   }
@@ -286,7 +337,7 @@ __device__ __forceinline__ JobRec load_job(const Params& p, int job) {
 
 __device__ __forceinline__ void stamp(const Params& p, int role, int idx, int which) {
 #ifdef COMET_TC_TRACE
-  if (p.stamps && blockIdx.x == 0 && idx < 64) p.stamps[(role * 64 + idx) * 2 + which] = clock64();
+  if (p.stamps && blockIdx.x == 0 && idx < (role == 3 ? 128 : 64)) p.stamps[(role * 64 + idx) * 2 + which] = clock64();
 #endif
 }
 
@@ -313,6 +364,7 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
   const int b = bs / p.S, s = bs - b * p.S;
   const int Wr = 2 * p.r + 1;
   int* myperm = perm + (long long)bs * p.npad;
+  int4* myslots = const_cast<int4*>(p.slots) + (long long)bs * p.npad;
   const bool track = p.mtiles <= PLAN_MAX_MT;  // else: sorted, but every job covers the full maps
 
   for (int i = threadIdx.x; i < PLAN_BINS; i += blockDim.x) hist[i] = 0;
@@ -321,7 +373,15 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
   __syncthreads();
 
   if (full) {
-    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) myperm[i] = i < p.N ? i : -1;
+    for (int i = threadIdx.x; i < p.npad; i += blockDim.x) {
+      myperm[i] = i < p.N ? i : -1;
+      float cx = 0.f, cy = 0.f;
+      if (i < p.N && p.coords) {
+        const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)i * p.c_sn;
+        cx = __ldg(cp); cy = __ldg(cp + 1);
+      }
+      myslots[i] = make_int4(i < p.N ? i : -1, __float_as_int(cx), __float_as_int(cy), 0);
+    }
   } else {
     const float* cbase = p.coords + b * p.c_sb + s * p.c_ss + 1;
     for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
@@ -340,6 +400,7 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
       const int key = min(max((int)floorf(fminf(fmaxf(cy, -1.0e6f), 1.0e6f)), -16), PLAN_BINS - 17) + 16;
       const int slot = atomicAdd(&hist[key], 1);
       myperm[slot] = n;
+      myslots[slot] = make_int4(n, __float_as_int(__ldg(cbase - 1 + (long long)n * p.c_sn)), __float_as_int(cy), 0);
       if (track) {
         const int mt = slot >> 7;
         for (int l = 0; l < p.L; ++l) {
@@ -350,7 +411,7 @@ __device__ __forceinline__ void plan_frame(const Params& p, int* __restrict__ pe
         }
       }
     }
-    for (int i = p.N + threadIdx.x; i < p.npad; i += blockDim.x) myperm[i] = -1;
+    for (int i = p.N + threadIdx.x; i < p.npad; i += blockDim.x) { myperm[i] = -1; myslots[i] = make_int4(-1, 0, 0, 0); }
   }
   __syncthreads();
 
@@ -440,6 +501,80 @@ __device__ __forceinline__ void token_misc_rows(const Params& p, long long warp_
   }
 }
 
+// The same rows with 16-byte accesses (token rows and position-embedding rows 16-byte aligned, D_tok % 4 == 0): a lane
+// owns whole float4 groups of the row -- all its position-embedding loads are issued before the first use, one sincosf
+// serves a (sin, cos) channel pair, and the row is written with STG.128.  Groups that lie entirely inside the window
+// channels are skipped unless p.red (then they receive the position embedding the bulk reductions add to).
+__device__ __forceinline__ void token_misc_rows_v4(const Params& p, long long warp_id, long long nwarps, int lane,
+                                                   float* feat_row) {
+  const int WW = (2 * p.r + 1) * (2 * p.r + 1);
+  const int Ce = KC >> 1;
+  const float step = 1000.0f / (float)Ce;
+  const int feat_off = KC + 2 + p.L * WW;
+  const int nv = p.D_tok >> 2;
+  const int f_lo = (KC + 2 + 3) >> 2, f_hi = feat_off >> 2;   // float4 groups [f_lo, f_hi) hold window channels only
+  const long long rows = (long long)p.B * p.N * p.S;
+  constexpr int T = 6;                                        // groups per lane and pass (D_tok <= 768 in one pass)
+  for (long long row = warp_id; row < rows; row += nwarps) {
+    const int s = (int)(row % p.S);
+    const long long bn = row / p.S;
+    const int n = (int)(bn % p.N), b = (int)(bn / p.N);
+    const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)n * p.c_sn;
+    const float* c0 = p.coords + b * p.c_sb + (long long)n * p.c_sn;  // frame 0
+    const float cx1 = __ldg(cp), cy1 = __ldg(cp + 1), cx0 = __ldg(c0), cy0 = __ldg(c0 + 1);
+    const float4* pq = reinterpret_cast<const float4*>(p.pos + bn * p.D_tok);
+    const float* tq = p.targets + b * p.t_sb + s * p.t_ss + (long long)n * p.t_sn;
+    float* o = p.out + row * p.D_tok;
+    for (int k0 = 0; k0 < nv; k0 += 32 * T) {
+      // every load of the row is issued before the first use: one memory round trip per row and warp.  The track
+      // features sit at an arbitrary 4-byte phase of the token row: they pass through a per-warp shared-memory row.
+      float4 pe[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int k = k0 + lane + 32 * t;
+        const bool need = k < nv && (p.red || k < f_lo || k >= f_hi);
+        pe[t] = need ? __ldg(pq + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (k0 == 0) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tq) + lane);   // KC = 128 floats = 32 lanes x float4
+        __syncwarp();
+        *reinterpret_cast<float4*>(feat_row + 4 * lane) = t4;
+        __syncwarp();
+      }
+      const float flx = cx1 - cx0, fly = cy1 - cy0;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int k = k0 + lane + 32 * t;
+        if (k >= nv || !(p.red || k < f_lo || k >= f_hi)) continue;
+        const int c = 4 * k;
+        float v[4];
+        if (c + 3 < KC) {
+          const int axis = c / Ce, w = c - axis * Ce;   // w is a multiple of 4: channels (sin, cos) of w and of w + 2
+          const float f = axis ? fly : flx;
+          sincosf(__fmul_rn(f, (float)w * step), &v[0], &v[1]);
+          sincosf(__fmul_rn(f, (float)(w + 2) * step), &v[2], &v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cj = c + j;
+            v[j] = (cj >= KC && cj < KC + 2) ? (cj == KC ? flx : fly)
+                 : (cj >= feat_off && cj < feat_off + KC) ? feat_row[cj - feat_off] : 0.f;
+          }
+        }
+        const float4 r = make_float4(v[0] + pe[t].x, v[1] + pe[t].y, v[2] + pe[t].z, v[3] + pe[t].w);
+        if (p.red || c + 3 < KC + 2 || c >= feat_off) {
+          *reinterpret_cast<float4*>(o + c) = r;
+        } else {   // a group shared with window channels the tensor kernel stores itself
+          const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < KC + 2 || c + j >= feat_off) o[c + j] = rr[j];
+        }
+      }
+    }
+  }
+}
+
 // Launch 1 of 2 per call: CTAs [0, BS) plan one frame each, the rest write the correlation-independent token channels.
 __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __restrict__ perm, JobRec* __restrict__ jobs,
                                                       int full) {
@@ -447,7 +582,10 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
     plan_frame(p, perm, jobs, full, blockIdx.x);
   } else {
     const long long nw = (long long)(gridDim.x - p.BS) * 8;
-    token_misc_rows(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
+    __shared__ __align__(16) float feat_rows[8][KC];
+    if (p.vec4) token_misc_rows_v4(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31,
+                                   feat_rows[threadIdx.x >> 5]);
+    else token_misc_rows(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
   }
   // programmatic dependent launch: once every CTA of this grid got here the tensor kernel may be scheduled, so its
   // prologue overlaps this grid's drain; it waits for this grid's completion (griddepcontrol.wait) before it reads
@@ -470,9 +608,21 @@ __global__ void __launch_bounds__(128, 1) tc_misc_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int R, bool BF16, bool VOLUME>
+// MODE_STORE: windows (+ position embedding) written with plain stores by the stager warps -- the lookup layout
+// (B,S,N,L*Wr*Wr), and token rows whose base / pitch are not 16-byte aligned.  MODE_VOLUME: the raw volume.
+// MODE_REDUCE (token rows): tc_pre_kernel has already written the position embedding into the window channels; the
+// epilogue stages each query's window as one 16-byte aligned row [a | Wr*Wr entries | zeros] and ONE lane per query
+// adds it to the token row with a bulk reduction (cp.reduce.async.bulk .add.f32, executed by the TMA unit and the L2):
+// the ~1400 instructions per window unit that the stores cost a stager warp (scalar LDS + FADD + predicated STG per
+// entry, the stager's critical path in the pyramid jobs) become ~20.  Entries a job does not own are zero in the staged
+// row, so the level-0 row chunks of one query simply add up.
+constexpr int MODE_STORE = 0, MODE_VOLUME = 1, MODE_REDUCE = 2;
+
+template <int R, bool BF16, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 corr_tc_kernel(const Params p) {
+  constexpr bool VOLUME = MODE == MODE_VOLUME;
+  constexpr bool RED = MODE == MODE_REDUCE;
   // dynamic shared memory is the only shared allocation of this kernel, so it starts 1024-byte aligned (SWIZZLE_128B
   // tiles need that); no integer round trip on the pointer, so that accesses stay LDS/STS rather than generic LD/ST
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -480,7 +630,8 @@ corr_tc_kernel(const Params p) {
   float* dump = reinterpret_cast<float*>(sB + NSTAGE * STAGE_BYTES);   // private accumulator rows
   float* win = dump + TILE_M * DUMP_STRIDE;                            // staged window rows
   long long* rowoff = reinterpret_cast<long long*>(win + NWIN * 4 * WIN_WARP);  // [2][TILE_M]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowoff + 2 * TILE_M);
+  int4* meta = reinterpret_cast<int4*>(rowoff + 2 * TILE_M);           // [2][TILE_M slots | 4 warps x 2 int4 job record]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + META_BYTES / 16);
   uint64_t* full = bars;                  // [NSTAGE]  TMA -> MMA
   uint64_t* empty = full + NSTAGE;        // [NSTAGE]  MMA -> TMA
   uint64_t* acc_full = empty + NSTAGE;    // [NACC]    MMA -> epilogue
@@ -518,30 +669,61 @@ corr_tc_kernel(const Params p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // Two cursors over the CTA's tile sequence: the load cursor feeds the 3-stage ring; the prefetch cursor runs
+    // COMET_TC_L2PF tiles ahead of it and only asks the L2 for the tile (cp.async.bulk.prefetch.L2), so that the ring's
+    // bulk copies hit in L2 -- the ring alone (96 KB in flight) covers ~2 tiles of MMA time, less than a DRAM round trip.
     if (elect_one()) {
+      struct Cursor {
+        JobRec cur, nxt;
+        int job, sg, t, te;
+      };
+      const int G = gridDim.x;
+      auto cursor_init = [&](Cursor& c) {
+        c.job = blockIdx.x;
+        c.cur = load_job(p, c.job);
+        c.nxt = load_job(p, c.job + G);
+        c.sg = 0; c.t = c.cur.t0(0); c.te = c.cur.t1(0);
+      };
+      auto cursor_next = [&](Cursor& c) {   // precondition: c.job < p.njobs
+        if (++c.t < c.te) return;
+        if (++c.sg < c.cur.nseg()) { c.t = c.cur.t0(c.sg); c.te = c.cur.t1(c.sg); return; }
+        c.job += G;
+        c.cur = c.nxt;
+        c.nxt = load_job(p, c.job + G);
+        c.sg = 0; c.t = c.cur.t0(0); c.te = c.cur.t1(0);
+      };
+      const uint32_t nbytes = BF16 ? B_TILE_BYTES : STAGE_BYTES;   // autocast mode issues hi x hi only: fetch the hi half
       uint32_t stage = 0, phase = 0;
       int tcount = 0;
-      JobRec nxt = load_job(p, blockIdx.x);
-      for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
-        const JobRec jr = nxt;
-        nxt = load_job(p, job + gridDim.x);   // record of the next job: in flight while this one streams
-        const int nseg = jr.nseg();
-        for (int sg = 0; sg < nseg; ++sg) {
-          for (int t = jr.t0(sg), te = jr.t1(sg); t < te; ++t) {
-            mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
-            stamp(p, 0, tcount++, 0);
-            uint8_t* dst = sB + stage * STAGE_BYTES;
-            if (TC_DBG(p, 64)) {
-              mbar_arrive(&full[stage]);
-            } else {
-              // autocast mode issues the hi x hi pass only: fetch just the hi half of the stage
-              const uint32_t nbytes = BF16 ? B_TILE_BYTES : STAGE_BYTES;
-              mbar_expect_tx(&full[stage], nbytes);
-              bulk_load(dst, p.split + ((long long)jr.bs * NTILES + t) * STAGE_BYTES, nbytes, &full[stage]);
-            }
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
+      Cursor ld;
+      cursor_init(ld);
+#if COMET_TC_L2PF > 0
+      Cursor pf = ld;
+      auto prefetch = [&]() {
+        if (pf.job < p.njobs) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                       ::"l"(p.split + ((long long)pf.cur.bs * NTILES + pf.t) * STAGE_BYTES), "r"(nbytes) : "memory");
+          cursor_next(pf);
         }
+      };
+      if (pf.job < p.njobs) cursor_next(pf);   // the very first tile goes straight to shared memory
+      for (int i = 0; i < COMET_TC_L2PF; ++i) prefetch();
+#endif
+      while (ld.job < p.njobs) {
+        mbar_wait(&empty[stage], phase ^ 1, p.status, 1);
+        stamp(p, 0, tcount++, 0);
+        uint8_t* dst = sB + stage * STAGE_BYTES;
+        if (TC_DBG(p, 64)) {
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_expect_tx(&full[stage], nbytes);
+          bulk_load(dst, p.split + ((long long)ld.cur.bs * NTILES + ld.t) * STAGE_BYTES, nbytes, &full[stage]);
+        }
+#if COMET_TC_L2PF > 0
+        prefetch();
+#endif
+        cursor_next(ld);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -600,35 +782,52 @@ corr_tc_kernel(const Params p) {
     const int wq = warp & 3;                    // TMEM lane quarter this warp may access
     const int q = 32 * wq + lane;               // TMEM lane == sorted query slot in the tile
     float* myrow = dump + q * DUMP_STRIDE;
+    const uint32_t myrow_u32 = smem_u32(myrow);
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
     constexpr int Wr = 2 * R + 1;
+    constexpr int RW = ((Wr * Wr + 6) / 4) * 4;   // floats per staged row in RED mode (<= 3 leading + Wr*Wr, 16-byte multiple)
+    constexpr int EI = RED ? Wr : Wr * WIN_LD;    // float stride between window columns i in the staged window
+    constexpr int EJ = RED ? 1 : WIN_LD;          // ... between window rows j
     uint32_t acc = 0, acc_phase = 0, wu = 0;  // wu: window units handed to the stager so far
     int tcount = 0;
     float* wcol = win + lane;                 // this lane's column of the warp's staged window: entry e at wcol[e * WIN_LD]
     float* wwarp = win;
 
-    // software pipeline over jobs: the record of job i+2 and the query (slot -> index -> coordinates) of job i+1 are
-    // fetched while job i is processed, so no dependent global load sits between two jobs
-    auto fetch_query = [&](const JobRec& r, bool in_range, int& n_, float& cx_, float& cy_) {
-      n_ = -1; cx_ = 0.f; cy_ = 0.f;
-      if (in_range) {
-        n_ = __ldg(p.perm + (long long)r.bs * p.npad + r.mt() * TILE_M + q);
-        if (n_ >= 0 && p.coords) {
-          const int b_ = r.bs / p.S, s_ = r.bs - b_ * p.S;
-          const float* cp = p.coords + b_ * p.c_sb + s_ * p.c_ss + (long long)n_ * p.c_sn;
-          cx_ = __ldg(cp);
-          cy_ = __ldg(cp + 1);
-        }
+    // Job metadata is prefetched into shared memory with cp.async, two jobs deep: the sorted slot of this lane (query
+    // index + coordinates, written by the plan kernel) and the job record.  Its address follows from the job NUMBER
+    // (jobs are laid out [frame][query tile][chunk]), so nothing in the chain is a dependent load, and no register
+    // carries prefetched data across a job (the register version spilled them -- and waited for the loads to do so).
+    const int G = gridDim.x;
+    auto prefetch_job = [&](int job, int buf) {
+      if (job < p.njobs) {
+        const int fq = job / p.nchunk;            // frame * mtiles + query tile
+        const uint32_t dst = smem_u32(meta + buf * META_JOB);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"(dst + (uint32_t)q * 16u), "l"(p.slots + (long long)fq * TILE_M + q) : "memory");
+        if (lane < 2)   // every warp keeps its own copy of the record: no synchronisation between the epilogue warps
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                       ::"r"(dst + (uint32_t)(TILE_M + 2 * wq + lane) * 16u),
+                         "l"(reinterpret_cast<const int4*>(p.jobs + job) + lane) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    JobRec jr = load_job(p, blockIdx.x);
-    JobRec jr1 = load_job(p, blockIdx.x + gridDim.x);
-    int n, n1;
-    float cx, cy, cx1, cy1;
-    fetch_query(jr, (int)blockIdx.x < p.njobs, n, cx, cy);
-    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x) {
-      const JobRec jr2 = load_job(p, job + 2 * gridDim.x);
-      fetch_query(jr1, job + (int)gridDim.x < p.njobs, n1, cx1, cy1);
+    prefetch_job(blockIdx.x, 0);
+    prefetch_job(blockIdx.x + G, 1);
+    uint32_t jseq = 0;
+    for (int job = blockIdx.x; job < p.njobs; job += G, ++jseq) {
+      const int mbuf = jseq & 1;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this job's group has landed (the next one may be in flight)
+      __syncwarp();                                           // the record was fetched by lanes 0 and 1
+      const int4* mb = meta + mbuf * META_JOB;
+      JobRec jr;
+      {
+        const int4 r0 = mb[TILE_M + 2 * wq], r1 = mb[TILE_M + 2 * wq + 1];
+        jr.bs = r0.x; jr.mnf = r0.y; jr.t0p = (uint32_t)r0.z; jr.t1p = (uint32_t)r0.w;
+        jr.own_lo = r1.x; jr.own_hi = r1.y; jr.pad0 = 0; jr.pad1 = 0;
+      }
+      const int4 slot = mb[q];
+      const int n = slot.x;
+      const float cx = __int_as_float(slot.y), cy = __int_as_float(slot.z);
       const int bs = jr.bs;
       const bool valid = n >= 0;
       const int nseg = jr.nseg();
@@ -651,6 +850,7 @@ corr_tc_kernel(const Params p) {
         }
         // x window: clamped column offsets; lerp weights with the zero-padding mask (and, in fp32 mode, the scale)
         int xo[Wr + 1];
+        uint32_t xo4[Wr + 1];
         float wa[Wr], wb[Wr];
         uint32_t xmask = 0, dmask = 0;
 #pragma unroll
@@ -658,6 +858,7 @@ corr_tc_kernel(const Params p) {
           const int xi = x0 + i;
           if (xi >= 0 && xi < Wl) xmask |= 1u << i;
           xo[i] = min(max(xi, 0), Wl - 1);
+          xo4[i] = (uint32_t)xo[i] * 4u;
         }
         // map rows this query touches; a window that misses the map (in x or in y) touches none -- such a lane never
         // reads its parked row (a clamped offset could otherwise hit stale shared memory)
@@ -681,12 +882,16 @@ corr_tc_kernel(const Params p) {
         float hprev[Wr];
 #pragma unroll
         for (int i = 0; i < Wr; ++i) hprev[i] = 0.f;
+        const float gy = 1.f - fy;
         if (!VOLUME && !TC_DBG(p, 1)) {
           // claim a window buffer and clear it cooperatively (entries whose rows are off the map stay 0)
           const uint32_t wbuf = wu % NWIN;
+          if (warp == 2 && lane == 0) stamp(p, 5, 2 * wu, 0);
           mbar_wait(&win_empty[wbuf * 4 + wq], ((wu / NWIN) & 1) ^ 1, p.status, 7);
+          if (warp == 2 && lane == 0) stamp(p, 5, 2 * wu, 1);
           wwarp = win + (wbuf * 4 + wq) * WIN_WARP;
-          wcol = wwarp + lane;
+          // RED: this lane's row, shifted so that entry 0 lands on the 16-byte phase of its token channel
+          wcol = RED ? wwarp + lane * RW + ((KC + 2 + level * Wr * Wr) & 3) : wwarp + lane;
 #pragma unroll 1
           for (int k = lane * 4; k < WIN_WARP; k += 128) *reinterpret_cast<float4*>(wwarp + k) = make_float4(0.f, 0.f, 0.f, 0.f);
           __syncwarp();
@@ -751,34 +956,49 @@ corr_tc_kernel(const Params p) {
             }
           }
           // ---- stream the map rows of this tile ----
-#pragma unroll 1
-          for (int rr = 0; rr < ti.rows; ++rr) {
-            const int y = ti.y_first + rr;
+          // Branch-free per row: all Wr+1 loads of a row are issued before the first use (explicit shared-memory
+          // addresses, so no generic-pointer conversion inside the loop), rows come in pairs where the tile has them
+          // (two loads batches in flight), and the window entries are written with predicated stores.  A row's values
+          // are only ever written for lanes whose window contains it (see the predicate), so rows a lane did not park
+          // may be read (stale, never stored).
+          const uint32_t wcol_u32 = smem_u32(wcol);
+          auto load_row = [&](int rr, float (&vv)[Wr + 1]) {
+            const uint32_t base = myrow_u32 + (uint32_t)(rr * Wl) * 4u;
+#pragma unroll
+            for (int i = 0; i <= Wr; ++i) vv[i] = lds_f32(base + xo4[i]);
+          };
+          auto finish_row = [&](int y, float (&vv)[Wr + 1]) {
+            if (BF16) {
+              // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
+#pragma unroll
+              for (int i = 0; i <= Wr; ++i) vv[i] = round_bf16(round_bf16(vv[i]) * p.inv_sqrt_c);
+            }
             float h[Wr];
-            if (y >= rl && y <= rh) {
-              const float* row = myrow + rr * Wl;
-              float vv[Wr + 1];
 #pragma unroll
-              for (int i = 0; i <= Wr; ++i) vv[i] = row[xo[i]];
-              if (BF16) {
-                // blocks.py:428 scales the volume after the matmul; under autocast both steps round to bf16
-#pragma unroll
-                for (int i = 0; i <= Wr; ++i) vv[i] = round_bf16(round_bf16(vv[i]) * p.inv_sqrt_c);
-              }
-#pragma unroll
-              for (int i = 0; i < Wr; ++i) h[i] = wa[i] * vv[i] + wb[i] * vv[i + 1];
-            } else {
-#pragma unroll
-              for (int i = 0; i < Wr; ++i) h[i] = 0.f;
-            }
+            for (int i = 0; i < Wr; ++i) h[i] = wa[i] * vv[i] + wb[i] * vv[i + 1];
             const int top = y - 1, j = top - y0;
-            if (j >= 0 && j < Wr && top >= ta && top <= tb_ && valid) {
-              float* wdst = wcol + j * WIN_LD;
+            const uint32_t ok = (j >= 0 && j < Wr && top >= ta && top <= tb_ && rl <= rh) ? 1u : 0u;
+            const uint32_t wd = wcol_u32 + (uint32_t)(min(max(j, 0), Wr - 1) * EJ) * 4u;
 #pragma unroll
-              for (int i = 0; i < Wr; ++i) wdst[i * Wr * WIN_LD] = (1.f - fy) * hprev[i] + fy * h[i];
-            }
+            for (int i = 0; i < Wr; ++i) sts_f32_if(wd + (uint32_t)(i * EI) * 4u, gy * hprev[i] + fy * h[i], ok);
 #pragma unroll
             for (int i = 0; i < Wr; ++i) hprev[i] = h[i];
+          };
+          {
+            int rr = 0;
+#pragma unroll 1
+            for (; rr + 1 < ti.rows; rr += 2) {
+              float va[Wr + 1], vb[Wr + 1];
+              load_row(rr, va);
+              load_row(rr + 1, vb);
+              finish_row(ti.y_first + rr, va);
+              finish_row(ti.y_first + rr + 1, vb);
+            }
+            if (rr < ti.rows) {
+              float va[Wr + 1];
+              load_row(rr, va);
+              finish_row(ti.y_first + rr, va);
+            }
           }
         }
 
@@ -789,26 +1009,33 @@ corr_tc_kernel(const Params p) {
           if (last && valid) {
             const int jb = (Hl - 1) - y0;  // top = H-1: its bottom row is off the map (hprev is row H-1: jb in range
                                            // means this query touches row H-1, so its warp streamed up to it)
-            if (jb >= 0 && jb < Wr) {
-              float* wdst = wcol + jb * WIN_LD;
+            if (jb >= 0 && jb < Wr && rl <= rh) {
+              float* wdst = wcol + jb * EJ;
 #pragma unroll
-              for (int i = 0; i < Wr; ++i) wdst[i * Wr * WIN_LD] = (1.f - fy) * hprev[i];
+              for (int i = 0; i < Wr; ++i) wdst[i * EI] = (1.f - fy) * hprev[i];
             }
           }
           // window rows (index j) this job owns: tops in [lo_top, hi_top]
           const int lo_top = is0 ? jr.own_lo : -BIG;
           const int hi_top = is0 ? jr.own_hi : BIG;
-          const int j_lo = valid ? max(0, lo_top - y0) : 1, j_hi = valid ? min(Wr - 1, hi_top - y0) : 0;
-          wcol[WIN_JLO * WIN_LD] = __int_as_float(j_lo);
-          wcol[WIN_JHI * WIN_LD] = __int_as_float(j_hi);
+          if (RED) {
+            // the TMA unit (async proxy) reads these rows: make this lane's generic-proxy writes visible to it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          } else {
+            const int j_lo = valid ? max(0, lo_top - y0) : 1, j_hi = valid ? min(Wr - 1, hi_top - y0) : 0;
+            wcol[WIN_JLO * WIN_LD] = __int_as_float(j_lo);
+            wcol[WIN_JHI * WIN_LD] = __int_as_float(j_hi);
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&win_full[(wu % NWIN) * 4 + wq]);  // release.cta: the STS above are visible
+          if (warp == 2 && lane == 0) stamp(p, 5, 2 * wu + 1, 0);
           ++wu;
         }
       }
-      jr = jr1; jr1 = jr2;
-      n = n1; cx = cx1; cy = cy1;
+      __syncwarp();                         // every lane has read this job's metadata long ago: refill the buffer
+      prefetch_job(job + 2 * G, mbuf);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     // ===================== stager warps (6..9): every global load/store except the TMA =====================
     // per job:  (1) stage the NEXT job's 128 target rows into the free TMEM A buffer (hi/lo split, tcgen05.st);
@@ -822,9 +1049,11 @@ corr_tc_kernel(const Params p) {
     constexpr int Wr = 2 * R + 1, WW = Wr * Wr;
     uint32_t wu = 0;
 
-    // stage the 128 target rows of job record `r` (hi/lo split) into TMEM A buffer (ji & 1); `nq` = this lane's query
-    auto stage_targets = [&](const JobRec& r, int nq, uint32_t ji) {
-      const int b = r.bs / p.S, s = r.bs - b * p.S;
+    // stage the 128 target rows of job number `jobno` (hi/lo split) into TMEM A buffer (ji & 1); `nq` = this lane's
+    // query.  Frame and query tile follow from the job number (jobs are laid out [frame][query tile][chunk]).
+    auto stage_targets = [&](int jobno, int nq, uint32_t ji) {
+      const int bs_ = (jobno / p.nchunk) / p.mtiles;
+      const int b = bs_ / p.S, s = bs_ - b * p.S;
       const uint32_t abuf = ji & 1;
       mbar_wait(&a_empty[abuf], ((ji >> 1) & 1) ^ 1, p.status, 6);
       tcgen05_fence_after();
@@ -858,26 +1087,64 @@ corr_tc_kernel(const Params p) {
       tcgen05_fence_before();
       mbar_arrive(&a_full[abuf]);
     };
-    auto slot_query = [&](const JobRec& r, bool in_range) {
-      return in_range ? __ldg(p.perm + (long long)r.bs * p.npad + r.mt() * TILE_M + q) : -1;
+    auto slot_query = [&](int jobno) {   // perm is [frame][query tile][128]: addressed by the job number alone
+      return jobno < p.njobs ? ldg_pin(p.perm + (long long)(jobno / p.nchunk) * TILE_M + q) : -1;
     };
 
-    // software pipeline: record of job i+2 and query index of job i+1 are in flight while job i is served
+    // software pipeline: record and query index of job i+2 are in flight while job i is served (no dependent loads)
+    const int G = gridDim.x;
+    int myn = slot_query(blockIdx.x);
+    int myn1 = slot_query(blockIdx.x + G);
     JobRec jr = load_job(p, blockIdx.x);
-    JobRec jr1 = load_job(p, blockIdx.x + gridDim.x);
-    int myn = slot_query(jr, (int)blockIdx.x < p.njobs);
-    int myn1 = slot_query(jr1, (int)(blockIdx.x + gridDim.x) < p.njobs);
-    if ((int)blockIdx.x < p.njobs) stage_targets(jr, myn, 0);
+    JobRec jr1 = load_job(p, blockIdx.x + G);
+    if ((int)blockIdx.x < p.njobs) stage_targets(blockIdx.x, myn, 0);
     uint32_t ji = 0;
-    for (int job = blockIdx.x; job < p.njobs; job += gridDim.x, ++ji) {
-      const JobRec jr2 = load_job(p, job + 2 * gridDim.x);
-      const int myn2 = slot_query(jr2, job + 2 * (int)gridDim.x < p.njobs);   // needs jr2: consumed two jobs later
-      if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 0);
-      if (job + (int)gridDim.x < p.njobs) stage_targets(jr1, myn1, ji + 1);
-      if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 0, 1);
+    constexpr int RW = ((WW + 6) / 4) * 4;   // floats per staged row in RED mode
+    const bool do_windows = !(VOLUME || TC_DBG(p, 1));
+    for (int job = blockIdx.x; job < p.njobs; job += G, ++ji) {
+      const JobRec jr2 = load_job(p, job + 2 * G);
+      const int myn2 = slot_query(job + 2 * G);
+      if (warp == 6 && lane == 0) stamp(p, 3, ji * 16 + 0, 0);
+      if (job + G < p.njobs) stage_targets(job + G, myn1, ji + 1);
+      if (warp == 6 && lane == 0) stamp(p, 3, ji * 16 + 0, 1);
       const int bs = jr.bs;
       const int b = bs / p.S, s = bs - b * p.S;
       const int nseg = jr.nseg();
+#ifdef COMET_TC_TRACE
+      if (warp == 6 && lane == 0 && p.stamps && blockIdx.x == 0 && ji < 8) {   // tiles of this job, for the trace reader
+        int nt = 0;
+        for (int sg = 0; sg < nseg; ++sg) nt += jr.t1(sg) - jr.t0(sg);
+        p.stamps[(3 * 64 + ji * 16 + 15) * 2] = nt;
+        p.stamps[(3 * 64 + ji * 16 + 15) * 2 + 1] = nseg;
+      }
+#endif
+      if (RED) {
+        // One lane = one query: add its staged row to its token row.  The row starts on the 16-byte boundary at or
+        // below the level's first window channel (`a` leading zeros) and ends on one (trailing zeros), so neighbouring
+        // channels receive + 0.0f.
+        float* orow = p.out + (((long long)b * p.N + (myn >= 0 ? myn : 0)) * p.S + s) * p.D_tok;
+        for (int sg = 0; do_windows && sg < nseg; ++sg, ++wu) {
+          const int lvl = tile_info(jr.t0(sg)).level;
+          const uint32_t wbuf = wu % NWIN;
+          mbar_wait(&win_full[wbuf * 4 + wq], (wu / NWIN) & 1, p.status, 8);
+          if (warp == 6 && lane == 0) stamp(p, 3, ji * 16 + 1 + 2 * sg, 0);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (myn >= 0 && !TC_DBG(p, 2)) {
+            const int ch = KC + 2 + lvl * WW;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                         ::"l"(orow + (ch & ~3)), "r"(smem_u32(win + (wbuf * 4 + wq) * WIN_WARP + lane * RW)), "r"(RW * 4)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staged rows have been read
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&win_empty[wbuf * 4 + wq]);
+          if (warp == 6 && lane == 0) stamp(p, 3, ji * 16 + 2 + 2 * sg, 1);
+        }
+        jr = jr1; jr1 = jr2;
+        myn = myn1; myn1 = myn2;
+        continue;
+      }
 
       // element offsets of this lane's query rows (pos_emb row, output row), shared with the warp through smem:
       // the store loop below then needs one broadcast LDS.64 per row instead of shuffles + 64-bit index math.
@@ -890,15 +1157,13 @@ corr_tc_kernel(const Params p) {
                                       : b * p.o_sb + s * p.o_ss + nq * p.o_sn;
         __syncwarp();
       }
-      if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 1, 0);
-      const bool do_windows = !(VOLUME || TC_DBG(p, 1));
       const int nvalid = min(32, p.N - (jr.mt() * TILE_M + 32 * wq));   // sorted slots: valid first, padding last
       // window units of this job: one per tile run (= one pyramid level)
       for (int sg = 0; do_windows && sg < nseg; ++sg, ++wu) {
         const int lvl = tile_info(jr.t0(sg)).level;
         const uint32_t wbuf = wu % NWIN;
         mbar_wait(&win_full[wbuf * 4 + wq], (wu / NWIN) & 1, p.status, 8);
-        if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 0);
+        if (warp == 6 && lane == 0) stamp(p, 3, ji * 16 + 1 + 2 * sg, 0);
         const float* wbase = win + (wbuf * 4 + wq) * WIN_WARP;   // [entry][WIN_LD] of this lane quarter
         const int lvl_off = (p.tokens ? KC + 2 : 0) + lvl * WW;
         const int jj0 = lane % Wr, jj1 = (lane + 32) % Wr, jj2 = (lane + 64) % Wr;
@@ -935,11 +1200,12 @@ corr_tc_kernel(const Params p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&win_empty[wbuf * 4 + wq]);
-        if (warp == 6 && lane == 0) stamp(p, 3, ji * 4 + 2, 1);
+        if (warp == 6 && lane == 0) stamp(p, 3, ji * 16 + 2 + 2 * sg, 1);
       }
       jr = jr1; jr1 = jr2;
       myn = myn1; myn1 = myn2;
     }
+    if (RED) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every reduction of this thread has completed
   }
 
   tcgen05_fence_before();
@@ -1081,7 +1347,7 @@ static void choose_split(int BS, int mtiles, int L, int sms, int& nsplit, int& n
 
 static long long workspace_bytes(int BS, int N) {
   const long long mtiles = (N + TILE_M - 1) / TILE_M;
-  return (long long)BS * mtiles * TILE_M * 4 + (long long)BS * mtiles * MAX_CHUNK * (long long)sizeof(JobRec) + 64;
+  return (long long)BS * mtiles * TILE_M * (4 + 16) + (long long)BS * mtiles * MAX_CHUNK * (long long)sizeof(JobRec) + 64;
 }
 
 static int launch(Params& p, const void* split, void* workspace, cudaStream_t stream) {
@@ -1107,14 +1373,18 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   }
   p.stamps = g_stamps;
 #endif
-  // workspace: [jobs: BS*mtiles*MAX_CHUNK records][perm: BS*npad ints]
+  // workspace: [jobs: BS*mtiles*MAX_CHUNK records][perm: BS*npad ints][slots: BS*npad int4]
   JobRec* jobs = reinterpret_cast<JobRec*>(workspace);
   int* perm = reinterpret_cast<int*>(jobs + (long long)p.BS * p.mtiles * MAX_CHUNK);
   p.jobs = jobs;
   p.perm = perm;
+  p.slots = reinterpret_cast<const int4*>(perm + (long long)p.BS * p.npad);
   p.split = reinterpret_cast<const uint8_t*>(split);
 
   const int full = (p.volume_mode || TC_DBG(p, 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
+  // token rows with a 16-byte aligned base and pitch take the bulk-reduction output path
+  p.vec4 = (p.tokens && ((uintptr_t)p.out % 16) == 0 && ((uintptr_t)p.pos % 16) == 0 && (p.D_tok % 4) == 0) ? 1 : 0;
+  p.red = (p.vec4 && !p.volume_mode && option(COMET_OPT_TC_REDUCE_STORE) && !option(COMET_OPT_TC_OVERLAP_MISC)) ? 1 : 0;
   // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
   long long misc = 0;
   const bool overlap_misc = p.tokens && COMET_TC_PDL && option(COMET_OPT_TC_OVERLAP_MISC);
@@ -1141,10 +1411,14 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
   } while (0)
 #define COMET_TC_LAUNCH_R(RR)                                                                                     \
   do {                                                                                                            \
-    if (p.bf16) COMET_TC_LAUNCH(RR, true, false); else COMET_TC_LAUNCH(RR, false, false);                         \
+    if (p.red) {                                                                                                  \
+      if (p.bf16) COMET_TC_LAUNCH(RR, true, MODE_REDUCE); else COMET_TC_LAUNCH(RR, false, MODE_REDUCE);           \
+    } else {                                                                                                      \
+      if (p.bf16) COMET_TC_LAUNCH(RR, true, MODE_STORE); else COMET_TC_LAUNCH(RR, false, MODE_STORE);             \
+    }                                                                                                             \
   } while (0)
   if (p.volume_mode) {
-    if (p.bf16) COMET_TC_LAUNCH(0, true, true); else COMET_TC_LAUNCH(0, false, true);
+    if (p.bf16) COMET_TC_LAUNCH(0, true, MODE_VOLUME); else COMET_TC_LAUNCH(0, false, MODE_VOLUME);
   } else {
     switch (p.r) {
       case 0: COMET_TC_LAUNCH_R(0); break;

@@ -76,7 +76,10 @@ int comet_has_tensor_path(void);
                                       tensor kernel (programmatic dependent launch) instead of before it.  OFF by default:
                                       measured 0.155 vs 0.112 ms per iteration (scripts/coarse_ab.py) -- the tensor CTAs leave
                                       room for 4 warps per SM, too few for a bandwidth kernel */
-#define COMET_OPT_COUNT 4
+#define COMET_OPT_TC_REDUCE_STORE 4 /* coarse tokens: the windows are added to the token rows by bulk reductions
+                                      (cp.reduce.async.bulk add.f32, one per query and level) onto the position embedding the
+                                      pre-kernel wrote there; off = per-entry stores by the stager warps.  ON by default */
+#define COMET_OPT_COUNT 5
 int comet_set_option(int option, int value);
 int comet_get_option(int option);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */

@@ -14,8 +14,9 @@ blk = cb.CorrBlock(fm, num_levels=5, radius=4)
 tk = cb.TrackTokenizer(blk, co[:, 0], tdim)
 out = torch.empty(Q, N, S, tdim, device=dev)
 ref = None
-for name, val in (("misc before (pre-kernel)", False), ("misc beside (PDL)", True), ("misc before (pre-kernel)", False), ("misc beside (PDL)", True)):
-    _lib.set_option(_lib.OPT_TC_OVERLAP_MISC, val)
+OPT = getattr(_lib, sys.argv[1]) if len(sys.argv) > 1 else _lib.OPT_TC_REDUCE_STORE
+for name, val in (("option off", False), ("option on", True), ("option off", False), ("option on", True)):
+    _lib.set_option(OPT, val)
     for _ in range(5): tk.tokens(co, ft, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
