@@ -501,78 +501,130 @@ __device__ __forceinline__ void token_misc_rows(const Params& p, long long warp_
   }
 }
 
-// The same rows with 16-byte accesses (token rows and position-embedding rows 16-byte aligned, D_tok % 4 == 0): a lane
-// owns whole float4 groups of the row -- all its position-embedding loads are issued before the first use, one sincosf
-// serves a (sin, cos) channel pair, and the row is written with STG.128.  Groups that lie entirely inside the window
-// channels are skipped unless p.red (then they receive the position embedding the bulk reductions add to).
+// The same rows with 16-byte accesses (token rows and position-embedding rows 16-byte aligned, D_tok % 4 == 0), as a
+// persistent loop: a warp walks its rows with the NEXT row's position-embedding row and track features already on
+// their way into shared memory (cp.async, two buffers per warp), so the loop runs at issue rate instead of one memory
+// round trip per row.  A lane owns whole float4 groups of the row; one sincosf serves a (sin, cos) channel pair; the
+// row is written with STG.128.  Groups that lie entirely inside the window channels are skipped unless p.red (then
+// they receive the position embedding the bulk reductions add to).
+// `buf`: this warp's 3 x (D_tok + KC) floats of dynamic shared memory.
 __device__ __forceinline__ void token_misc_rows_v4(const Params& p, long long warp_id, long long nwarps, int lane,
-                                                   float* feat_row) {
+                                                   float* buf) {
   const int WW = (2 * p.r + 1) * (2 * p.r + 1);
   const int Ce = KC >> 1;
   const float step = 1000.0f / (float)Ce;
   const int feat_off = KC + 2 + p.L * WW;
   const int nv = p.D_tok >> 2;
   const int f_lo = (KC + 2 + 3) >> 2, f_hi = feat_off >> 2;   // float4 groups [f_lo, f_hi) hold window channels only
-  const long long rows = (long long)p.B * p.N * p.S;
-  constexpr int T = 6;                                        // groups per lane and pass (D_tok <= 768 in one pass)
-  for (long long row = warp_id; row < rows; row += nwarps) {
-    const int s = (int)(row % p.S);
-    const long long bn = row / p.S;
-    const int n = (int)(bn % p.N), b = (int)(bn / p.N);
-    const float* cp = p.coords + b * p.c_sb + s * p.c_ss + (long long)n * p.c_sn;
-    const float* c0 = p.coords + b * p.c_sb + (long long)n * p.c_sn;  // frame 0
-    const float cx1 = __ldg(cp), cy1 = __ldg(cp + 1), cx0 = __ldg(c0), cy0 = __ldg(c0 + 1);
-    const float4* pq = reinterpret_cast<const float4*>(p.pos + bn * p.D_tok);
-    const float* tq = p.targets + b * p.t_sb + s * p.t_ss + (long long)n * p.t_sn;
-    float* o = p.out + row * p.D_tok;
-    for (int k0 = 0; k0 < nv; k0 += 32 * T) {
-      // every load of the row is issued before the first use: one memory round trip per row and warp.  The track
-      // features sit at an arbitrary 4-byte phase of the token row: they pass through a per-warp shared-memory row.
-      float4 pe[T];
+  const int rows = p.B * p.N * p.S;               // < 2^31 (checked by the host): 32-bit row arithmetic
+  const int bstride = p.D_tok + KC;
+  constexpr int T = 6;                             // float4 groups per lane: D_tok <= 768 (checked by the host)
+  auto needed = [&](int k) { return k < nv && (p.red || k < f_lo || k >= f_hi); };
+  // position-embedding groups this lane needs + its float4 of the track features -> shared memory buffer `which`;
+  // the flow of the row (coordinates of this frame minus frame 0) into registers
+  auto issue = [&](int row, int which, float& flx, float& fly) {
+    flx = 0.f; fly = 0.f;
+    if (row < rows) {
+      const int bn = row / p.S, s_ = row - bn * p.S;
+      const int b_ = bn / p.N, n_ = bn - b_ * p.N;
+      const uint32_t dst = smem_u32(buf + which * bstride);
+      const float4* pq = reinterpret_cast<const float4*>(p.pos + (long long)bn * p.D_tok);
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const int k = k0 + lane + 32 * t;
-        const bool need = k < nv && (p.red || k < f_lo || k >= f_hi);
-        pe[t] = need ? __ldg(pq + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k = lane + 32 * t;
+        if (needed(k))
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(pq + k) : "memory");
       }
-      if (k0 == 0) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tq) + lane);   // KC = 128 floats = 32 lanes x float4
-        __syncwarp();
-        *reinterpret_cast<float4*>(feat_row + 4 * lane) = t4;
-        __syncwarp();
+      const float4* tq = reinterpret_cast<const float4*>(p.targets + b_ * p.t_sb + s_ * p.t_ss + (long long)n_ * p.t_sn);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                   ::"r"(dst + (uint32_t)(nv + lane) * 16u), "l"(tq + lane) : "memory");
+      const float* c0 = p.coords + b_ * p.c_sb + (long long)n_ * p.c_sn;  // frame 0
+      const float* cp = c0 + s_ * p.c_ss;
+      flx = __ldg(cp) - __ldg(c0);
+      fly = __ldg(cp + 1) - __ldg(c0 + 1);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int w0 = (int)warp_id, nw = (int)nwarps;
+  float flx, fly;
+  issue(w0, 0, flx, fly);
+  int which = 0;   // three buffers in rotation: being filled | being worked on | being read by its bulk store
+  for (int row = w0; row < rows; row += nw, which = which == 2 ? 0 : which + 1) {
+    float flx1, fly1;
+    issue(row + nw, which == 2 ? 0 : which + 1, flx1, fly1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();                                   // the feature row was copied by all 32 lanes
+    float* o = p.out + (long long)row * p.D_tok;
+    if (p.red) {
+      // Whole row leaves as ONE bulk store: the position-embedding row sits in shared memory; add the few channels that
+      // carry something else in place (sin/cos: one group per lane; flow; track features) and hand the row to the TMA.
+      float* rowb = buf + which * bstride;
+      const float* feat_row = rowb + p.D_tok;
+      {
+        float4 pk = reinterpret_cast<float4*>(rowb)[lane];
+        const int c = 4 * lane, axis = c / Ce, w = c - axis * Ce;
+        const float f = axis ? fly : flx;
+        float v0, v1, v2, v3;
+        sincosf(__fmul_rn(f, (float)w * step), &v0, &v1);
+        sincosf(__fmul_rn(f, (float)(w + 2) * step), &v2, &v3);
+        pk.x += v0; pk.y += v1; pk.z += v2; pk.w += v3;
+        reinterpret_cast<float4*>(rowb)[lane] = pk;
       }
-      const float flx = cx1 - cx0, fly = cy1 - cy0;
+      if (lane < 2) rowb[KC + lane] += lane ? fly : flx;
+      {
+        const float4 f4 = reinterpret_cast<const float4*>(feat_row)[lane];
+        float* d = rowb + feat_off + 4 * lane;
+        d[0] += f4.x; d[1] += f4.y; d[2] += f4.z; d[3] += f4.w;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(o), "r"(smem_u32(rowb)), "r"(p.D_tok * 4) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      // the buffer the NEXT iteration's issue refills is the one whose store was committed one iteration ago: wait
+      // until that store has read its source (this iteration's store may still be pending)
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      flx = flx1; fly = fly1;
+      continue;
+    }
+    const float4* pe = reinterpret_cast<const float4*>(buf + which * bstride);
+    const float* feat_row = buf + which * bstride + p.D_tok;
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int k = k0 + lane + 32 * t;
-        if (k >= nv || !(p.red || k < f_lo || k >= f_hi)) continue;
-        const int c = 4 * k;
-        float v[4];
-        if (c + 3 < KC) {
-          const int axis = c / Ce, w = c - axis * Ce;   // w is a multiple of 4: channels (sin, cos) of w and of w + 2
-          const float f = axis ? fly : flx;
-          sincosf(__fmul_rn(f, (float)w * step), &v[0], &v[1]);
-          sincosf(__fmul_rn(f, (float)(w + 2) * step), &v[2], &v[3]);
-        } else {
+    for (int t = 0; t < T; ++t) {
+      const int k = lane + 32 * t;
+      if (!needed(k)) continue;
+      const int c = 4 * k;
+      const float4 pk = pe[k];
+      float v[4];
+      if (t == 0 && KC >= 128) {                    // groups 0..31 are the 128 sin/cos channels
+        const int axis = c / Ce, w = c - axis * Ce;   // w is a multiple of 4: channels (sin, cos) of w and of w + 2
+        const float f = axis ? fly : flx;
+        sincosf(__fmul_rn(f, (float)w * step), &v[0], &v[1]);
+        sincosf(__fmul_rn(f, (float)(w + 2) * step), &v[2], &v[3]);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int cj = c + j;
-            v[j] = (cj >= KC && cj < KC + 2) ? (cj == KC ? flx : fly)
-                 : (cj >= feat_off && cj < feat_off + KC) ? feat_row[cj - feat_off] : 0.f;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int cj = c + j;
+          v[j] = (cj >= KC && cj < KC + 2) ? (cj == KC ? flx : fly)
+               : (cj >= feat_off && cj < feat_off + KC) ? feat_row[cj - feat_off] : 0.f;
         }
-        const float4 r = make_float4(v[0] + pe[t].x, v[1] + pe[t].y, v[2] + pe[t].z, v[3] + pe[t].w);
-        if (p.red || c + 3 < KC + 2 || c >= feat_off) {
-          *reinterpret_cast<float4*>(o + c) = r;
-        } else {   // a group shared with window channels the tensor kernel stores itself
-          const float rr[4] = {r.x, r.y, r.z, r.w};
+      }
+      const float4 r = make_float4(v[0] + pk.x, v[1] + pk.y, v[2] + pk.z, v[3] + pk.w);
+      if (p.red || c + 3 < KC + 2 || c >= feat_off) {
+        *reinterpret_cast<float4*>(o + c) = r;
+      } else {   // a group shared with window channels the tensor kernel stores itself
+        const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (c + j < KC + 2 || c + j >= feat_off) o[c + j] = rr[j];
-        }
+        for (int j = 0; j < 4; ++j)
+          if (c + j < KC + 2 || c + j >= feat_off) o[c + j] = rr[j];
       }
     }
+    __syncwarp();                                   // buffer `which` is refilled by the next iteration's issue
+    flx = flx1; fly = fly1;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Launch 1 of 2 per call: CTAs [0, BS) plan one frame each, the rest write the correlation-independent token channels.
@@ -582,9 +634,9 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
     plan_frame(p, perm, jobs, full, blockIdx.x);
   } else {
     const long long nw = (long long)(gridDim.x - p.BS) * 8;
-    __shared__ __align__(16) float feat_rows[8][KC];
+    extern __shared__ __align__(16) float pre_smem[];   // vec4: 8 warps x 3 x (D_tok + KC) floats
     if (p.vec4) token_misc_rows_v4(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31,
-                                   feat_rows[threadIdx.x >> 5]);
+                                   pre_smem + (threadIdx.x >> 5) * 3 * (p.D_tok + KC));
     else token_misc_rows(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
   }
   // programmatic dependent launch: once every CTA of this grid got here the tensor kernel may be scheduled, so its
@@ -1383,16 +1435,25 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
 
   const int full = (p.volume_mode || TC_DBG(p, 512)) ? 1 : 0;   // 512: unsorted, every tile (A/B experiments)
   // token rows with a 16-byte aligned base and pitch take the bulk-reduction output path
-  p.vec4 = (p.tokens && ((uintptr_t)p.out % 16) == 0 && ((uintptr_t)p.pos % 16) == 0 && (p.D_tok % 4) == 0) ? 1 : 0;
+  p.vec4 = (p.tokens && ((uintptr_t)p.out % 16) == 0 && ((uintptr_t)p.pos % 16) == 0 && (p.D_tok % 4) == 0 &&
+            p.D_tok <= 768 && (long long)p.B * p.N * p.S < 0x7fffffffLL) ? 1 : 0;
   p.red = (p.vec4 && !p.volume_mode && option(COMET_OPT_TC_REDUCE_STORE) && !option(COMET_OPT_TC_OVERLAP_MISC)) ? 1 : 0;
   // launch 1: plan (one CTA per frame) + the correlation-independent token channels (8 token rows per CTA, capped)
   long long misc = 0;
   const bool overlap_misc = p.tokens && COMET_TC_PDL && option(COMET_OPT_TC_OVERLAP_MISC);
+  size_t pre_smem = 0;
   if (p.tokens && !overlap_misc) {
     misc = ((long long)p.B * p.N * p.S + 7) / 8;
+    if (p.vec4) {
+      // persistent rows loop: 2 CTAs per SM (8 warps x 3 row buffers each)
+      pre_smem = (size_t)8 * 3 * (p.D_tok + KC) * sizeof(float);
+      if (misc > 2LL * sms) misc = 2LL * sms;
+    }
     if (misc > 64LL * sms) misc = 64LL * sms;
+    if (pre_smem > 48 * 1024)
+      COMET_CUDA(cudaFuncSetAttribute(tc_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem));
   }
-  tc_pre_kernel<<<(unsigned)(p.BS + misc), 256, 0, stream>>>(p, perm, jobs, full);
+  tc_pre_kernel<<<(unsigned)(p.BS + misc), 256, pre_smem, stream>>>(p, perm, jobs, full);
   int rc = launch_status("tc_pre_kernel");
   if (rc != COMET_OK) return rc;
   const int grid = (int)(njobs < sms ? njobs : sms);
