@@ -17,29 +17,31 @@
 // Work decomposition.  Launch 1 (tc_pre_kernel): per frame, the queries are counting-sorted by floor(y), so the 128
 // queries of an MMA tile -- and the 32 of an epilogue warp -- share a narrow band of map rows; the per-(tile, level)
 // band is reduced and turned into job records (nsplit level-0 row chunks with one row of overlap + npyr jobs for
-// levels 1..L-1); the remaining CTAs of that launch write the correlation-independent token channels (flow sin/cos,
-// flow, track_feats, pad) with one warp per token row.  Launch 2 (corr_tc_kernel): persistent CTAs (one per SM) walk
-// the job list; only the tiles of a band are loaded and multiplied (~45 % of the dense GEMM at 512 random queries per
-// frame), and an epilogue warp skips the tiles none of its queries touches.
+// levels 1..L-1), and per sorted slot {query, x, y} is written for the epilogue's prefetch; the remaining CTAs of that
+// launch write the correlation-independent token channels (flow sin/cos, flow, track_feats, pad) -- and, in reduce
+// mode, the position embedding of the window channels -- as a persistent loop over token rows whose next row is
+// already on its way into shared memory (cp.async), one bulk store per row.  Launch 2 (corr_tc_kernel): persistent
+// CTAs (one per SM) walk the job list; only the tiles of a band are loaded and multiplied (~45 % of the dense GEMM at
+// 512 random queries per frame), and an epilogue warp skips the tiles none of its queries touches.
 //
 // CTA = 10 warps:  warp 0 bulk-copy producer (3-stage ring) | warp 1 TMEM alloc + single-thread tcgen05.mma issue
 // (A operand = targets in TMEM, `.ts` form; D 128x64 fp32 in TMEM, 4-stage accumulator ring) | warps 2-5 epilogue:
 // tcgen05.ld the accumulator row of "their" query (TMEM lane == sorted query slot), park it in a private shared-memory
 // row (the window columns are indexed dynamically), horizontal lerp at the query's x window, vertical lerp with the
-// previous row, write the staged window | warps 6-9 stager: every global access -- stage the next job's targets into
-// TMEM (hi/lo split, tcgen05.st), and write the staged windows + position embedding with coalesced stores.
+// previous row, write the staged window; job metadata (record, sorted slot) arrives by cp.async two jobs ahead |
+// warps 6-9 stager: stage the next job's targets into TMEM (hi/lo split, tcgen05.st) and send the staged windows out:
+// MODE_REDUCE (token rows): one lane per query adds its 16-byte aligned staged row to the token row with a bulk
+// reduction (cp.reduce.async.bulk add.f32 -- the TMA unit and the L2 do the work); MODE_STORE (lookup layout,
+// unaligned token rows): coalesced stores + position embedding, entry by entry.
 // The two launches are chained with programmatic dependent launch: the tensor kernel's prologue (barrier init, TMEM
 // allocation) overlaps the drain of tc_pre_kernel and it waits (griddepcontrol.wait) before touching the plan.
 //
-// Measured and rejected in round 2 (scripts/variant_bench.sh, B200, batch of 4 sequences, ms per iteration): EIGHT
-// epilogue warps, two per TMEM lane quarter, each producing half of the window's x entries (no synchronisation between
-// the halves): 0.170 vs 0.118 -- with 14 warps one scheduler hosts 4 of them, which caps the kernel at 128 registers per
-// thread (16384 per scheduler) and spills the epilogue's accumulator row, and a 2-stage operand ring is all that fits
-// beside two sets of private rows.  The stall samples of the 4-warp kernel (profiles/r02_coarse_tc_stalls.md) show why
-// the split does not pay: the epilogue warps spend 21 % of their time WAITING for accumulators -- the MMA warp in turn
-// waits for the target tile of the next job, which the stager warps stage (~5700 clk) only after they have stored the
-// previous job's windows (~6000 clk per level): the roles starve one another in turn rather than one role being the
-// limiter.
+// Measured and rejected (profiles/r02_coarse_tc_stalls.md, profiles/r02b_coarse_tc_analysis.md; B200, batch of 4
+// sequences, ms per iteration): EIGHT epilogue warps, two per TMEM lane quarter: 0.170 vs 0.118 -- with 14 warps one
+// scheduler hosts 4 of them, which caps the kernel at 128 registers per thread and spills the accumulator row; an L2
+// prefetch ahead of the operand ring: no change (the level-0 phases pull 6.9 TB/s of first-touch tiles -- HBM, not
+// latency); staging the targets of job i+2 early: no change; the token rows as a third grid beside the plan: slower;
+// the row initialisation inside the stager warps behind global-memory flags: 0.15-0.39 vs 0.108.
 #include "comet_common.cuh"
 
 #include <cuda.h>

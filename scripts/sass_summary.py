@@ -1,5 +1,5 @@
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native path (B200_PROFILING.md: UTC*MMA = tcgen05.mma,
-LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk, HMMA = legacy mma.sync), from the in-tree
+LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA tensor load, UBLKCP = cp.async.bulk, UBLKRED = cp.reduce.async.bulk, LDGSTS = cp.async, HMMA = legacy mma.sync), from the in-tree
 libcomet_b200.so.  No GPU needed:  python scripts/sass_summary.py > profiles/r02_sass_summary.txt"""
 import collections
 import os
@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "comet_pose_estimation_b200", "libcomet_b200.so")
-MN = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "HGMMA", "LDGSTS"]
+MN = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "UTCBAR", "SYNCS", "HMMA", "HGMMA", "LDGSTS"]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 counts = collections.OrderedDict()
 cur = None
