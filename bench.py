@@ -291,6 +291,30 @@ TRACKER = dict(coarse=dict(stride=4, corr_levels=5, corr_radius=4, latent_dim=12
                fine=dict(stride=1, corr_levels=3, corr_radius=3, latent_dim=32, hidden_size=256, depth=4, use_spaceatt=False, fine=True))
 
 
+def cpu_encoders_s(torch):
+    """CPU baseline scope (iii) of BASELINE.md section 4, the part scope (ii) does not contain: the two encoders of one
+    sequence on the host cores -- BasicEncoder on 16 frames of 512x512 and ShallowEncoder on 512 x 16 patches of 31x31
+    (their torch.nn / ATen definition, which is what the reference executes; random-init weights, one pass each after a
+    small warm-up; the patch encoder runs in chunks of 1024 patches like refine_track does for memory)."""
+    import importlib
+
+    tp = importlib.import_module("comet_pose_estimation_b200.track_predictor")
+    rt = importlib.import_module("comet_pose_estimation_b200.refine_track")
+    torch.manual_seed(0)
+    basic, shallow = tp.BasicEncoder().eval(), rt.ShallowEncoder().eval()
+    frames = torch.randn(16, 3, 512, 512)
+    patches = torch.randn(COARSE["N"] * 16, 3, 31, 31)
+    with torch.no_grad():
+        basic(frames[:1]); shallow(patches[:64])          # warm-up (thread pool, oneDNN primitives)
+        t0 = time.perf_counter()
+        basic(frames)
+        t1 = time.perf_counter()
+        for i in range(0, patches.shape[0], 1024):
+            shallow(patches[i:i + 1024])
+        t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
 def cpu_tracker_loop_s(torch, reps=1):
     """CPU baseline scope (ii) of BASELINE.md section 4: coarse (4 it) + fine (6 it) tracker loops of ONE sequence WITH the
     update transformer -- hot path through oracle/torch_port.py (the reference's ATen calls), transformer and state update
@@ -823,6 +847,12 @@ def main():
             cpu["tracker_loop_s_per_sequence"] = cpu_tracker_loop_s(torch, reps=1)
             cpu["tracker_loop_sample"] = ("scope (ii): coarse 4 it + fine 6 it of one sequence incl. the update transformer "
                                           "(torch.nn on the host cores) and state updates, best of 1 after a warm-up")
+            # scope (iii): from images -- scope (ii) plus the two encoders on the host cores
+            t_basic, t_shallow = cpu_encoders_s(torch)
+            cpu["from_images_s_per_sequence"] = cpu["tracker_loop_s_per_sequence"] + t_basic + t_shallow
+            cpu["from_images_sample"] = (f"scope (iii): scope (ii) + BasicEncoder on 16 frames of 512x512 ({t_basic:.2f} s) + ShallowEncoder "
+                                         f"on 8192 patches of 31x31 ({t_shallow:.2f} s), torch.nn on the host cores, one pass each; "
+                                         "compare variants.tracker_from_images")
 
     if rank == 0:
         config = make_config(Q, world, layout)
