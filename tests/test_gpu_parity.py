@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the Python mirror -> ctypes -> C ABI) against the reference goldens and the
 CPU oracle.  Bars: fp32 max|a-b|/max|b| <= 1e-4; bf16-autocast <= 2e-2."""
 import numpy as np
+import contextlib
+
 import pytest
 import torch
 
@@ -710,3 +712,38 @@ def test_up2_pyramid_level2_matches_pooled_upsampling(cb):
     full = F.interpolate(src.reshape(10, 32, 16, 16), (31, 31), mode="bilinear", align_corners=True)
     want = F.avg_pool2d(F.avg_pool2d(full, 2, 2), 2, 2)
     assert rel_to_max(host(got), host(want)) < 1e-6
+
+def test_tensor_path_output_modes_agree(cb):
+    """Token rows of the tcgen05 path: windows added by bulk reductions onto the pre-kernel's rows (default for 16-byte
+    aligned rows) == windows stored entry by entry (COMET_OPT_TC_REDUCE_STORE off, or a token buffer that is not 16-byte
+    aligned), bit for bit -- float32 and autocast, N not a multiple of the tile, queries off the map and non-finite."""
+    if not cb._lib.lib.comet_has_tensor_path():
+        pytest.skip("no sm_100 tensor path on this device")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (B, S, N, L, r, autocast) in ((2, 3, 200, 5, 4, False), (1, 2, 129, 3, 2, False), (1, 4, 512, 5, 4, True), (1, 1, 7, 2, 1, False)):
+        fmaps = torch.randn(B, S, 128, 64, 64, device="cuda", generator=g)
+        feats = torch.randn(B, S, N, 128, device="cuda", generator=g)
+        coords = torch.rand(B, S, N, 2, device="cuda", generator=g) * 80 - 8
+        coords[0, 0, 0] = torch.tensor([float("nan"), 5.0], device="cuda")
+        coords[0, 0, 1] = torch.tensor([1.0e9, -1.0e9], device="cuda")
+        # the reference's token width where it holds the channels, else the channel count rounded up to a multiple of 4
+        tdim = max(cb.transformer_dim(L, r, 128, False), (2 * 128 + 2 + L * (2 * r + 1) ** 2 + 3) // 4 * 4)
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+        with ctx:
+            blk = cb.CorrBlock(fmaps, num_levels=L, radius=r)
+            assert blk._pyr.split is not None
+            tk = cb.TrackTokenizer(blk, coords[:, 0].nan_to_num(0.0).clamp(0, 63), tdim)
+            red = tk.tokens(coords, feats).clone()
+            cb._lib.set_option(cb._lib.OPT_TC_REDUCE_STORE, False)
+            try:
+                stored = tk.tokens(coords, feats).clone()
+            finally:
+                cb._lib.set_option(cb._lib.OPT_TC_REDUCE_STORE, True)
+            # a token buffer whose rows start 4 bytes off a 16-byte boundary: the library must take the store path itself
+            flat = torch.empty(B * N * S * tdim + 1, device="cuda")
+            off = flat[1:].view(B, N, S, tdim)
+            assert off.data_ptr() % 16 != 0
+            tk.tokens(coords, feats, out=off)
+        assert torch.equal(red.nan_to_num(1234.5), stored.nan_to_num(1234.5))
+        assert torch.equal(red.nan_to_num(1234.5), off.nan_to_num(1234.5))
+        assert cb._lib.lib.comet_tc_status() == 0
