@@ -62,6 +62,9 @@ constexpr int MAX_WR = 9;      // 2*4+1
 #ifndef COMET_TC_PDL
 #define COMET_TC_PDL 1
 #endif
+#ifndef COMET_TC_EVICT_FIRST
+#define COMET_TC_EVICT_FIRST 0  // operand tiles loaded with an L2 evict-first policy (experiment)
+#endif
 #ifndef COMET_TC_L2PF
 #define COMET_TC_L2PF 0        // tiles the producer's L2 prefetch runs ahead of the operand ring (0: off)
 #endif
@@ -230,6 +233,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bulk copy with an L2 eviction-priority hint (createpolicy): the operand stream of the tensor kernel is read once or
+// twice within microseconds and should not push the token rows -- which the bulk reductions read-modify-write -- out of L2
+__device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -505,8 +514,8 @@ __device__ __forceinline__ void token_misc_rows(const Params& p, long long warp_
 
 // The same rows with 16-byte accesses (token rows and position-embedding rows 16-byte aligned, D_tok % 4 == 0), as a
 // persistent loop: a warp walks its rows with the NEXT row's position-embedding row and track features already on
-// their way into shared memory (cp.async, two buffers per warp), so the loop runs at issue rate instead of one memory
-// round trip per row.  A lane owns whole float4 groups of the row; one sincosf serves a (sin, cos) channel pair; the
+// their way into shared memory (reduce mode: two bulk copies per row onto the buffer's mbarrier; store mode: cp.async
+// of the groups it needs), so the loop runs at issue rate instead of one memory round trip per row.  A lane owns whole float4 groups of the row; one sincosf serves a (sin, cos) channel pair; the
 // row is written with STG.128.  Groups that lie entirely inside the window channels are skipped unless p.red (then
 // they receive the position embedding the bulk reductions add to).
 // `buf`: this warp's 3 x (D_tok + KC) floats of dynamic shared memory.
@@ -524,6 +533,17 @@ __device__ __forceinline__ void token_misc_rows_v4(const Params& p, long long wa
   auto needed = [&](int k) { return k < nv && (p.red || k < f_lo || k >= f_hi); };
   // position-embedding groups this lane needs + its float4 of the track features -> shared memory buffer `which`;
   // the flow of the row (coordinates of this frame minus frame 0) into registers
+  // reduce mode copies whole rows: two bulk copies per row (position-embedding row, track features) onto the buffer's
+  // mbarrier, issued by one lane -- no per-lane copy instructions and nothing through the L1TEX pipe
+  uint64_t* mb = reinterpret_cast<uint64_t*>(buf + 3 * bstride);   // [3], one per buffer
+  if (p.red) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) mbar_init(&mb[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  uint32_t mphase = 0;                                              // bit i: parity buffer i's next completion has
   auto issue = [&](int row, int which, float& flx, float& fly) {
     flx = 0.f; fly = 0.f;
     if (row < rows) {
@@ -531,15 +551,23 @@ __device__ __forceinline__ void token_misc_rows_v4(const Params& p, long long wa
       const int b_ = bn / p.N, n_ = bn - b_ * p.N;
       const uint32_t dst = smem_u32(buf + which * bstride);
       const float4* pq = reinterpret_cast<const float4*>(p.pos + (long long)bn * p.D_tok);
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int k = lane + 32 * t;
-        if (needed(k))
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(pq + k) : "memory");
-      }
       const float4* tq = reinterpret_cast<const float4*>(p.targets + b_ * p.t_sb + s_ * p.t_ss + (long long)n_ * p.t_sn);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                   ::"r"(dst + (uint32_t)(nv + lane) * 16u), "l"(tq + lane) : "memory");
+      if (p.red) {
+        if (lane == 0) {
+          mbar_expect_tx(&mb[which], (uint32_t)(p.D_tok + KC) * 4u);
+          bulk_load(buf + which * bstride, pq, (uint32_t)p.D_tok * 4u, &mb[which]);
+          bulk_load(buf + which * bstride + p.D_tok, tq, (uint32_t)KC * 4u, &mb[which]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int k = lane + 32 * t;
+          if (needed(k))
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 16u), "l"(pq + k) : "memory");
+        }
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"(dst + (uint32_t)(nv + lane) * 16u), "l"(tq + lane) : "memory");
+      }
       const float* c0 = p.coords + b_ * p.c_sb + (long long)n_ * p.c_sn;  // frame 0
       const float* cp = c0 + s_ * p.c_ss;
       flx = __ldg(cp) - __ldg(c0);
@@ -554,8 +582,13 @@ __device__ __forceinline__ void token_misc_rows_v4(const Params& p, long long wa
   for (int row = w0; row < rows; row += nw, which = which == 2 ? 0 : which + 1) {
     float flx1, fly1;
     issue(row + nw, which == 2 ? 0 : which + 1, flx1, fly1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();                                   // the feature row was copied by all 32 lanes
+    if (p.red) {
+      mbar_wait(&mb[which], (mphase >> which) & 1u, p.status, 11);
+      mphase ^= 1u << which;
+    } else {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();                                 // the feature row was copied by all 32 lanes
+    }
     float* o = p.out + (long long)row * p.D_tok;
     if (p.red) {
       // Whole row leaves as ONE bulk store: the position-embedding row sits in shared memory; add the few channels that
@@ -638,7 +671,7 @@ __global__ void __launch_bounds__(256) tc_pre_kernel(const Params p, int* __rest
     const long long nw = (long long)(gridDim.x - p.BS) * 8;
     extern __shared__ __align__(16) float pre_smem[];   // vec4: 8 warps x 3 x (D_tok + KC) floats
     if (p.vec4) token_misc_rows_v4(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31,
-                                   pre_smem + (threadIdx.x >> 5) * 3 * (p.D_tok + KC));
+                                   pre_smem + (threadIdx.x >> 5) * (3 * (p.D_tok + KC) + 8));
     else token_misc_rows(p, (long long)(blockIdx.x - p.BS) * 8 + (threadIdx.x >> 5), nw, threadIdx.x & 31);
   }
   // programmatic dependent launch: once every CTA of this grid got here the tensor kernel may be scheduled, so its
@@ -749,6 +782,10 @@ corr_tc_kernel(const Params p) {
       const uint32_t nbytes = BF16 ? B_TILE_BYTES : STAGE_BYTES;   // autocast mode issues hi x hi only: fetch the hi half
       uint32_t stage = 0, phase = 0;
       int tcount = 0;
+#if COMET_TC_EVICT_FIRST
+      uint64_t l2_policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy));
+#endif
       Cursor ld;
       cursor_init(ld);
 #if COMET_TC_L2PF > 0
@@ -771,7 +808,11 @@ corr_tc_kernel(const Params p) {
           mbar_arrive(&full[stage]);
         } else {
           mbar_expect_tx(&full[stage], nbytes);
+#if COMET_TC_EVICT_FIRST
+          bulk_load_hint(dst, p.split + ((long long)ld.cur.bs * NTILES + ld.t) * STAGE_BYTES, nbytes, &full[stage], l2_policy);
+#else
           bulk_load(dst, p.split + ((long long)ld.cur.bs * NTILES + ld.t) * STAGE_BYTES, nbytes, &full[stage]);
+#endif
         }
 #if COMET_TC_L2PF > 0
         prefetch();
@@ -1448,7 +1489,7 @@ static int launch(Params& p, const void* split, void* workspace, cudaStream_t st
     misc = ((long long)p.B * p.N * p.S + 7) / 8;
     if (p.vec4) {
       // persistent rows loop: 2 CTAs per SM (8 warps x 3 row buffers each)
-      pre_smem = (size_t)8 * 3 * (p.D_tok + KC) * sizeof(float);
+      pre_smem = (size_t)8 * (3 * (p.D_tok + KC) + 8) * sizeof(float);
       if (misc > 2LL * sms) misc = 2LL * sms;
     }
     if (misc > 64LL * sms) misc = 64LL * sms;
