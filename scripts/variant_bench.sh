@@ -11,7 +11,7 @@ import json, sys
 n = sys.argv[1]
 try:
     d = json.loads(open(f"gpurun_out/vb_{n}.json").read().strip().splitlines()[-1])
-    print(n, "coarse_tokens ms", round(d["kernels"]["coarse_tokens"]["ms_avg"], 4), "step", round(d["ms_per_step"], 3))
+    print(n, "coarse_tokens ms", round(d["kernels"]["coarse_tokens"]["ms_avg"], 4), "coarse_pyramid ms", round(d["kernels"]["coarse_pyramid"]["ms_avg"], 4), "step", round(d["ms_per_step"], 3))
 except Exception as e:
     print(n, "failed", e, open(f"gpurun_out/vb_{n}.err").read()[-500:])
 PY
