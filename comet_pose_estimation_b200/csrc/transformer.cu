@@ -35,6 +35,18 @@ __device__ __forceinline__ void store_planes(__nv_bfloat16* p0, long long plane_
   }
 }
 
+// four consecutive values as np bf16 planes: one 8-byte store per plane (idx and plane_stride multiples of 4, base 8-byte aligned)
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* p0, long long plane_stride, long long idx, float4 v, int np) {
+  for (int k = 0; k < np; ++k) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&a);
+    pk.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p0 + k * plane_stride + idx) = pk;
+    v.x -= __low2float(a); v.y -= __high2float(a); v.z -= __low2float(b); v.w -= __high2float(b);
+  }
+}
+
 // One warp per row; D <= 32 * KPL (KPL values per lane, compile time).
 constexpr int LN_MAX_PER_LANE = 32;
 template <int KPL>
@@ -78,6 +90,72 @@ __global__ void __launch_bounds__(256) layernorm_planes_kernel(const float* __re
   }
 }
 
+// The same with 16-byte accesses: a lane owns KG groups of four consecutive columns (column 4 * lane + 128 * g), so a row
+// is read with LDG.128, written with STG.128 (float32) and STG.64 (four bf16 of a plane) -- the scalar kernel issues
+// 12 + 12 + 36 memory instructions per lane for a 384-wide row with three planes, this one 3 + 3 + 9.
+// Needs D % 4 == 0 and 16-byte aligned rows (8-byte for the planes); D <= 128 * KG.
+template <int KG>
+__global__ void __launch_bounds__(256) layernorm_planes_v4_kernel(const float* __restrict__ x, long long x_ld,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float eps, float* __restrict__ out, long long out_ld,
+                                                                   __nv_bfloat16* __restrict__ planes, long long plane_stride,
+                                                                   long long p_ld, int np, long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float4 gm[KG], bt[KG];
+#pragma unroll
+  for (int g = 0; g < KG; ++g) {
+    const int c = 4 * lane + 128 * g;
+    gm[g] = (gamma && c < D) ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    bt[g] = (beta && c < D) ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + r * x_ld;
+    float4 v[KG];
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+      const int c = 4 * lane + 128 * g;
+      v[g] = c < D ? __ldg(reinterpret_cast<const float4*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[g].x + v[g].y) + (v[g].z + v[g].w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+      const int c = 4 * lane + 128 * g;
+      if (c < D) {
+        const float dx = v[g].x - mean, dy = v[g].y - mean, dz = v[g].z - mean, dw = v[g].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+      const int c = 4 * lane + 128 * g;
+      if (c < D) {
+        float y[4] = {(v[g].x - mean) * rstd, (v[g].y - mean) * rstd, (v[g].z - mean) * rstd, (v[g].w - mean) * rstd};
+        if (gamma) {
+          y[0] = y[0] * gm[g].x + bt[g].x; y[1] = y[1] * gm[g].y + bt[g].y;
+          y[2] = y[2] * gm[g].z + bt[g].z; y[3] = y[3] * gm[g].w + bt[g].w;
+        }
+        if (out) *reinterpret_cast<float4*>(out + r * out_ld + c) = make_float4(y[0], y[1], y[2], y[3]);
+        if (planes) {
+          for (int k = 0; k < np; ++k) {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(y[0], y[1]), b = __floats2bfloat162_rn(y[2], y[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&a);
+            pk.y = *reinterpret_cast<const uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(planes + k * plane_stride + r * p_ld + c) = pk;
+            y[0] -= __low2float(a); y[1] -= __high2float(a); y[2] -= __low2float(b); y[3] -= __high2float(b);
+          }
+        }
+      }
+    }
+  }
+}
+
 // q/k/v element (batch b, position i, head h, dim d) at ptr + b * sb + i * si + h * dh + d  (float32).
 // One warp per (batch, head, query position); scores of a query live in shared memory (Lk floats per warp).
 struct AttnParams {
@@ -88,6 +166,7 @@ struct AttnParams {
   int np;
   int B, H, Lq, Lk, dh;
   float scale;
+  int vec_out;   // output planes can be written four values (8 bytes) at a time
 };
 // One CTA per (batch item, head, chunk of ATT_QB queries): the query chunk and one tile of ATT_KT keys / values are staged
 // in shared memory (coalesced 128-bit loads, rows padded by 4 floats so that lanes <-> keys read conflict-free
@@ -299,6 +378,13 @@ __global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const A
         *reinterpret_cast<float4*>(Os + lane * OLD + 4 * t) = make_float4(acc[t].x * inv, acc[t].y * inv, acc[t].z * inv, acc[t].w * inv);
     }
     __syncwarp();
+    if (p.vec_out) {
+      for (int e = lane; e < p.Lq * dh4; e += 32) {
+        const int i = e / dh4, t = e - i * dh4;
+        store_planes4(p.out, p.o_plane_stride, b * p.o_sb + (long long)i * p.o_si + h * p.dh + 4 * t,
+                      *reinterpret_cast<const float4*>(Os + i * OLD + 4 * t), p.np);
+      }
+    } else
     for (int e = lane; e < p.Lq * p.dh; e += 32) {
       const int i = e / p.dh, d = e - i * p.dh;
       store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)i * p.o_si + h * p.dh + d, Os[i * OLD + d], p.np);
@@ -387,6 +473,13 @@ __global__ void __launch_bounds__(ATR_WARPS * 32) attention_rows_kernel(const At
     __syncwarp();
     const int q0w = qc * (ATR_WARPS * 32) + warp * 32;
     const int nqw = min(32, p.Lq - q0w);
+    if (p.vec_out) {
+      for (int e = lane; e < nqw * dh4; e += 32) {
+        const int i = e / dh4, t = e - i * dh4;
+        store_planes4(p.out, p.o_plane_stride, b * p.o_sb + (long long)(q0w + i) * p.o_si + h * p.dh + 4 * t,
+                      *reinterpret_cast<const float4*>(Os + i * OLD + 4 * t), p.np);
+      }
+    } else
     for (int e = lane; e < nqw * p.dh; e += 32) {
       const int i = e / p.dh, d = e - i * p.dh;
       store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)(q0w + i) * p.o_si + h * p.dh + d, Os[i * OLD + d], p.np);
@@ -521,6 +614,13 @@ __global__ void __launch_bounds__(256) attention_ksplit_kernel(const AttnParams 
       __syncwarp();
       const int q0w = qc * 64 + grp * 32;
       const int nqw = min(32, p.Lq - q0w);
+      if (p.vec_out) {
+        for (int e = lane; e < nqw * (p.dh >> 2); e += 32) {
+          const int i = e / (p.dh >> 2), t = e - i * (p.dh >> 2);
+          store_planes4(p.out, p.o_plane_stride, b * p.o_sb + (long long)(q0w + i) * p.o_si + h * p.dh + 4 * t,
+                        *reinterpret_cast<const float4*>(Os + i * MP + 4 * t), p.np);
+        }
+      } else
       for (int e = lane; e < nqw * p.dh; e += 32) {
         const int i = e / p.dh, d = e - i * p.dh;
         store_planes(p.out, p.o_plane_stride, b * p.o_sb + (long long)(q0w + i) * p.o_si + h * p.dh + d, Os[i * MP + d], p.np);
@@ -552,6 +652,21 @@ extern "C" int comet_layernorm_planes_f32(const float* x, long long x_ld, const 
   long long blocks = (rows + 7) / 8;
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   __nv_bfloat16* pl = np > 0 ? reinterpret_cast<__nv_bfloat16*>(planes) : nullptr;
+  const bool v4 = (D % 4) == 0 && D <= 512 && (x_ld % 4) == 0 && ((uintptr_t)x % 16) == 0 &&
+                  (!out || ((out_ld % 4) == 0 && ((uintptr_t)out % 16) == 0)) &&
+                  (!pl || ((p_ld % 4) == 0 && (plane_stride % 4) == 0 && ((uintptr_t)pl % 8) == 0)) &&
+                  (!gamma || (((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0));
+  if (v4) {
+#define COMET_LN4_LAUNCH(KG)                                                                                        \
+  layernorm_planes_v4_kernel<KG><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, gamma, beta, eps, out, out_ld, pl, \
+                                                                                     plane_stride, p_ld, np, rows, D)
+    if (D <= 128) COMET_LN4_LAUNCH(1);
+    else if (D <= 256) COMET_LN4_LAUNCH(2);
+    else if (D <= 384) COMET_LN4_LAUNCH(3);
+    else COMET_LN4_LAUNCH(4);
+#undef COMET_LN4_LAUNCH
+    return launch_status("layernorm_planes_v4_kernel");
+  }
 #define COMET_LN_LAUNCH(KPL)                                                                                        \
   layernorm_planes_kernel<KPL><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, gamma, beta, eps, out, out_ld, pl, \
                                                                                   plane_stride, p_ld, np, rows, D)
@@ -579,7 +694,8 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
                     k_si % 4 == 0, "q / k rows must be 16-byte aligned");
   COMET_REQUIRE(((uintptr_t)v % 16) == 0 && v_sb % 4 == 0 && v_si % 4 == 0, "v rows must be 16-byte aligned");
   AttnParams p{q, q_sb, q_si, k, k_sb, k_si, v, v_sb, v_si, reinterpret_cast<__nv_bfloat16*>(out_planes),
-               o_plane_stride, o_sb, o_si, np, B, H, Lq, Lk, dh, 1.0f / sqrtf((float)dh)};
+               o_plane_stride, o_sb, o_si, np, B, H, Lq, Lk, dh, 1.0f / sqrtf((float)dh),
+               (o_sb % 4 == 0 && o_si % 4 == 0 && o_plane_stride % 4 == 0 && ((uintptr_t)out_planes % 8) == 0) ? 1 : 0};
   if (Lq <= 32 && Lk <= 32) {
     long long nb = ((long long)B * H + ATS_WARPS - 1) / ATS_WARPS;
     if (nb > 148LL * 16) nb = 148LL * 16;
