@@ -49,6 +49,10 @@ SIGNATURES = {
     "comet_upsample_bilinear_ac_f32": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _i, _p]),
     "comet_instance_norm_f32": (_i, [_p, _p, _ll, _i, _i, _i, _i, C.c_float, _p]),
     "comet_extract_patches_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_shallow_encoder_packed_elems": (_ll, []),
+    "comet_shallow_encoder_pack_f32": (_i, [_p, _p, _p]),
+    "comet_shallow_encoder_f32": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _ll, C.c_float, _p]),
+    "comet_shallow_encoder_from_images_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, C.c_float, _p]),
     "comet_embed2d_f32": (_i, [_p, _p, _ll, _i, _i, _p]),
     "comet_sincos1d_from_grid_f32": (_i, [_p, _p, _ll, _i, _p]),
     "comet_sincos2d_f32": (_i, [_p, _i, _i, _i, _p]),

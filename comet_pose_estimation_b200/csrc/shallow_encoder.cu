@@ -1,0 +1,416 @@
+// ShallowEncoder of the fine tracker (comet/models/track_modules/blocks.py:114-196, norm_fn="instance"; ResidualBlock:
+// comet/models/modules.py:39-117) as ONE kernel: patch gather (refine_track.py:71-111) -> conv1 3x3/2 -> InstanceNorm ->
+// ReLU -> two stride-2 residual blocks -> two bilinear residual up-samplings -> 1x1 conv + skip, for 31x31 patches.
+//
+// Every operator of the encoder is local to one patch (instance norm reduces over the positions of one patch and one
+// channel), so a patch never has to leave the SM between its 3-channel pixels and the 16x16x32 map the fine tracker
+// consumes (blocks.Upsampled2x evaluates the encoder's last 16x16 -> 31x31 resize lazily).  One CTA carries two
+// patches through all layers in shared memory (77 KB each); HBM sees 11.5 KB in and 32 KB out per patch.  The library
+// convolutions + separate norm / resize kernels this replaces wrote and re-read ten intermediate maps per patch.
+//
+// Arithmetic is float32 FMA (the reference's float32 convolution; no TF32): 2.04 M multiply-adds per patch, so this
+// kernel is bound by the FP32 pipe, not by HBM: 8192 patches of a 512-track, 16-frame sequence are 16.7 G multiply-adds
+// against 37 T/s (148 SMs x 128 lanes x 1.965 GHz).
+//
+// Work split inside the CTA (8 warps): a warp task is 16 output positions x 32 output channels, lane = output channel.
+// Per 4 input channels a lane loads its 4 weights with one 16-byte load (L1-resident packed layout [tap][ci/4][co][4])
+// and, per position, the 4 inputs with one 16-byte *broadcast* shared load (channel-last activations) -> 64 FMA per
+// 17 loads.  The 4x4 layers have only 32 positions per CTA: their 288-deep sums are split four ways over the input
+// channels and combined in a fixed order (deterministic).
+#include "comet_common.cuh"
+
+namespace comet {
+namespace senc {
+
+constexpr int C = 32;            // feature channels
+constexpr int G = 2;             // patches per CTA
+constexpr int THREADS = 256;
+constexpr int PSZ = 31;          // patch extent
+
+// per-patch shared-memory map (float offsets).  Padded buffers carry the zero border the next convolution reads.
+constexpr int IN_W = 33;                       // input 31x31 padded by one on every side, 4 floats per position (RGB0)
+constexpr int OFF_IN = 0;                      // [33*33][4]   = 4356
+constexpr int OFF_A8P = 0;                     // [10*10][32]  = 3200   (aliases IN once conv1 is done)
+constexpr int OFF_A4P = 3200;                  // [6*6][32]    = 1152   (aliases IN)
+constexpr int XP_W = 17;                       // 16x16 map padded on top / left
+constexpr int OFF_XP = 4356;                   // [17*17][32]  = 9248
+constexpr int OFF_B8 = OFF_XP + 9248;          // [8*8][32]    = 2048   (later: the four partial sums of the 4x4 layers)
+constexpr int T1P_W = 9;                       // 8x8 map padded on top / left
+constexpr int OFF_T1P = OFF_B8 + 2048;         // [9*9][32]    = 2592
+constexpr int OFF_B4 = OFF_T1P + 2592;         // [4*4][32]    = 512
+constexpr int OFF_T2 = OFF_B4 + 512;           // [4*4][32]    = 512
+constexpr int PATCH_FLOATS = OFF_T2 + 512;     // 19268 floats = 77072 bytes
+constexpr int RED_FLOATS = 2 * G * 4 * C;      // two reduction scratch arrays [G][4][32]
+constexpr int SMEM_BYTES = (G * PATCH_FLOATS + RED_FLOATS) * 4;
+
+// packed parameter blob (float offsets): weights [tap][ci/4][co][4], then 32 biases, per layer
+constexpr int W_CONV1 = 0, B_CONV1 = 1152;
+constexpr int W_L1C1 = 1184, B_L1C1 = W_L1C1 + 9216;
+constexpr int W_L1C2 = B_L1C1 + 32, B_L1C2 = W_L1C2 + 9216;
+constexpr int W_L1DN = B_L1C2 + 32, B_L1DN = W_L1DN + 1024;
+constexpr int W_L2C1 = B_L1DN + 32, B_L2C1 = W_L2C1 + 9216;
+constexpr int W_L2C2 = B_L2C1 + 32, B_L2C2 = W_L2C2 + 9216;
+constexpr int W_L2DN = B_L2C2 + 32, B_L2DN = W_L2DN + 1024;
+constexpr int W_CONV2 = B_L2DN + 32, B_CONV2 = W_CONV2 + 1024;
+constexpr int PACKED_FLOATS = B_CONV2 + 32;    // 41344
+
+// 16 positions x 32 channels of one convolution: acc[j] += sum over taps and the input-channel groups [cb, cb+NC) of
+// in[position j, tap, ci] * w[tap, ci, lane].  Position j of the task sits at (j / OW, j % OW) of an OW-wide output
+// block; `in0` is the (padded) input address of position 0's first tap, WP the padded input width, CPP the floats per
+// input position, KW x KW the kernel, CH = CPP / 4 channel groups per tap.
+template <int OW, int STRIDE, int WP, int CPP, int KW, int NC>
+__device__ __forceinline__ void conv16(const float* __restrict__ in0, const float4* __restrict__ w, int lane, int cb,
+                                       float (&acc)[16]) {
+  constexpr int CH = CPP / 4;
+#pragma unroll 1
+  for (int tap = 0; tap < KW * KW; ++tap) {
+    const int ky = tap / KW, kx = tap - ky * KW;
+    const float* pt = in0 + (ky * WP + kx) * CPP + cb * 4;
+    const float4* wt = w + (tap * CH + cb) * 32 + lane;
+#pragma unroll 2
+    for (int i = 0; i < NC; ++i) {
+      const float4 wv = __ldg(wt + i * 32);
+      const float* p = pt + i * 4;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(p + ((j / OW) * STRIDE * WP + (j % OW) * STRIDE) * CPP);
+        acc[j] = fmaf(x.x, wv.x, acc[j]);
+        acc[j] = fmaf(x.y, wv.y, acc[j]);
+        acc[j] = fmaf(x.z, wv.z, acc[j]);
+        acc[j] = fmaf(x.w, wv.w, acc[j]);
+      }
+    }
+  }
+}
+
+// store the 16 x 32 block: position j -> out0 + ((j / OW) * OWP + j % OW) * 32 + lane
+template <int OW, int OWP>
+__device__ __forceinline__ void store16(float* out0, int lane, const float (&acc)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out0[((j / OW) * OWP + (j % OW)) * C + lane] = acc[j];
+}
+
+__device__ __forceinline__ void fill16(float (&acc)[16], float v) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = v;
+}
+
+// nn.InstanceNorm2d(affine=False) over the OW x OW interior of a buffer whose rows are OWP positions wide, for both
+// patches of the CTA: thread <-> (patch g, position class q = positions q, q+4, .., channel).  Biased variance, two
+// passes.  `x0` / `acc0` point at patch 0 (patch g: + g * PATCH_FLOATS).  relu: y = max(y, 0).  With `acc0` the result
+// is not written back but folded into the residual sum: acc = max(acc + y, 0)  (modules.py:115-117).
+template <int OW, int OWP, int AWP>
+__device__ __forceinline__ void inorm(float* x0, float* acc0, bool relu, float eps, float* red, int tid) {
+  constexpr int NPOS = OW * OW;
+  const int g = tid >> 7, q = (tid >> 5) & 3, co = tid & 31;
+  float* x = x0 + g * PATCH_FLOATS + co;
+  float* r1 = red + (g * 4) * C + co;
+  float* r2 = r1 + G * 4 * C;
+  float s = 0.f;
+#pragma unroll 4
+  for (int p = q; p < NPOS; p += 4) s += x[((p / OW) * OWP + (p % OW)) * C];
+  r1[q * C] = s;
+  __syncthreads();
+  const float mean = (((r1[0] + r1[C]) + r1[2 * C]) + r1[3 * C]) * (1.f / (float)NPOS);
+  float v = 0.f;
+#pragma unroll 4
+  for (int p = q; p < NPOS; p += 4) {
+    const float d = x[((p / OW) * OWP + (p % OW)) * C] - mean;
+    v = fmaf(d, d, v);
+  }
+  r2[q * C] = v;
+  __syncthreads();
+  const float rstd = rsqrtf((((r2[0] + r2[C]) + r2[2 * C]) + r2[3 * C]) * (1.f / (float)NPOS) + eps);
+  float* a = acc0 ? acc0 + g * PATCH_FLOATS + co : nullptr;
+#pragma unroll 4
+  for (int p = q; p < NPOS; p += 4) {
+    const int o = ((p / OW) * OWP + (p % OW)) * C;
+    float y = (x[o] - mean) * rstd;
+    if (relu) y = fmaxf(y, 0.f);
+    if (a) {
+      const int oa = ((p / OW) * AWP + (p % OW)) * C;
+      a[oa] = fmaxf(a[oa] + y, 0.f);
+    } else {
+      x[o] = y;
+    }
+  }
+  __syncthreads();
+}
+
+// x (16x16 interior of the padded XP buffer) += F.interpolate(t, (16, 16), "bilinear", align_corners=True) of the
+// IW x IW map `t0` (rows TWP positions wide); ATen's arithmetic: src = dst * (in-1)/(out-1), i0 = (int)src,
+// i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1, value = wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11).
+template <int IW, int TWP>
+__device__ __forceinline__ void upsample_add(float* xp0, const float* t0, int warp, int lane) {
+  const int g = warp >> 2;
+  float* xp = xp0 + g * PATCH_FLOATS + lane;
+  const float* t = t0 + g * PATCH_FLOATS + lane;
+  const float scale = (float)(IW - 1) / 15.f;
+#pragma unroll 1
+  for (int yo = (warp & 3) * 4; yo < (warp & 3) * 4 + 4; ++yo) {
+    const float sy = scale * (float)yo;
+    const int y0 = (int)sy, y1 = y0 + (y0 < IW - 1 ? 1 : 0);
+    const float wy1 = sy - (float)y0, wy0 = 1.f - wy1;
+#pragma unroll 4
+    for (int xo = 0; xo < 16; ++xo) {
+      const float sx = scale * (float)xo;
+      const int x0 = (int)sx, x1 = x0 + (x0 < IW - 1 ? 1 : 0);
+      const float wx1 = sx - (float)x0, wx0 = 1.f - wx1;
+      const float v00 = t[(y0 * TWP + x0) * C], v01 = t[(y0 * TWP + x1) * C];
+      const float v10 = t[(y1 * TWP + x0) * C], v11 = t[(y1 * TWP + x1) * C];
+      xp[((yo + 1) * XP_W + xo + 1) * C] += wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
+    }
+  }
+}
+
+// zero the border cells of a padded [HP][WP][CPP] buffer of both patches (FULL: all four sides, else top row / left column)
+template <int WP, int CPP, bool FULL>
+__device__ __forceinline__ void zero_border(float* b0, int tid) {
+  for (int i = tid; i < G * WP * WP * CPP; i += THREADS) {
+    const int g = i / (WP * WP * CPP), r = i - g * (WP * WP * CPP);
+    const int cell = r / CPP, y = cell / WP, x = cell - y * WP;
+    if (y == 0 || x == 0 || (FULL && (y == WP - 1 || x == WP - 1))) b0[g * PATCH_FLOATS + r] = 0.f;
+  }
+}
+
+struct Params {
+  const float* src;        // images (B,S,3,H,W) or a patch tensor
+  const int* topleft;      // (B,S,N,2) (x, y) corners, or null: `src` holds the patches themselves
+  const float* packed;
+  float* out;              // (P, 16, 16, 32) channel-last
+  long long P;             // number of patches
+  long long sn, sc, sy, sx;  // element strides of the patch tensor (topleft == null) / of the image (sc, sy, sx)
+  int S, N, H, W;
+  float eps;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* red = smem + G * PATCH_FLOATS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ pk = p.packed;
+
+  // ---- phase 0: zero the padded input and the borders nobody overwrites, then gather the two patches ----------------
+  for (int i = tid; i < G * (IN_W * IN_W); i += THREADS) {
+    const int g = i / (IN_W * IN_W), r = i - g * (IN_W * IN_W);
+    reinterpret_cast<float4*>(smem + g * PATCH_FLOATS + OFF_IN)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  zero_border<XP_W, C, false>(smem + OFF_XP, tid);
+  zero_border<T1P_W, C, false>(smem + OFF_T1P, tid);
+  const float* base[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    long long pi = (long long)blockIdx.x * G + g;
+    if (pi >= p.P) pi = p.P - 1;   // odd patch count: the last CTA encodes the last patch twice and stores it once
+    if (p.topleft) {
+      const int s = (int)(pi % p.S);
+      const long long bn = pi / p.S;
+      const int n = (int)(bn % p.N);
+      const long long b = bn / p.N;
+      const int* tl = p.topleft + ((b * p.S + s) * p.N + n) * 2;
+      const int x0 = min(max(__ldg(tl), 0), p.W - PSZ), y0 = min(max(__ldg(tl + 1), 0), p.H - PSZ);
+      base[g] = p.src + (b * p.S + s) * 3 * p.sc + (long long)y0 * p.sy + (long long)x0 * p.sx;
+    } else {
+      base[g] = p.src + pi * p.sn;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < G * 3 * PSZ * PSZ; i += THREADS) {
+    const int g = i / (3 * PSZ * PSZ), r = i - g * (3 * PSZ * PSZ);
+    const int c = r / (PSZ * PSZ), yx = r - c * (PSZ * PSZ), y = yx / PSZ, x = yx - y * PSZ;
+    const float* b = g == 0 ? base[0] : base[1];
+    smem[g * PATCH_FLOATS + OFF_IN + ((y + 1) * IN_W + x + 1) * 4 + c] = __ldg(b + c * p.sc + y * p.sy + x * p.sx);
+  }
+  __syncthreads();
+
+  float acc[16];
+
+  // ---- phase 1: conv1 (3 -> 32, 3x3, stride 2): 32 row tasks (patch, output row) ------------------------------------
+  {
+    const float bias = __ldg(pk + B_CONV1 + lane);
+    const float4* w = reinterpret_cast<const float4*>(pk + W_CONV1);
+#pragma unroll 1
+    for (int t = warp; t < G * 16; t += 8) {
+      const int g = t >> 4, oy = t & 15;
+      fill16(acc, bias);
+      conv16<16, 2, IN_W, 4, 3, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W) * 4, w, lane, 0, acc);
+      store16<16, XP_W>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1) * C, lane, acc);
+    }
+  }
+  __syncthreads();
+  // the input is dead: its space now holds the padded 8x8 / 4x4 maps, whose borders must read as zero
+  zero_border<10, C, true>(smem + OFF_A8P, tid);
+  zero_border<6, C, true>(smem + OFF_A4P, tid);
+  inorm<16, XP_W, 0>(smem + OFF_XP + (XP_W + 1) * C, nullptr, true, p.eps, red, tid);      // x0 = relu(norm1(conv1))
+
+  // ---- phase 2: layer1.conv1 (3x3 / 2) -> A8, layer1.downsample (1x1 / 2) -> T1: warp <-> (patch, two output rows) --
+  {
+    const int g = warp >> 2, pg = warp & 3;
+    const float* xp = smem + g * PATCH_FLOATS + OFF_XP;
+    fill16(acc, __ldg(pk + B_L1C1 + lane));
+    conv16<8, 2, XP_W, C, 3, 8>(xp + (4 * pg * XP_W) * C, reinterpret_cast<const float4*>(pk + W_L1C1), lane, 0, acc);
+    store16<8, 10>(smem + g * PATCH_FLOATS + OFF_A8P + ((2 * pg + 1) * 10 + 1) * C, lane, acc);
+    fill16(acc, __ldg(pk + B_L1DN + lane));
+    conv16<8, 2, XP_W, C, 1, 8>(xp + ((4 * pg + 1) * XP_W + 1) * C, reinterpret_cast<const float4*>(pk + W_L1DN), lane, 0, acc);
+    store16<8, T1P_W>(smem + g * PATCH_FLOATS + OFF_T1P + ((2 * pg + 1) * T1P_W + 1) * C, lane, acc);
+  }
+  __syncthreads();
+  inorm<8, 10, 0>(smem + OFF_A8P + (10 + 1) * C, nullptr, true, p.eps, red, tid);           // relu(norm1(conv1))
+  inorm<8, T1P_W, 0>(smem + OFF_T1P + (T1P_W + 1) * C, nullptr, false, p.eps, red, tid);    // norm3(downsample)
+
+  // ---- phase 3: layer1.conv2 (3x3) -> B8; T1 = relu(T1 + relu(norm2(B8))) -------------------------------------------
+  {
+    const int g = warp >> 2, pg = warp & 3;
+    fill16(acc, __ldg(pk + B_L1C2 + lane));
+    conv16<8, 1, 10, C, 3, 8>(smem + g * PATCH_FLOATS + OFF_A8P + (2 * pg * 10) * C,
+                              reinterpret_cast<const float4*>(pk + W_L1C2), lane, 0, acc);
+    store16<8, 8>(smem + g * PATCH_FLOATS + OFF_B8 + (2 * pg * 8) * C, lane, acc);
+  }
+  __syncthreads();
+  inorm<8, 8, T1P_W>(smem + OFF_B8, smem + OFF_T1P + (T1P_W + 1) * C, true, p.eps, red, tid);
+
+  // ---- phase 4: x += up(T1);  layer2.conv1 (3x3 / 2) four-way split over ci -> partial sums;  layer2.downsample -> T2
+  {
+    const int g = warp >> 2, ks = warp & 3;
+    const float* t1 = smem + g * PATCH_FLOATS + OFF_T1P;
+    fill16(acc, 0.f);
+    conv16<4, 2, T1P_W, C, 3, 2>(t1, reinterpret_cast<const float4*>(pk + W_L2C1), lane, 2 * ks, acc);
+    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * 512, lane, acc);
+    if (ks == 0) {
+      fill16(acc, __ldg(pk + B_L2DN + lane));
+      conv16<4, 2, T1P_W, C, 1, 8>(t1 + (T1P_W + 1) * C, reinterpret_cast<const float4*>(pk + W_L2DN), lane, 0, acc);
+      store16<4, 4>(smem + g * PATCH_FLOATS + OFF_T2, lane, acc);
+    }
+    upsample_add<8, T1P_W>(smem + OFF_XP, smem + OFF_T1P + (T1P_W + 1) * C, warp, lane);
+  }
+  __syncthreads();
+  for (int i = tid; i < G * 512; i += THREADS) {
+    const int g = i >> 9, r = i & 511, pos = r >> 5;
+    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + r;
+    smem[g * PATCH_FLOATS + OFF_A4P + (((pos >> 2) + 1) * 6 + (pos & 3) + 1) * C + (r & 31)] =
+        __ldg(pk + B_L2C1 + (r & 31)) + (((part[0] + part[512]) + part[1024]) + part[1536]);
+  }
+  __syncthreads();
+  inorm<4, 6, 0>(smem + OFF_A4P + (6 + 1) * C, nullptr, true, p.eps, red, tid);
+  inorm<4, 4, 0>(smem + OFF_T2, nullptr, false, p.eps, red, tid);
+
+  // ---- phase 5: layer2.conv2 (3x3), same split -> B4; T2 = relu(T2 + relu(norm2(B4))) -------------------------------
+  {
+    const int g = warp >> 2, ks = warp & 3;
+    fill16(acc, 0.f);
+    conv16<4, 1, 6, C, 3, 2>(smem + g * PATCH_FLOATS + OFF_A4P, reinterpret_cast<const float4*>(pk + W_L2C2), lane, 2 * ks, acc);
+    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * 512, lane, acc);
+  }
+  __syncthreads();
+  for (int i = tid; i < G * 512; i += THREADS) {
+    const int g = i >> 9, r = i & 511;
+    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + r;
+    smem[g * PATCH_FLOATS + OFF_B4 + r] = __ldg(pk + B_L2C2 + (r & 31)) + (((part[0] + part[512]) + part[1024]) + part[1536]);
+  }
+  __syncthreads();
+  inorm<4, 4, 4>(smem + OFF_B4, smem + OFF_T2, true, p.eps, red, tid);
+
+  // ---- phase 6: x += up(T2);  out = conv2(x) + x (1x1) ---------------------------------------------------------------
+  upsample_add<4, 4>(smem + OFF_XP, smem + OFF_T2, warp, lane);
+  __syncthreads();
+  {
+    const float bias = __ldg(pk + B_CONV2 + lane);
+    const float4* w = reinterpret_cast<const float4*>(pk + W_CONV2);
+#pragma unroll 1
+    for (int t = warp; t < G * 16; t += 8) {
+      const int g = t >> 4, oy = t & 15;
+      const long long pi = (long long)blockIdx.x * G + g;
+      if (pi >= p.P) continue;
+      const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1) * C;
+      fill16(acc, bias);
+      conv16<16, 1, XP_W, C, 1, 8>(row, w, lane, 0, acc);
+      float* o = p.out + (pi * 256 + oy * 16) * C + lane;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j * C] = acc[j] + row[j * C + lane];
+    }
+  }
+}
+
+// parameter packing: raw state-dict tensors (OIHW weights, biases) -> the blob the kernel reads
+struct PackParams {
+  const float* t[16];
+  float* packed;
+};
+__global__ void __launch_bounds__(256) shallow_encoder_pack_kernel(const PackParams pp) {
+  // layer l: weight t[2l] (32, CI, K, K), bias t[2l+1]; order conv1, layer1.{conv1,conv2,downsample.0},
+  // layer2.{conv1,conv2,downsample.0}, conv2
+  const int woff[8] = {W_CONV1, W_L1C1, W_L1C2, W_L1DN, W_L2C1, W_L2C2, W_L2DN, W_CONV2};
+  const int boff[8] = {B_CONV1, B_L1C1, B_L1C2, B_L1DN, B_L2C1, B_L2C2, B_L2DN, B_CONV2};
+  const int ci_n[8] = {3, 32, 32, 32, 32, 32, 32, 32};
+  const int kk[8] = {3, 3, 3, 1, 3, 3, 1, 1};
+  for (int l = 0; l < 8; ++l) {
+    const int CI = ci_n[l], K = kk[l], CH = (CI + 3) / 4, n = K * K * CH * 32 * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int e = i & 3, co = (i >> 2) & 31, r = i >> 7, c4 = r % CH, tap = r / CH, ci = c4 * 4 + e;
+      pp.packed[woff[l] + i] = ci < CI ? __ldg(pp.t[2 * l] + ((long long)co * CI + ci) * K * K + tap) : 0.f;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 32; i += gridDim.x * blockDim.x)
+      pp.packed[boff[l] + i] = __ldg(pp.t[2 * l + 1] + i);
+  }
+}
+
+}  // namespace senc
+}  // namespace comet
+
+using namespace comet;
+
+extern "C" long long comet_shallow_encoder_packed_elems(void) { return senc::PACKED_FLOATS; }
+
+extern "C" int comet_shallow_encoder_pack_f32(const float* const* params_host, float* packed, comet_stream_t stream) {
+  COMET_REQUIRE(params_host && packed, "null pointer");
+  senc::PackParams pp;
+  for (int i = 0; i < 16; ++i) {
+    COMET_REQUIRE(params_host[i], "parameter %d is null", i);
+    pp.t[i] = params_host[i];
+  }
+  pp.packed = packed;
+  senc::shallow_encoder_pack_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(pp);
+  return launch_status("shallow_encoder_pack_kernel");
+}
+
+static int launch_shallow_encoder(const senc::Params& p, comet_stream_t stream) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  COMET_CUDA(cudaGetDevice(&dev));
+  COMET_REQUIRE(device_sm_count_if_sm100() > 0, "the fused patch encoder needs an sm_100 device");
+  if (dev < 64 && !configured[dev]) {
+    COMET_CUDA(cudaFuncSetAttribute(senc::shallow_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, senc::SMEM_BYTES));
+    configured[dev] = true;
+  }
+  const long long ctas = (p.P + senc::G - 1) / senc::G;
+  COMET_REQUIRE(ctas <= 0x7fffffffLL, "too many patches");
+  senc::shallow_encoder_kernel<<<(unsigned)ctas, senc::THREADS, senc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  return launch_status("shallow_encoder_kernel");
+}
+
+extern "C" int comet_shallow_encoder_f32(const float* patches, long long sn, long long sc, long long sy, long long sx,
+                                         const float* packed, float* out, long long P, float eps, comet_stream_t stream) {
+  COMET_REQUIRE(P >= 0, "bad shape");
+  if (P == 0) return COMET_OK;
+  COMET_REQUIRE(patches && packed && out, "null pointer");
+  COMET_REQUIRE(((uintptr_t)packed % 16) == 0, "packed parameters must be 16-byte aligned");
+  senc::Params p{};
+  p.src = patches; p.topleft = nullptr; p.packed = packed; p.out = out; p.P = P;
+  p.sn = sn; p.sc = sc; p.sy = sy; p.sx = sx;
+  p.S = 1; p.N = 1; p.H = senc::PSZ; p.W = senc::PSZ; p.eps = eps;
+  return launch_shallow_encoder(p, stream);
+}
+
+extern "C" int comet_shallow_encoder_from_images_f32(const float* images, const int* topleft, const float* packed, float* out,
+                                                     int B, int S, int N, int H, int W, float eps, comet_stream_t stream) {
+  COMET_REQUIRE(B >= 0 && S >= 0 && N >= 0 && H >= senc::PSZ && W >= senc::PSZ, "bad shape");
+  const long long P = (long long)B * S * N;
+  if (P == 0) return COMET_OK;
+  COMET_REQUIRE(images && topleft && packed && out, "null pointer");
+  COMET_REQUIRE(((uintptr_t)packed % 16) == 0, "packed parameters must be 16-byte aligned");
+  senc::Params p{};
+  p.src = images; p.topleft = topleft; p.packed = packed; p.out = out; p.P = P;
+  p.sn = 0; p.sc = (long long)H * W; p.sy = W; p.sx = 1;
+  p.S = S; p.N = N; p.H = H; p.W = W; p.eps = eps;
+  return launch_shallow_encoder(p, stream);
+}

@@ -34,6 +34,9 @@ from .blocks import Upsampled2x, up2_supported
 USE_LIBRARY_KERNELS = True
 # False makes refine_track materialise the up-sampled patch features (the reference's data flow; A/B timing and tests)
 DEFER_UPSAMPLE = True
+# False keeps the encoder on the per-operator path (cuDNN convolutions + the library's norm / resize kernels) instead of
+# the fused one-kernel encoder (csrc/shallow_encoder.cu); A/B timing and tests
+USE_FUSED_ENCODER = True
 
 
 def _library_ok(x: torch.Tensor) -> bool:
@@ -113,10 +116,78 @@ class ShallowEncoder(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
+    _PARAM_ORDER = ("conv1", "layer1.conv1", "layer1.conv2", "layer1.downsample.0",
+                    "layer2.conv1", "layer2.conv2", "layer2.downsample.0", "conv2")
+
+    def _fused_ok(self, x: torch.Tensor, H: int, W: int) -> bool:
+        """The one-kernel encoder (csrc/shallow_encoder.cu) covers the shipped configuration: 3 -> 32 channels, stride 1,
+        31x31 patches, float32 parameters, CUDA inference.  Everything else takes the per-operator path below."""
+        w = self.conv1.weight
+        return (USE_FUSED_ENCODER and USE_LIBRARY_KERNELS and x.is_cuda and x.dtype == torch.float32 and (H, W) == (31, 31)
+                and tuple(w.shape) == (32, 3, 3, 3) and self.stride == 1 and w.dtype == torch.float32 and w.device == x.device
+                and not (torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)))
+
+    def packed_parameters(self) -> torch.Tensor:
+        """The 16 state-dict tensors in the layout the fused kernel reads (``comet_shallow_encoder_pack_f32``); rebuilt
+        when a parameter is replaced or modified in place."""
+        mods = [self.get_submodule(n) for n in self._PARAM_ORDER]
+        tensors = [t for m in mods for t in (m.weight, m.bias)]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        cache = getattr(self, "_packed_cache", None)
+        if cache is None or cache[0] != key:
+            import ctypes
+
+            from . import _lib
+            from ._dev import stream_ptr
+
+            dev = tensors[0].device
+            keep = [t.detach().contiguous() for t in tensors]
+            packed = torch.empty(int(_lib.lib.comet_shallow_encoder_packed_elems()), dtype=torch.float32, device=dev)
+            ptrs = (ctypes.c_void_p * 16)(*[t.data_ptr() for t in keep])
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib.comet_shallow_encoder_pack_f32(ptrs, packed.data_ptr(), stream_ptr(dev)))
+            cache = (key, packed)
+            object.__setattr__(self, "_packed_cache", cache)
+        return cache[1]
+
+    def _fused_result(self, half_cl: torch.Tensor, size, defer_upsample: bool):
+        half = half_cl.permute(0, 3, 1, 2)   # (P, 32, 16, 16) shape, channels-last memory
+        if defer_upsample:
+            return half, size
+        return _resize(half, size)
+
+    def encode_patches_of(self, images: torch.Tensor, topleft: torch.Tensor, defer_upsample: bool = True):
+        """``forward(extract_patches(images, topleft, 31))`` without the patch tensor: the kernel reads patch (b, n, s)
+        straight from ``images`` (B,S,3,H,W) at the clamped integer corners ``topleft`` (B,S,N,2)."""
+        from . import _lib
+        from ._dev import stream_ptr
+
+        B, S, _, H, W = images.shape
+        N = topleft.shape[2]
+        img = images.contiguous()
+        tl32 = topleft.to(torch.int32).contiguous()
+        out = torch.empty((B * N * S, 16, 16, 32), dtype=torch.float32, device=images.device)
+        with torch.cuda.device(images.device):
+            _lib.check(_lib.lib.comet_shallow_encoder_from_images_f32(
+                img.data_ptr(), tl32.data_ptr(), self.packed_parameters().data_ptr(), out.data_ptr(), B, S, N, H, W,
+                float(self.norm1.eps), stream_ptr(images.device)))
+        return self._fused_result(out, (31 // self.stride, 31 // self.stride), defer_upsample)
+
     def forward(self, x, defer_upsample: bool = False):
         """``defer_upsample=True`` returns the map *before* the last resize together with the size that resize would
         produce -- ``(x_half, (Ho, Wo))`` -- for callers that consume the up-sampling lazily (:class:`Upsampled2x`)."""
         _, _, H, W = x.shape
+        if self._fused_ok(x, H, W):
+            from . import _lib
+            from ._dev import stream_ptr
+
+            P = x.shape[0]
+            out = torch.empty((P, 16, 16, 32), dtype=torch.float32, device=x.device)
+            sn, sc, sy, sx = x.stride()
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.lib.comet_shallow_encoder_f32(x.data_ptr(), sn, sc, sy, sx, self.packed_parameters().data_ptr(),
+                                                              out.data_ptr(), P, float(self.norm1.eps), stream_ptr(x.device)))
+            return self._fused_result(out, (H // self.stride, W // self.stride), defer_upsample)
         x = _inorm(self.norm1, self.conv1(x), True)
         tmp = self.layer1(x)
         x = x + _resize(tmp, x.shape[-2:])
@@ -177,17 +248,25 @@ def refine_track(images, fine_fnet, fine_tracker, coarse_pred, pradius=15, sradi
     # otherwise); clamping x with W and y with H is the same for square images and stays in bounds for the others
     topleft = torch.stack([topleft[..., 0].clamp(0, W - psize), topleft[..., 1].clamp(0, H - psize)], dim=-1)
 
-    with torch.no_grad():
-        patch_input = extract_patches(images, topleft, psize)
     patch_feat = None
     from .base_track_predictor import BaseTrackerPredictor
 
-    if (USE_LIBRARY_KERNELS and DEFER_UPSAMPLE and isinstance(fine_fnet, ShallowEncoder) and patch_input.is_cuda
-            and isinstance(fine_tracker, BaseTrackerPredictor) and not torch.is_grad_enabled()):
+    lazy = (USE_LIBRARY_KERNELS and DEFER_UPSAMPLE and isinstance(fine_fnet, ShallowEncoder) and images.is_cuda
+            and isinstance(fine_tracker, BaseTrackerPredictor) and not torch.is_grad_enabled())
+    # one kernel from the images to the encoder's 16x16 map: the patches themselves are never written either
+    from_images = lazy and images.shape[2] == 3 and psize == 31 and fine_fnet._fused_ok(images, psize, psize)
+    patch_input = None
+    if not from_images:
+        with torch.no_grad():
+            patch_input = extract_patches(images, topleft, psize)
+    if lazy:
         # The encoder's last op is an exact 2x-1 bilinear up-sampling (16x16 -> 31x31): hand the fine tracker the
         # half-resolution map and let the fused lookup evaluate the up-sampled pyramid from it (blocks.Upsampled2x) --
         # the 1 GB-per-sequence patch-feature tensor is never written.
-        half, size = fine_fnet(patch_input, defer_upsample=True)
+        if from_images:
+            half, size = fine_fnet.encode_patches_of(images, topleft, defer_upsample=True)
+        else:
+            half, size = fine_fnet(patch_input, defer_upsample=True)
         Hs, Ws = half.shape[-2:]
         if size == (2 * Hs - 1, 2 * Ws - 1) and size == (psize, psize):
             C_out = half.shape[1]

@@ -184,6 +184,26 @@ int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int
 int comet_extract_patches_f32(const float* images, const int* topleft, float* out, int B, int S, int N, int C, int H, int W,
                               int P, comet_stream_t stream);
 
+/* ---- ShallowEncoder, the patch encoder of the fine tracker, as one kernel ---------------------------------------
+ * comet/models/track_modules/blocks.py:114-196 (norm_fn="instance", input_dim 3, output_dim 32, 31x31 patches) with
+ * ResidualBlock of comet/models/modules.py:39-117: conv1 3x3/2 -> InstanceNorm -> ReLU -> layer1 -> layer2 -> two
+ * bilinear residual up-samplings -> conv2 1x1 + skip, every intermediate map in shared memory, float32 FMA.
+ * The result is the 16x16 map *before* the encoder's final resize to 31x31 (blocks.py:183-190), channel-last:
+ * out (P, 16, 16, 32) -- what COMET_PYR_UP2_SOURCE consumes; comet_upsample_bilinear_ac_f32 gives the 31x31 map.
+ *
+ * comet_shallow_encoder_pack_f32: params_host is a HOST array of 16 DEVICE pointers in state-dict order
+ *   conv1.{weight,bias}, layer1.conv1.{w,b}, layer1.conv2.{w,b}, layer1.downsample.0.{w,b}, layer2.(same six),
+ *   conv2.{w,b} (contiguous OIHW float32) -> packed (comet_shallow_encoder_packed_elems() floats, 16-byte aligned).
+ * comet_shallow_encoder_f32: patches (P,3,31,31) with element strides (sn, sc, sy, sx) -- any memory format.
+ * comet_shallow_encoder_from_images_f32: fuses the patch gather of refine_track.py:71-111 (same arguments as
+ *   comet_extract_patches_f32 with C = 3, P = 31): patch (b, n, s) is read straight from images (B,S,3,H,W). */
+long long comet_shallow_encoder_packed_elems(void);
+int comet_shallow_encoder_pack_f32(const float* const* params_host, float* packed, comet_stream_t stream);
+int comet_shallow_encoder_f32(const float* patches, long long sn, long long sc, long long sy, long long sx,
+                              const float* packed, float* out, long long P, float eps, comet_stream_t stream);
+int comet_shallow_encoder_from_images_f32(const float* images, const int* topleft, const float* packed, float* out,
+                                          int B, int S, int N, int H, int W, float eps, comet_stream_t stream);
+
 /* ---- sin/cos encodings: comet/models/utils.py:37-101, :724-832 ----------- */
 /* get_2d_embedding(xy, C, cat_coords): xy (M,2) contiguous -> out (M, 2*C [+2 in front if cat_coords]). */
 int comet_embed2d_f32(const float* xy, float* out, long long M, int C, int cat_coords, comet_stream_t stream);

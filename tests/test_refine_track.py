@@ -198,3 +198,79 @@ def test_dropin_refine_track_matches_reference(golden, defer):
     assert rel_to_max(refined.cpu().numpy(), g[NAME + "/refined"]) < 1e-4   # "refined tracks" check-point, fp32 bar
     assert np.array_equal(refined[:, 0].cpu().numpy(), coarse[:, 0])
     assert rel_to_max(score.cpu().numpy(), g[NAME + "/score"]) < 1e-4       # "pred_score" check-point
+
+
+def _per_operator(rt, fnet, x, **kw):
+    """The encoder on the per-operator path (cuDNN float32 convolutions + the library's norm / resize kernels)."""
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    rt.USE_FUSED_ENCODER = False
+    try:
+        with torch.no_grad():
+            return fnet(x, **kw)
+    finally:
+        rt.USE_FUSED_ENCODER = True
+        torch.backends.cudnn.allow_tf32 = tf32
+
+
+@pytest.mark.gpu
+def test_fused_shallow_encoder_matches_reference(golden):
+    """csrc/shallow_encoder.cu (all layers of one patch in shared memory, float32 FMA) against the encoder output of the
+    executed reference, for NCHW and channels-last patch tensors."""
+    import importlib
+
+    rt = importlib.import_module("comet_pose_estimation_b200.refine_track")
+    g = golden("refine")
+    fnet, _ = modules(g)
+    fnet = fnet.cuda()
+    x = torch.from_numpy(g[NAME + "/enc_in"]).cuda()
+    from comet_pose_estimation_b200 import _lib
+
+    n0 = _lib.lib.comet_launch_count()
+    with torch.no_grad():
+        y = fnet(x)
+        y_cl = fnet(x.contiguous(memory_format=torch.channels_last))
+        half, size = fnet(x, defer_upsample=True)
+    assert _lib.lib.comet_launch_count() - n0 >= 3            # the library's kernels ran, not torch.nn
+    assert size == (31, 31) and tuple(half.shape) == (4, 32, 16, 16)
+    assert half.permute(0, 2, 3, 1).is_contiguous()           # channel-last memory: what Upsampled2x consumes
+    assert rel_to_max(y.cpu().numpy(), g[NAME + "/enc_out"]) < 1e-5
+    assert torch.equal(y, y_cl)
+    ref_half, _ = _per_operator(rt, fnet, x, defer_upsample=True)
+    assert rel_to_max(half.cpu().numpy(), ref_half.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_fused_shallow_encoder_from_images_odd_count_and_repacking():
+    """Gather fused into the encoder: same values as extract_patches + forward, bit for bit; an odd patch count
+    (the last CTA carries one patch); parameters modified in place are re-packed."""
+    import importlib
+
+    rt = importlib.import_module("comet_pose_estimation_b200.refine_track")
+    torch.manual_seed(11)
+    fnet = rt.ShallowEncoder(input_dim=3).eval().cuda()
+    with torch.no_grad():
+        for prm in fnet.parameters():
+            if prm.dim() == 1:
+                prm.uniform_(-0.5, 0.5)                       # biases are zero-initialised by default: exercise them
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    B, S, N, H, W = 1, 3, 7, 80, 64                            # 21 patches
+    images = torch.rand(B, S, 3, H, W, device="cuda", generator=gen)
+    tl = torch.stack([torch.randint(0, W - 31 + 1, (B, S, N), device="cuda", generator=gen),
+                      torch.randint(0, H - 31 + 1, (B, S, N), device="cuda", generator=gen)], -1).int()
+    tl[0, 0, 0] = 0
+    tl[0, 2, 6, 0], tl[0, 2, 6, 1] = W - 31, H - 31
+    with torch.no_grad():
+        patches = rt.extract_patches(images, tl, 31)
+        a, _ = fnet(patches, defer_upsample=True)
+        b, _ = fnet.encode_patches_of(images, tl, defer_upsample=True)
+    assert tuple(a.shape) == (21, 32, 16, 16)
+    assert torch.equal(a, b)
+    ref, _ = _per_operator(rt, fnet, patches, defer_upsample=True)
+    assert rel_to_max(a.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    with torch.no_grad():
+        fnet.layer2.conv2.weight.mul_(-1.5)
+        c, _ = fnet(patches, defer_upsample=True)
+    ref2, _ = _per_operator(rt, fnet, patches, defer_upsample=True)
+    assert not torch.equal(a, c)
+    assert rel_to_max(c.cpu().numpy(), ref2.cpu().numpy()) < 1e-5
