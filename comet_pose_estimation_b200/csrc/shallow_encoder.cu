@@ -5,24 +5,29 @@
 // Every operator of the encoder is local to one patch (instance norm reduces over the positions of one patch and one
 // channel), so a patch never has to leave the SM between its 3-channel pixels and the 16x16x32 map the fine tracker
 // consumes (blocks.Upsampled2x evaluates the encoder's last 16x16 -> 31x31 resize lazily).  One CTA carries two
-// patches through all layers in shared memory (77 KB each); HBM sees 11.5 KB in and 32 KB out per patch.  The library
+// patches through all layers in shared memory (87 KB each); HBM sees 11.5 KB in and 32 KB out per patch.  The library
 // convolutions + separate norm / resize kernels this replaces wrote and re-read ten intermediate maps per patch.
 //
 // Arithmetic is float32 FMA (the reference's float32 convolution; no TF32): 2.04 M multiply-adds per patch, so this
 // kernel is bound by the FP32 pipe, not by HBM: 8192 patches of a 512-track, 16-frame sequence are 16.7 G multiply-adds
 // against 37 T/s (148 SMs x 128 lanes x 1.965 GHz).
 //
-// Work split inside the CTA (8 warps): a warp task is 16 output positions x 32 output channels, lane = output channel.
-// Per 4 input channels a lane loads its 4 weights with one 16-byte load (L1-resident packed layout [tap][ci/4][co][4])
-// and, per position, the 4 inputs with one 16-byte *broadcast* shared load (channel-last activations) -> 64 FMA per
-// 17 loads.  The 4x4 layers have only 32 positions per CTA: their 288-deep sums are split four ways over the input
-// channels and combined in a fixed order (deterministic).
+// Work split inside the CTA (8 warps): a warp task is 16 output positions x 32 output channels; a lane owns a 4 x 4
+// block of it (positions pq, pq+4, pq+8, pq+12 x channels 4cq..4cq+3, lane = 8 pq + cq).  Per 4 input channels a lane
+// reads 4 weight vectors and 4 input vectors (16-byte shared loads) for 64 FMA -- the first version (lane = channel,
+// inputs as warp-wide broadcasts: 17 loads = 36 shared wavefronts per 64 FMA) sat at 25 % of the FMA pipe, bound by
+// shared-memory wavefronts (profiles/r02c_shallow_encoder_v1_summary.csv).  Activations are channel-last with 36 floats
+// per position (32 + 4 of padding) so that the four positions a half-warp reads fall into different banks.  Weights of
+// the current layer sit in shared memory ([tap][ci/4][co%4][co/4][4]), fetched with cp.async while the previous layer's
+// instance norm runs.  The 4x4 layers have only 32 positions per CTA: their 288-deep sums are split four ways over the
+// input channels and combined in a fixed order (deterministic).
 #include "comet_common.cuh"
 
 namespace comet {
 namespace senc {
 
 constexpr int C = 32;            // feature channels
+constexpr int CS = 36;           // floats per position of a channel-last activation buffer (32 + 4 padding: bank shift)
 constexpr int G = 2;             // patches per CTA
 constexpr int THREADS = 256;
 constexpr int PSZ = 31;          // patch extent
@@ -30,20 +35,28 @@ constexpr int PSZ = 31;          // patch extent
 // per-patch shared-memory map (float offsets).  Padded buffers carry the zero border the next convolution reads.
 constexpr int IN_W = 33;                       // input 31x31 padded by one on every side, 4 floats per position (RGB0)
 constexpr int OFF_IN = 0;                      // [33*33][4]   = 4356
-constexpr int OFF_A8P = 0;                     // [10*10][32]  = 3200   (aliases IN once conv1 is done)
-constexpr int OFF_A4P = 3200;                  // [6*6][32]    = 1152   (aliases IN)
+constexpr int OFF_A8P = 0;                     // [10*10][CS]  = 3600   (aliases IN once conv1 is done)
+constexpr int OFF_A4P = 3600;                  // [6*6][CS]    = 1296   (aliases IN)
 constexpr int XP_W = 17;                       // 16x16 map padded on top / left
-constexpr int OFF_XP = 4356;                   // [17*17][32]  = 9248
-constexpr int OFF_B8 = OFF_XP + 9248;          // [8*8][32]    = 2048   (later: the four partial sums of the 4x4 layers)
+constexpr int OFF_XP = 4896;                   // [17*17][CS]  = 10404
+constexpr int OFF_B8 = OFF_XP + 10404;         // [8*8][CS]    = 2304   (later: the four partial sums of the 4x4 layers)
 constexpr int T1P_W = 9;                       // 8x8 map padded on top / left
-constexpr int OFF_T1P = OFF_B8 + 2048;         // [9*9][32]    = 2592
-constexpr int OFF_B4 = OFF_T1P + 2592;         // [4*4][32]    = 512
-constexpr int OFF_T2 = OFF_B4 + 512;           // [4*4][32]    = 512
-constexpr int PATCH_FLOATS = OFF_T2 + 512;     // 19268 floats = 77072 bytes
-constexpr int RED_FLOATS = 2 * G * 4 * C;      // two reduction scratch arrays [G][4][32]
-constexpr int SMEM_BYTES = (G * PATCH_FLOATS + RED_FLOATS) * 4;
+constexpr int OFF_T1P = OFF_B8 + 2304;         // [9*9][CS]    = 2916
+constexpr int OFF_B4 = OFF_T1P + 2916;         // [4*4][CS]    = 576
+constexpr int OFF_T2 = OFF_B4 + 576;           // [4*4][CS]    = 576
+constexpr int PATCH_FLOATS = OFF_T2 + 576;     // 21672 floats = 86688 bytes
+// CTA-wide regions behind the G patch regions
+constexpr int OFF_WB = G * PATCH_FLOATS;       // weights of the current 3x3 32->32 layer (9216)
+constexpr int OFF_WS = OFF_WB + 9216;          // conv1 (1152) | layer1.downsample (1024) | layer2.downsample | conv2
+constexpr int WS_CONV1 = 0, WS_L1DN = 1152, WS_L2DN = 2176, WS_CONV2 = 3200, WS_FLOATS = 4224;
+constexpr int OFF_BIAS = OFF_WS + WS_FLOATS;   // 8 x 32 biases, layer order of the packed blob
+constexpr int OFF_RED = OFF_BIAS + 256;        // two reduction scratch arrays [G][4][32]
+constexpr int SMEM_FLOATS = OFF_RED + 2 * G * 4 * C;
+constexpr int SMEM_BYTES = SMEM_FLOATS * 4;    // 230208
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_XP % 4 == 0 && OFF_B8 % 4 == 0 && OFF_T1P % 4 == 0 && OFF_B4 % 4 == 0 && PATCH_FLOATS % 4 == 0, "16-byte alignment");
 
-// packed parameter blob (float offsets): weights [tap][ci/4][co][4], then 32 biases, per layer
+// packed parameter blob (float offsets): per layer the weights [tap][ci/4][co%4][co/4][ci%4], then 32 biases
 constexpr int W_CONV1 = 0, B_CONV1 = 1152;
 constexpr int W_L1C1 = 1184, B_L1C1 = W_L1C1 + 9216;
 constexpr int W_L1C2 = B_L1C1 + 32, B_L1C2 = W_L1C2 + 9216;
@@ -53,46 +66,66 @@ constexpr int W_L2C2 = B_L2C1 + 32, B_L2C2 = W_L2C2 + 9216;
 constexpr int W_L2DN = B_L2C2 + 32, B_L2DN = W_L2DN + 1024;
 constexpr int W_CONV2 = B_L2DN + 32, B_CONV2 = W_CONV2 + 1024;
 constexpr int PACKED_FLOATS = B_CONV2 + 32;    // 41344
+// bias slots in shared memory
+enum { L_CONV1 = 0, L_L1C1, L_L1C2, L_L1DN, L_L2C1, L_L2C2, L_L2DN, L_CONV2 };
 
-// 16 positions x 32 channels of one convolution: acc[j] += sum over taps and the input-channel groups [cb, cb+NC) of
-// in[position j, tap, ci] * w[tap, ci, lane].  Position j of the task sits at (j / OW, j % OW) of an OW-wide output
-// block; `in0` is the (padded) input address of position 0's first tap, WP the padded input width, CPP the floats per
-// input position, KW x KW the kernel, CH = CPP / 4 channel groups per tap.
-template <int OW, int STRIDE, int WP, int CPP, int KW, int NC>
-__device__ __forceinline__ void conv16(const float* __restrict__ in0, const float4* __restrict__ w, int lane, int cb,
-                                       float (&acc)[16]) {
-  constexpr int CH = CPP / 4;
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all threads: copy n floats (multiple of 4) global -> shared
+__device__ __forceinline__ void stage(float* dst, const float* __restrict__ src, int n, int tid) {
+  for (int i = tid * 4; i < n; i += THREADS * 4) cp_async16(dst + i, src + i);
+}
+
+// One warp task: 16 positions x 32 channels of a convolution, a 4 x 4 block per lane.
+//   acc[jj][k] += sum over taps and the input-channel groups [cb, cb+NC) of in[position 4jj+pq, tap, ci] * w[tap, ci, 4cq+k]
+// Position j of the task sits at (j / OW, j % OW) of an OW-wide output block (OW % 4 == 0: the four positions of one
+// jj are neighbours in a row); `in_lane` = (padded) input address of position pq's first tap, WP the padded input
+// width, CPP the floats per input position, KW x KW the kernel, CH input-channel groups per tap in the weight layout.
+template <int OW, int STRIDE, int WP, int CPP, int KW, int CH, int NC>
+__device__ __forceinline__ void conv16(const float* __restrict__ in_lane, const float* __restrict__ w, int cq, int cb,
+                                       float (&acc)[4][4]) {
+  static_assert(OW % 4 == 0, "a lane's four positions share a row");
+  const float4* w4 = reinterpret_cast<const float4*>(w) + cq;
 #pragma unroll 1
   for (int tap = 0; tap < KW * KW; ++tap) {
     const int ky = tap / KW, kx = tap - ky * KW;
-    const float* pt = in0 + (ky * WP + kx) * CPP + cb * 4;
-    const float4* wt = w + (tap * CH + cb) * 32 + lane;
+    const float* pt = in_lane + (ky * WP + kx) * CPP + cb * 4;
+    const float4* wt = w4 + (tap * CH + cb) * 32;
 #pragma unroll 2
     for (int i = 0; i < NC; ++i) {
-      const float4 wv = __ldg(wt + i * 32);
-      const float* p = pt + i * 4;
+      float4 wv[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 x = *reinterpret_cast<const float4*>(p + ((j / OW) * STRIDE * WP + (j % OW) * STRIDE) * CPP);
-        acc[j] = fmaf(x.x, wv.x, acc[j]);
-        acc[j] = fmaf(x.y, wv.y, acc[j]);
-        acc[j] = fmaf(x.z, wv.z, acc[j]);
-        acc[j] = fmaf(x.w, wv.w, acc[j]);
+      for (int k = 0; k < 4; ++k) wv[k] = wt[i * 32 + k * 8];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 x = *reinterpret_cast<const float4*>(pt + i * 4 + (((jj * 4) / OW) * STRIDE * WP + ((jj * 4) % OW) * STRIDE) * CPP);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[jj][k] = fmaf(x.x, wv[k].x, acc[jj][k]);
+          acc[jj][k] = fmaf(x.y, wv[k].y, acc[jj][k]);
+          acc[jj][k] = fmaf(x.z, wv[k].z, acc[jj][k]);
+          acc[jj][k] = fmaf(x.w, wv[k].w, acc[jj][k]);
+        }
       }
     }
   }
 }
 
-// store the 16 x 32 block: position j -> out0 + ((j / OW) * OWP + j % OW) * 32 + lane
+// store the block: position 4jj+pq -> out_lane + ((4jj / OW) * OWP + 4jj % OW) * CS, out_lane = out0 + pq * CS + 4 cq
 template <int OW, int OWP>
-__device__ __forceinline__ void store16(float* out0, int lane, const float (&acc)[16]) {
+__device__ __forceinline__ void store16(float* out_lane, const float (&acc)[4][4]) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) out0[((j / OW) * OWP + (j % OW)) * C + lane] = acc[j];
+  for (int jj = 0; jj < 4; ++jj)
+    *reinterpret_cast<float4*>(out_lane + (((jj * 4) / OW) * OWP + (jj * 4) % OW) * CS) =
+        make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
 }
 
-__device__ __forceinline__ void fill16(float (&acc)[16], float v) {
+__device__ __forceinline__ void fill16(float (&acc)[4][4], const float4 b) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = v;
+  for (int jj = 0; jj < 4; ++jj) { acc[jj][0] = b.x; acc[jj][1] = b.y; acc[jj][2] = b.z; acc[jj][3] = b.w; }
 }
 
 // nn.InstanceNorm2d(affine=False) over the OW x OW interior of a buffer whose rows are OWP positions wide, for both
@@ -108,14 +141,14 @@ __device__ __forceinline__ void inorm(float* x0, float* acc0, bool relu, float e
   float* r2 = r1 + G * 4 * C;
   float s = 0.f;
 #pragma unroll 4
-  for (int p = q; p < NPOS; p += 4) s += x[((p / OW) * OWP + (p % OW)) * C];
+  for (int p = q; p < NPOS; p += 4) s += x[((p / OW) * OWP + (p % OW)) * CS];
   r1[q * C] = s;
   __syncthreads();
   const float mean = (((r1[0] + r1[C]) + r1[2 * C]) + r1[3 * C]) * (1.f / (float)NPOS);
   float v = 0.f;
 #pragma unroll 4
   for (int p = q; p < NPOS; p += 4) {
-    const float d = x[((p / OW) * OWP + (p % OW)) * C] - mean;
+    const float d = x[((p / OW) * OWP + (p % OW)) * CS] - mean;
     v = fmaf(d, d, v);
   }
   r2[q * C] = v;
@@ -124,11 +157,11 @@ __device__ __forceinline__ void inorm(float* x0, float* acc0, bool relu, float e
   float* a = acc0 ? acc0 + g * PATCH_FLOATS + co : nullptr;
 #pragma unroll 4
   for (int p = q; p < NPOS; p += 4) {
-    const int o = ((p / OW) * OWP + (p % OW)) * C;
+    const int o = ((p / OW) * OWP + (p % OW)) * CS;
     float y = (x[o] - mean) * rstd;
     if (relu) y = fmaxf(y, 0.f);
     if (a) {
-      const int oa = ((p / OW) * AWP + (p % OW)) * C;
+      const int oa = ((p / OW) * AWP + (p % OW)) * CS;
       a[oa] = fmaxf(a[oa] + y, 0.f);
     } else {
       x[o] = y;
@@ -156,14 +189,14 @@ __device__ __forceinline__ void upsample_add(float* xp0, const float* t0, int wa
       const float sx = scale * (float)xo;
       const int x0 = (int)sx, x1 = x0 + (x0 < IW - 1 ? 1 : 0);
       const float wx1 = sx - (float)x0, wx0 = 1.f - wx1;
-      const float v00 = t[(y0 * TWP + x0) * C], v01 = t[(y0 * TWP + x1) * C];
-      const float v10 = t[(y1 * TWP + x0) * C], v11 = t[(y1 * TWP + x1) * C];
-      xp[((yo + 1) * XP_W + xo + 1) * C] += wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
+      const float v00 = t[(y0 * TWP + x0) * CS], v01 = t[(y0 * TWP + x1) * CS];
+      const float v10 = t[(y1 * TWP + x0) * CS], v11 = t[(y1 * TWP + x1) * CS];
+      xp[((yo + 1) * XP_W + xo + 1) * CS] += wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
     }
   }
 }
 
-// zero the border cells of a padded [HP][WP][CPP] buffer of both patches (FULL: all four sides, else top row / left column)
+// zero the border cells of a padded [WP][WP][CPP] buffer of both patches (FULL: all four sides, else top row / left column)
 template <int WP, int CPP, bool FULL>
 __device__ __forceinline__ void zero_border(float* b0, int tid) {
   for (int i = tid; i < G * WP * WP * CPP; i += THREADS) {
@@ -186,17 +219,30 @@ struct Params {
 
 __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
-  float* red = smem + G * PATCH_FLOATS;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* red = smem + OFF_RED;
+  float* wb = smem + OFF_WB;
+  const float* ws = smem + OFF_WS;
+  const float4* bias4 = reinterpret_cast<const float4*>(smem + OFF_BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, pq = lane >> 3, cq = lane & 7;
   const float* __restrict__ pk = p.packed;
 
-  // ---- phase 0: zero the padded input and the borders nobody overwrites, then gather the two patches ----------------
+  // ---- phase 0: parameters on their way (cp.async); zero the padded input and the borders nobody overwrites; gather --
+  stage(smem + OFF_WS + WS_CONV1, pk + W_CONV1, 1152, tid);
+  stage(smem + OFF_WS + WS_L1DN, pk + W_L1DN, 1024, tid);
+  stage(smem + OFF_WS + WS_L2DN, pk + W_L2DN, 1024, tid);
+  stage(smem + OFF_WS + WS_CONV2, pk + W_CONV2, 1024, tid);
+  if (tid < 64) {
+    const int boff[8] = {B_CONV1, B_L1C1, B_L1C2, B_L1DN, B_L2C1, B_L2C2, B_L2DN, B_CONV2};
+    cp_async16(smem + OFF_BIAS + tid * 4, pk + boff[tid >> 3] + (tid & 7) * 4);
+  }
+  stage(wb, pk + W_L1C1, 9216, tid);
+  cp_async_commit();
   for (int i = tid; i < G * (IN_W * IN_W); i += THREADS) {
     const int g = i / (IN_W * IN_W), r = i - g * (IN_W * IN_W);
     reinterpret_cast<float4*>(smem + g * PATCH_FLOATS + OFF_IN)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  zero_border<XP_W, C, false>(smem + OFF_XP, tid);
-  zero_border<T1P_W, C, false>(smem + OFF_T1P, tid);
+  zero_border<XP_W, CS, false>(smem + OFF_XP, tid);
+  zero_border<T1P_W, CS, false>(smem + OFF_T1P, tid);
   const float* base[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -221,91 +267,100 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
     const float* b = g == 0 ? base[0] : base[1];
     smem[g * PATCH_FLOATS + OFF_IN + ((y + 1) * IN_W + x + 1) * 4 + c] = __ldg(b + c * p.sc + y * p.sy + x * p.sx);
   }
+  cp_async_wait_all();
   __syncthreads();
 
-  float acc[16];
+  float acc[4][4];
 
   // ---- phase 1: conv1 (3 -> 32, 3x3, stride 2): 32 row tasks (patch, output row) ------------------------------------
-  {
-    const float bias = __ldg(pk + B_CONV1 + lane);
-    const float4* w = reinterpret_cast<const float4*>(pk + W_CONV1);
 #pragma unroll 1
-    for (int t = warp; t < G * 16; t += 8) {
-      const int g = t >> 4, oy = t & 15;
-      fill16(acc, bias);
-      conv16<16, 2, IN_W, 4, 3, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W) * 4, w, lane, 0, acc);
-      store16<16, XP_W>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1) * C, lane, acc);
-    }
+  for (int t = warp; t < G * 16; t += 8) {
+    const int g = t >> 4, oy = t & 15;
+    fill16(acc, bias4[L_CONV1 * 8 + cq]);
+    conv16<16, 2, IN_W, 4, 3, 1, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W + 2 * pq) * 4, ws + WS_CONV1, cq, 0, acc);
+    store16<16, XP_W>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS + 4 * cq, acc);
   }
   __syncthreads();
   // the input is dead: its space now holds the padded 8x8 / 4x4 maps, whose borders must read as zero
-  zero_border<10, C, true>(smem + OFF_A8P, tid);
-  zero_border<6, C, true>(smem + OFF_A4P, tid);
-  inorm<16, XP_W, 0>(smem + OFF_XP + (XP_W + 1) * C, nullptr, true, p.eps, red, tid);      // x0 = relu(norm1(conv1))
+  zero_border<10, CS, true>(smem + OFF_A8P, tid);
+  zero_border<6, CS, true>(smem + OFF_A4P, tid);
+  inorm<16, XP_W, 0>(smem + OFF_XP + (XP_W + 1) * CS, nullptr, true, p.eps, red, tid);      // x0 = relu(norm1(conv1))
 
   // ---- phase 2: layer1.conv1 (3x3 / 2) -> A8, layer1.downsample (1x1 / 2) -> T1: warp <-> (patch, two output rows) --
   {
     const int g = warp >> 2, pg = warp & 3;
     const float* xp = smem + g * PATCH_FLOATS + OFF_XP;
-    fill16(acc, __ldg(pk + B_L1C1 + lane));
-    conv16<8, 2, XP_W, C, 3, 8>(xp + (4 * pg * XP_W) * C, reinterpret_cast<const float4*>(pk + W_L1C1), lane, 0, acc);
-    store16<8, 10>(smem + g * PATCH_FLOATS + OFF_A8P + ((2 * pg + 1) * 10 + 1) * C, lane, acc);
-    fill16(acc, __ldg(pk + B_L1DN + lane));
-    conv16<8, 2, XP_W, C, 1, 8>(xp + ((4 * pg + 1) * XP_W + 1) * C, reinterpret_cast<const float4*>(pk + W_L1DN), lane, 0, acc);
-    store16<8, T1P_W>(smem + g * PATCH_FLOATS + OFF_T1P + ((2 * pg + 1) * T1P_W + 1) * C, lane, acc);
+    fill16(acc, bias4[L_L1C1 * 8 + cq]);
+    conv16<8, 2, XP_W, CS, 3, 8, 8>(xp + (4 * pg * XP_W + 2 * pq) * CS, wb, cq, 0, acc);
+    store16<8, 10>(smem + g * PATCH_FLOATS + OFF_A8P + ((2 * pg + 1) * 10 + 1 + pq) * CS + 4 * cq, acc);
+    fill16(acc, bias4[L_L1DN * 8 + cq]);
+    conv16<8, 2, XP_W, CS, 1, 8, 8>(xp + ((4 * pg + 1) * XP_W + 1 + 2 * pq) * CS, ws + WS_L1DN, cq, 0, acc);
+    store16<8, T1P_W>(smem + g * PATCH_FLOATS + OFF_T1P + ((2 * pg + 1) * T1P_W + 1 + pq) * CS + 4 * cq, acc);
   }
   __syncthreads();
-  inorm<8, 10, 0>(smem + OFF_A8P + (10 + 1) * C, nullptr, true, p.eps, red, tid);           // relu(norm1(conv1))
-  inorm<8, T1P_W, 0>(smem + OFF_T1P + (T1P_W + 1) * C, nullptr, false, p.eps, red, tid);    // norm3(downsample)
+  stage(wb, pk + W_L1C2, 9216, tid);
+  cp_async_commit();
+  inorm<8, 10, 0>(smem + OFF_A8P + (10 + 1) * CS, nullptr, true, p.eps, red, tid);           // relu(norm1(conv1))
+  inorm<8, T1P_W, 0>(smem + OFF_T1P + (T1P_W + 1) * CS, nullptr, false, p.eps, red, tid);    // norm3(downsample)
+  cp_async_wait_all();
+  __syncthreads();
 
   // ---- phase 3: layer1.conv2 (3x3) -> B8; T1 = relu(T1 + relu(norm2(B8))) -------------------------------------------
   {
     const int g = warp >> 2, pg = warp & 3;
-    fill16(acc, __ldg(pk + B_L1C2 + lane));
-    conv16<8, 1, 10, C, 3, 8>(smem + g * PATCH_FLOATS + OFF_A8P + (2 * pg * 10) * C,
-                              reinterpret_cast<const float4*>(pk + W_L1C2), lane, 0, acc);
-    store16<8, 8>(smem + g * PATCH_FLOATS + OFF_B8 + (2 * pg * 8) * C, lane, acc);
+    fill16(acc, bias4[L_L1C2 * 8 + cq]);
+    conv16<8, 1, 10, CS, 3, 8, 8>(smem + g * PATCH_FLOATS + OFF_A8P + (2 * pg * 10 + pq) * CS, wb, cq, 0, acc);
+    store16<8, 8>(smem + g * PATCH_FLOATS + OFF_B8 + (2 * pg * 8 + pq) * CS + 4 * cq, acc);
   }
   __syncthreads();
-  inorm<8, 8, T1P_W>(smem + OFF_B8, smem + OFF_T1P + (T1P_W + 1) * C, true, p.eps, red, tid);
+  stage(wb, pk + W_L2C1, 9216, tid);
+  cp_async_commit();
+  inorm<8, 8, T1P_W>(smem + OFF_B8, smem + OFF_T1P + (T1P_W + 1) * CS, true, p.eps, red, tid);
+  cp_async_wait_all();
+  __syncthreads();
 
   // ---- phase 4: x += up(T1);  layer2.conv1 (3x3 / 2) four-way split over ci -> partial sums;  layer2.downsample -> T2
   {
     const int g = warp >> 2, ks = warp & 3;
     const float* t1 = smem + g * PATCH_FLOATS + OFF_T1P;
-    fill16(acc, 0.f);
-    conv16<4, 2, T1P_W, C, 3, 2>(t1, reinterpret_cast<const float4*>(pk + W_L2C1), lane, 2 * ks, acc);
-    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * 512, lane, acc);
+    fill16(acc, make_float4(0.f, 0.f, 0.f, 0.f));
+    conv16<4, 2, T1P_W, CS, 3, 8, 2>(t1 + 2 * pq * CS, wb, cq, 2 * ks, acc);
+    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * (16 * CS) + pq * CS + 4 * cq, acc);
     if (ks == 0) {
-      fill16(acc, __ldg(pk + B_L2DN + lane));
-      conv16<4, 2, T1P_W, C, 1, 8>(t1 + (T1P_W + 1) * C, reinterpret_cast<const float4*>(pk + W_L2DN), lane, 0, acc);
-      store16<4, 4>(smem + g * PATCH_FLOATS + OFF_T2, lane, acc);
+      fill16(acc, bias4[L_L2DN * 8 + cq]);
+      conv16<4, 2, T1P_W, CS, 1, 8, 8>(t1 + (T1P_W + 1 + 2 * pq) * CS, ws + WS_L2DN, cq, 0, acc);
+      store16<4, 4>(smem + g * PATCH_FLOATS + OFF_T2 + pq * CS + 4 * cq, acc);
     }
-    upsample_add<8, T1P_W>(smem + OFF_XP, smem + OFF_T1P + (T1P_W + 1) * C, warp, lane);
+    upsample_add<8, T1P_W>(smem + OFF_XP, smem + OFF_T1P + (T1P_W + 1) * CS, warp, lane);
   }
   __syncthreads();
+  stage(wb, pk + W_L2C2, 9216, tid);
+  cp_async_commit();
   for (int i = tid; i < G * 512; i += THREADS) {
-    const int g = i >> 9, r = i & 511, pos = r >> 5;
-    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + r;
-    smem[g * PATCH_FLOATS + OFF_A4P + (((pos >> 2) + 1) * 6 + (pos & 3) + 1) * C + (r & 31)] =
-        __ldg(pk + B_L2C1 + (r & 31)) + (((part[0] + part[512]) + part[1024]) + part[1536]);
+    const int g = i >> 9, r = i & 511, pos = r >> 5, co = r & 31;
+    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + pos * CS + co;
+    smem[g * PATCH_FLOATS + OFF_A4P + (((pos >> 2) + 1) * 6 + (pos & 3) + 1) * CS + co] =
+        smem[OFF_BIAS + L_L2C1 * 32 + co] + (((part[0] + part[16 * CS]) + part[32 * CS]) + part[48 * CS]);
   }
   __syncthreads();
-  inorm<4, 6, 0>(smem + OFF_A4P + (6 + 1) * C, nullptr, true, p.eps, red, tid);
+  inorm<4, 6, 0>(smem + OFF_A4P + (6 + 1) * CS, nullptr, true, p.eps, red, tid);
   inorm<4, 4, 0>(smem + OFF_T2, nullptr, false, p.eps, red, tid);
+  cp_async_wait_all();
+  __syncthreads();
 
   // ---- phase 5: layer2.conv2 (3x3), same split -> B4; T2 = relu(T2 + relu(norm2(B4))) -------------------------------
   {
     const int g = warp >> 2, ks = warp & 3;
-    fill16(acc, 0.f);
-    conv16<4, 1, 6, C, 3, 2>(smem + g * PATCH_FLOATS + OFF_A4P, reinterpret_cast<const float4*>(pk + W_L2C2), lane, 2 * ks, acc);
-    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * 512, lane, acc);
+    fill16(acc, make_float4(0.f, 0.f, 0.f, 0.f));
+    conv16<4, 1, 6, CS, 3, 8, 2>(smem + g * PATCH_FLOATS + OFF_A4P + pq * CS, wb, cq, 2 * ks, acc);
+    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * (16 * CS) + pq * CS + 4 * cq, acc);
   }
   __syncthreads();
   for (int i = tid; i < G * 512; i += THREADS) {
-    const int g = i >> 9, r = i & 511;
-    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + r;
-    smem[g * PATCH_FLOATS + OFF_B4 + r] = __ldg(pk + B_L2C2 + (r & 31)) + (((part[0] + part[512]) + part[1024]) + part[1536]);
+    const int g = i >> 9, r = i & 511, pos = r >> 5, co = r & 31;
+    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + pos * CS + co;
+    smem[g * PATCH_FLOATS + OFF_B4 + pos * CS + co] =
+        smem[OFF_BIAS + L_L2C2 * 32 + co] + (((part[0] + part[16 * CS]) + part[32 * CS]) + part[48 * CS]);
   }
   __syncthreads();
   inorm<4, 4, 4>(smem + OFF_B4, smem + OFF_T2, true, p.eps, red, tid);
@@ -313,20 +368,19 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
   // ---- phase 6: x += up(T2);  out = conv2(x) + x (1x1) ---------------------------------------------------------------
   upsample_add<4, 4>(smem + OFF_XP, smem + OFF_T2, warp, lane);
   __syncthreads();
-  {
-    const float bias = __ldg(pk + B_CONV2 + lane);
-    const float4* w = reinterpret_cast<const float4*>(pk + W_CONV2);
 #pragma unroll 1
-    for (int t = warp; t < G * 16; t += 8) {
-      const int g = t >> 4, oy = t & 15;
-      const long long pi = (long long)blockIdx.x * G + g;
-      if (pi >= p.P) continue;
-      const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1) * C;
-      fill16(acc, bias);
-      conv16<16, 1, XP_W, C, 1, 8>(row, w, lane, 0, acc);
-      float* o = p.out + (pi * 256 + oy * 16) * C + lane;
+  for (int t = warp; t < G * 16; t += 8) {
+    const int g = t >> 4, oy = t & 15;
+    const long long pi = (long long)blockIdx.x * G + g;
+    if (pi >= p.P) continue;
+    const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS;
+    fill16(acc, bias4[L_CONV2 * 8 + cq]);
+    conv16<16, 1, XP_W, CS, 1, 8, 8>(row, ws + WS_CONV2, cq, 0, acc);
+    float* o = p.out + (pi * 256 + oy * 16 + pq) * C + 4 * cq;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j * C] = acc[j] + row[j * C + lane];
+    for (int jj = 0; jj < 4; ++jj) {
+      const float4 x = *reinterpret_cast<const float4*>(row + jj * 4 * CS + 4 * cq);
+      *reinterpret_cast<float4*>(o + jj * 4 * C) = make_float4(acc[jj][0] + x.x, acc[jj][1] + x.y, acc[jj][2] + x.z, acc[jj][3] + x.w);
     }
   }
 }
@@ -346,7 +400,9 @@ __global__ void __launch_bounds__(256) shallow_encoder_pack_kernel(const PackPar
   for (int l = 0; l < 8; ++l) {
     const int CI = ci_n[l], K = kk[l], CH = (CI + 3) / 4, n = K * K * CH * 32 * 4;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-      const int e = i & 3, co = (i >> 2) & 31, r = i >> 7, c4 = r % CH, tap = r / CH, ci = c4 * 4 + e;
+      // [tap][c4][k][cq][e]: output channel 4 cq + k, input channel 4 c4 + e
+      const int e = i & 3, cq = (i >> 2) & 7, k = (i >> 5) & 3, r = i >> 7, c4 = r % CH, tap = r / CH;
+      const int co = cq * 4 + k, ci = c4 * 4 + e;
       pp.packed[woff[l] + i] = ci < CI ? __ldg(pp.t[2 * l] + ((long long)co * CI + ci) * K * K + tap) : 0.f;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 32; i += gridDim.x * blockDim.x)
