@@ -134,39 +134,45 @@ __device__ __forceinline__ void fill16(float (&acc)[4][4], const float4 b) {
 // is not written back but folded into the residual sum: acc = max(acc + y, 0)  (modules.py:115-117).
 template <int OW, int OWP, int AWP>
 __device__ __forceinline__ void inorm(float* x0, float* acc0, bool relu, float eps, float* red, int tid) {
-  constexpr int NPOS = OW * OW;
+  constexpr int NPOS = OW * OW, XQ = OW / 4;
   const int g = tid >> 7, q = (tid >> 5) & 3, co = tid & 31;
-  float* x = x0 + g * PATCH_FLOATS + co;
+  float* x = x0 + g * PATCH_FLOATS + q * CS + co;     // positions (row, q + 4 xi)
   float* r1 = red + (g * 4) * C + co;
   float* r2 = r1 + G * 4 * C;
   float s = 0.f;
 #pragma unroll 4
-  for (int p = q; p < NPOS; p += 4) s += x[((p / OW) * OWP + (p % OW)) * CS];
+  for (int row = 0; row < OW; ++row)
+#pragma unroll
+    for (int xi = 0; xi < XQ; ++xi) s += x[(row * OWP + 4 * xi) * CS];
   r1[q * C] = s;
   __syncthreads();
   const float mean = (((r1[0] + r1[C]) + r1[2 * C]) + r1[3 * C]) * (1.f / (float)NPOS);
   float v = 0.f;
 #pragma unroll 4
-  for (int p = q; p < NPOS; p += 4) {
-    const float d = x[((p / OW) * OWP + (p % OW)) * CS] - mean;
-    v = fmaf(d, d, v);
-  }
+  for (int row = 0; row < OW; ++row)
+#pragma unroll
+    for (int xi = 0; xi < XQ; ++xi) {
+      const float d = x[(row * OWP + 4 * xi) * CS] - mean;
+      v = fmaf(d, d, v);
+    }
   r2[q * C] = v;
   __syncthreads();
   const float rstd = rsqrtf((((r2[0] + r2[C]) + r2[2 * C]) + r2[3 * C]) * (1.f / (float)NPOS) + eps);
-  float* a = acc0 ? acc0 + g * PATCH_FLOATS + co : nullptr;
+  float* a = acc0 ? acc0 + g * PATCH_FLOATS + q * CS + co : nullptr;
 #pragma unroll 4
-  for (int p = q; p < NPOS; p += 4) {
-    const int o = ((p / OW) * OWP + (p % OW)) * CS;
-    float y = (x[o] - mean) * rstd;
-    if (relu) y = fmaxf(y, 0.f);
-    if (a) {
-      const int oa = ((p / OW) * AWP + (p % OW)) * CS;
-      a[oa] = fmaxf(a[oa] + y, 0.f);
-    } else {
-      x[o] = y;
+  for (int row = 0; row < OW; ++row)
+#pragma unroll
+    for (int xi = 0; xi < XQ; ++xi) {
+      const int o = (row * OWP + 4 * xi) * CS;
+      float y = (x[o] - mean) * rstd;
+      if (relu) y = fmaxf(y, 0.f);
+      if (a) {
+        const int oa = (row * AWP + 4 * xi) * CS;
+        a[oa] = fmaxf(a[oa] + y, 0.f);
+      } else {
+        x[o] = y;
+      }
     }
-  }
   __syncthreads();
 }
 
@@ -174,35 +180,49 @@ __device__ __forceinline__ void inorm(float* x0, float* acc0, bool relu, float e
 // IW x IW map `t0` (rows TWP positions wide); ATen's arithmetic: src = dst * (in-1)/(out-1), i0 = (int)src,
 // i1 = i0 + (i0 < in-1), w1 = src - i0, w0 = 1 - w1, value = wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11).
 template <int IW, int TWP>
-__device__ __forceinline__ void upsample_add(float* xp0, const float* t0, int warp, int lane) {
+__device__ __forceinline__ void upsample_add(float* xp0, const float* t0, int warp, int pq, int cq) {
+  // warp <-> (patch, four output rows); lane <-> (output column pq + 4 i, channels 4 cq .. 4 cq + 3)
   const int g = warp >> 2;
-  float* xp = xp0 + g * PATCH_FLOATS + lane;
-  const float* t = t0 + g * PATCH_FLOATS + lane;
+  float* xp = xp0 + g * PATCH_FLOATS + 4 * cq;
+  const float* t = t0 + g * PATCH_FLOATS + 4 * cq;
   const float scale = (float)(IW - 1) / 15.f;
 #pragma unroll 1
   for (int yo = (warp & 3) * 4; yo < (warp & 3) * 4 + 4; ++yo) {
     const float sy = scale * (float)yo;
     const int y0 = (int)sy, y1 = y0 + (y0 < IW - 1 ? 1 : 0);
     const float wy1 = sy - (float)y0, wy0 = 1.f - wy1;
-#pragma unroll 4
-    for (int xo = 0; xo < 16; ++xo) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int xo = pq + 4 * i;
       const float sx = scale * (float)xo;
       const int x0 = (int)sx, x1 = x0 + (x0 < IW - 1 ? 1 : 0);
       const float wx1 = sx - (float)x0, wx0 = 1.f - wx1;
-      const float v00 = t[(y0 * TWP + x0) * CS], v01 = t[(y0 * TWP + x1) * CS];
-      const float v10 = t[(y1 * TWP + x0) * CS], v11 = t[(y1 * TWP + x1) * CS];
-      xp[((yo + 1) * XP_W + xo + 1) * CS] += wy0 * (wx0 * v00 + wx1 * v01) + wy1 * (wx0 * v10 + wx1 * v11);
+      const float4 v00 = *reinterpret_cast<const float4*>(t + (y0 * TWP + x0) * CS), v01 = *reinterpret_cast<const float4*>(t + (y0 * TWP + x1) * CS);
+      const float4 v10 = *reinterpret_cast<const float4*>(t + (y1 * TWP + x0) * CS), v11 = *reinterpret_cast<const float4*>(t + (y1 * TWP + x1) * CS);
+      float4* o = reinterpret_cast<float4*>(xp + ((yo + 1) * XP_W + xo + 1) * CS);
+      float4 r = *o;
+      r.x += wy0 * (wx0 * v00.x + wx1 * v01.x) + wy1 * (wx0 * v10.x + wx1 * v11.x);
+      r.y += wy0 * (wx0 * v00.y + wx1 * v01.y) + wy1 * (wx0 * v10.y + wx1 * v11.y);
+      r.z += wy0 * (wx0 * v00.z + wx1 * v01.z) + wy1 * (wx0 * v10.z + wx1 * v11.z);
+      r.w += wy0 * (wx0 * v00.w + wx1 * v01.w) + wy1 * (wx0 * v10.w + wx1 * v11.w);
+      *o = r;
     }
   }
 }
 
-// zero the border cells of a padded [WP][WP][CPP] buffer of both patches (FULL: all four sides, else top row / left column)
+// zero the border cells of a padded [WP][WP][CPP] buffer of both patches (FULL: all four sides, else top row / left
+// column), one 16-byte store per (border cell, 4 floats)
 template <int WP, int CPP, bool FULL>
 __device__ __forceinline__ void zero_border(float* b0, int tid) {
-  for (int i = tid; i < G * WP * WP * CPP; i += THREADS) {
-    const int g = i / (WP * WP * CPP), r = i - g * (WP * WP * CPP);
-    const int cell = r / CPP, y = cell / WP, x = cell - y * WP;
-    if (y == 0 || x == 0 || (FULL && (y == WP - 1 || x == WP - 1))) b0[g * PATCH_FLOATS + r] = 0.f;
+  constexpr int NB = FULL ? 4 * WP - 4 : 2 * WP - 1, V = CPP / 4;
+  for (int i = tid; i < G * NB * V; i += THREADS) {
+    const int g = i / (NB * V), r = i - g * (NB * V), b = r / V, v = r - b * V;
+    int y, x;
+    if (b < WP) { y = 0; x = b; }
+    else if (FULL && b < 2 * WP) { y = WP - 1; x = b - WP; }
+    else if (FULL) { y = 1 + ((b - 2 * WP) >> 1); x = ((b - 2 * WP) & 1) * (WP - 1); }
+    else { y = b - WP + 1; x = 0; }
+    *reinterpret_cast<float4*>(b0 + g * PATCH_FLOATS + (y * WP + x) * CPP + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -217,37 +237,13 @@ struct Params {
   float eps;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Params p) {
-  extern __shared__ __align__(16) float smem[];
-  float* red = smem + OFF_RED;
-  float* wb = smem + OFF_WB;
-  const float* ws = smem + OFF_WS;
-  const float4* bias4 = reinterpret_cast<const float4*>(smem + OFF_BIAS);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, pq = lane >> 3, cq = lane & 7;
-  const float* __restrict__ pk = p.packed;
-
-  // ---- phase 0: parameters on their way (cp.async); zero the padded input and the borders nobody overwrites; gather --
-  stage(smem + OFF_WS + WS_CONV1, pk + W_CONV1, 1152, tid);
-  stage(smem + OFF_WS + WS_L1DN, pk + W_L1DN, 1024, tid);
-  stage(smem + OFF_WS + WS_L2DN, pk + W_L2DN, 1024, tid);
-  stage(smem + OFF_WS + WS_CONV2, pk + W_CONV2, 1024, tid);
-  if (tid < 64) {
-    const int boff[8] = {B_CONV1, B_L1C1, B_L1C2, B_L1DN, B_L2C1, B_L2C2, B_L2DN, B_CONV2};
-    cp_async16(smem + OFF_BIAS + tid * 4, pk + boff[tid >> 3] + (tid & 7) * 4);
-  }
-  stage(wb, pk + W_L1C1, 9216, tid);
-  cp_async_commit();
-  for (int i = tid; i < G * (IN_W * IN_W); i += THREADS) {
-    const int g = i / (IN_W * IN_W), r = i - g * (IN_W * IN_W);
-    reinterpret_cast<float4*>(smem + g * PATCH_FLOATS + OFF_IN)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  zero_border<XP_W, CS, false>(smem + OFF_XP, tid);
-  zero_border<T1P_W, CS, false>(smem + OFF_T1P, tid);
+// pixels of patch pair `pair` -> registers: thread <-> cells tid + 256 k of the 2 x 31 x 31 cells, 3 channels each
+__device__ __forceinline__ void prefetch_pixels(const Params& p, long long pair, int tid, float (&pre)[24]) {
   const float* base[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    long long pi = (long long)blockIdx.x * G + g;
-    if (pi >= p.P) pi = p.P - 1;   // odd patch count: the last CTA encodes the last patch twice and stores it once
+    long long pi = pair * G + g;
+    if (pi >= p.P) pi = p.P - 1;   // odd patch count: the last pair encodes the last patch twice and stores it once
     if (p.topleft) {
       const int s = (int)(pi % p.S);
       const long long bn = pi / p.S;
@@ -260,128 +256,190 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
       base[g] = p.src + pi * p.sn;
     }
   }
-  __syncthreads();
-  for (int i = tid; i < G * 3 * PSZ * PSZ; i += THREADS) {
-    const int g = i / (3 * PSZ * PSZ), r = i - g * (3 * PSZ * PSZ);
-    const int c = r / (PSZ * PSZ), yx = r - c * (PSZ * PSZ), y = yx / PSZ, x = yx - y * PSZ;
-    const float* b = g == 0 ? base[0] : base[1];
-    smem[g * PATCH_FLOATS + OFF_IN + ((y + 1) * IN_W + x + 1) * 4 + c] = __ldg(b + c * p.sc + y * p.sy + x * p.sx);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int cell = tid + k * THREADS;
+    if (cell < G * PSZ * PSZ) {
+      const int g = cell >= PSZ * PSZ ? 1 : 0, r = cell - g * (PSZ * PSZ), y = r / PSZ, x = r - y * PSZ;
+      const float* b = (g == 0 ? base[0] : base[1]) + y * p.sy + x * p.sx;
+      pre[3 * k] = __ldg(b);
+      pre[3 * k + 1] = __ldg(b + p.sc);
+      pre[3 * k + 2] = __ldg(b + 2 * p.sc);
+    }
   }
+}
+__device__ __forceinline__ void store_pixels(float* smem, int tid, const float (&pre)[24]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int cell = tid + k * THREADS;
+    if (cell < G * PSZ * PSZ) {
+      const int g = cell >= PSZ * PSZ ? 1 : 0, r = cell - g * (PSZ * PSZ), y = r / PSZ, x = r - y * PSZ;
+      *reinterpret_cast<float4*>(smem + g * PATCH_FLOATS + OFF_IN + ((y + 1) * IN_W + x + 1) * 4) =
+          make_float4(pre[3 * k], pre[3 * k + 1], pre[3 * k + 2], 0.f);
+    }
+  }
+}
+
+// Persistent: CTA b encodes patch pairs b, b + gridDim.x, ...  The pixels of the next pair are loaded into registers
+// while the current pair is in its convolutions and stored once the region they share with the 8x8 / 4x4 maps is free.
+__global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Params p) {
+  extern __shared__ __align__(16) float smem[];
+  float* red = smem + OFF_RED;
+  float* wb = smem + OFF_WB;
+  const float* ws = smem + OFF_WS;
+  const float4* bias4 = reinterpret_cast<const float4*>(smem + OFF_BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, pq = lane >> 3, cq = lane & 7;
+  const float* __restrict__ pk = p.packed;
+  const long long npairs = (p.P + G - 1) / G;
+  long long pair = blockIdx.x;
+  if (pair >= npairs) return;
+
+  // ---- once per CTA: small-layer weights and biases (cp.async), borders nobody overwrites, the first pair's pixels ---
+  stage(smem + OFF_WS + WS_CONV1, pk + W_CONV1, 1152, tid);
+  stage(smem + OFF_WS + WS_L1DN, pk + W_L1DN, 1024, tid);
+  stage(smem + OFF_WS + WS_L2DN, pk + W_L2DN, 1024, tid);
+  stage(smem + OFF_WS + WS_CONV2, pk + W_CONV2, 1024, tid);
+  if (tid < 64) {
+    const int l = tid >> 3;
+    const int boff = l == 0 ? B_CONV1 : l == 1 ? B_L1C1 : l == 2 ? B_L1C2 : l == 3 ? B_L1DN : l == 4 ? B_L2C1 : l == 5 ? B_L2C2 : l == 6 ? B_L2DN : B_CONV2;
+    cp_async16(smem + OFF_BIAS + tid * 4, pk + boff + (tid & 7) * 4);
+  }
+  stage(wb, pk + W_L1C1, 9216, tid);
+  cp_async_commit();
+  float pre[24];
+  prefetch_pixels(p, pair, tid, pre);
+  zero_border<XP_W, CS, false>(smem + OFF_XP, tid);
+  zero_border<T1P_W, CS, false>(smem + OFF_T1P, tid);
+  zero_border<IN_W, 4, true>(smem + OFF_IN, tid);
+  store_pixels(smem, tid, pre);
   cp_async_wait_all();
   __syncthreads();
 
   float acc[4][4];
+  while (true) {
+    const long long next = pair + gridDim.x;
+    const bool has_next = next < npairs;
 
-  // ---- phase 1: conv1 (3 -> 32, 3x3, stride 2): 32 row tasks (patch, output row) ------------------------------------
+    // ---- phase 1: conv1 (3 -> 32, 3x3, stride 2): 32 row tasks (patch, output row) ----------------------------------
 #pragma unroll 1
-  for (int t = warp; t < G * 16; t += 8) {
-    const int g = t >> 4, oy = t & 15;
-    fill16(acc, bias4[L_CONV1 * 8 + cq]);
-    conv16<16, 2, IN_W, 4, 3, 1, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W + 2 * pq) * 4, ws + WS_CONV1, cq, 0, acc);
-    store16<16, XP_W>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS + 4 * cq, acc);
-  }
-  __syncthreads();
-  // the input is dead: its space now holds the padded 8x8 / 4x4 maps, whose borders must read as zero
-  zero_border<10, CS, true>(smem + OFF_A8P, tid);
-  zero_border<6, CS, true>(smem + OFF_A4P, tid);
-  inorm<16, XP_W, 0>(smem + OFF_XP + (XP_W + 1) * CS, nullptr, true, p.eps, red, tid);      // x0 = relu(norm1(conv1))
-
-  // ---- phase 2: layer1.conv1 (3x3 / 2) -> A8, layer1.downsample (1x1 / 2) -> T1: warp <-> (patch, two output rows) --
-  {
-    const int g = warp >> 2, pg = warp & 3;
-    const float* xp = smem + g * PATCH_FLOATS + OFF_XP;
-    fill16(acc, bias4[L_L1C1 * 8 + cq]);
-    conv16<8, 2, XP_W, CS, 3, 8, 8>(xp + (4 * pg * XP_W + 2 * pq) * CS, wb, cq, 0, acc);
-    store16<8, 10>(smem + g * PATCH_FLOATS + OFF_A8P + ((2 * pg + 1) * 10 + 1 + pq) * CS + 4 * cq, acc);
-    fill16(acc, bias4[L_L1DN * 8 + cq]);
-    conv16<8, 2, XP_W, CS, 1, 8, 8>(xp + ((4 * pg + 1) * XP_W + 1 + 2 * pq) * CS, ws + WS_L1DN, cq, 0, acc);
-    store16<8, T1P_W>(smem + g * PATCH_FLOATS + OFF_T1P + ((2 * pg + 1) * T1P_W + 1 + pq) * CS + 4 * cq, acc);
-  }
-  __syncthreads();
-  stage(wb, pk + W_L1C2, 9216, tid);
-  cp_async_commit();
-  inorm<8, 10, 0>(smem + OFF_A8P + (10 + 1) * CS, nullptr, true, p.eps, red, tid);           // relu(norm1(conv1))
-  inorm<8, T1P_W, 0>(smem + OFF_T1P + (T1P_W + 1) * CS, nullptr, false, p.eps, red, tid);    // norm3(downsample)
-  cp_async_wait_all();
-  __syncthreads();
-
-  // ---- phase 3: layer1.conv2 (3x3) -> B8; T1 = relu(T1 + relu(norm2(B8))) -------------------------------------------
-  {
-    const int g = warp >> 2, pg = warp & 3;
-    fill16(acc, bias4[L_L1C2 * 8 + cq]);
-    conv16<8, 1, 10, CS, 3, 8, 8>(smem + g * PATCH_FLOATS + OFF_A8P + (2 * pg * 10 + pq) * CS, wb, cq, 0, acc);
-    store16<8, 8>(smem + g * PATCH_FLOATS + OFF_B8 + (2 * pg * 8 + pq) * CS + 4 * cq, acc);
-  }
-  __syncthreads();
-  stage(wb, pk + W_L2C1, 9216, tid);
-  cp_async_commit();
-  inorm<8, 8, T1P_W>(smem + OFF_B8, smem + OFF_T1P + (T1P_W + 1) * CS, true, p.eps, red, tid);
-  cp_async_wait_all();
-  __syncthreads();
-
-  // ---- phase 4: x += up(T1);  layer2.conv1 (3x3 / 2) four-way split over ci -> partial sums;  layer2.downsample -> T2
-  {
-    const int g = warp >> 2, ks = warp & 3;
-    const float* t1 = smem + g * PATCH_FLOATS + OFF_T1P;
-    fill16(acc, make_float4(0.f, 0.f, 0.f, 0.f));
-    conv16<4, 2, T1P_W, CS, 3, 8, 2>(t1 + 2 * pq * CS, wb, cq, 2 * ks, acc);
-    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * (16 * CS) + pq * CS + 4 * cq, acc);
-    if (ks == 0) {
-      fill16(acc, bias4[L_L2DN * 8 + cq]);
-      conv16<4, 2, T1P_W, CS, 1, 8, 8>(t1 + (T1P_W + 1 + 2 * pq) * CS, ws + WS_L2DN, cq, 0, acc);
-      store16<4, 4>(smem + g * PATCH_FLOATS + OFF_T2 + pq * CS + 4 * cq, acc);
+    for (int t = warp; t < G * 16; t += 8) {
+      const int g = t >> 4, oy = t & 15;
+      fill16(acc, bias4[L_CONV1 * 8 + cq]);
+      conv16<16, 2, IN_W, 4, 3, 1, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W + 2 * pq) * 4, ws + WS_CONV1, cq, 0, acc);
+      store16<16, XP_W>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS + 4 * cq, acc);
     }
-    upsample_add<8, T1P_W>(smem + OFF_XP, smem + OFF_T1P + (T1P_W + 1) * CS, warp, lane);
-  }
-  __syncthreads();
-  stage(wb, pk + W_L2C2, 9216, tid);
-  cp_async_commit();
-  for (int i = tid; i < G * 512; i += THREADS) {
-    const int g = i >> 9, r = i & 511, pos = r >> 5, co = r & 31;
-    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + pos * CS + co;
-    smem[g * PATCH_FLOATS + OFF_A4P + (((pos >> 2) + 1) * 6 + (pos & 3) + 1) * CS + co] =
-        smem[OFF_BIAS + L_L2C1 * 32 + co] + (((part[0] + part[16 * CS]) + part[32 * CS]) + part[48 * CS]);
-  }
-  __syncthreads();
-  inorm<4, 6, 0>(smem + OFF_A4P + (6 + 1) * CS, nullptr, true, p.eps, red, tid);
-  inorm<4, 4, 0>(smem + OFF_T2, nullptr, false, p.eps, red, tid);
-  cp_async_wait_all();
-  __syncthreads();
+    __syncthreads();
+    if (has_next) prefetch_pixels(p, next, tid, pre);   // in flight until this pair's convolutions are done
+    // the input is dead: its space now holds the padded 8x8 / 4x4 maps, whose borders must read as zero
+    zero_border<10, CS, true>(smem + OFF_A8P, tid);
+    zero_border<6, CS, true>(smem + OFF_A4P, tid);
+    cp_async_wait_all();                                                                     // layer1.conv1 weights
+    inorm<16, XP_W, 0>(smem + OFF_XP + (XP_W + 1) * CS, nullptr, true, p.eps, red, tid);     // x0 = relu(norm1(conv1))
 
-  // ---- phase 5: layer2.conv2 (3x3), same split -> B4; T2 = relu(T2 + relu(norm2(B4))) -------------------------------
-  {
-    const int g = warp >> 2, ks = warp & 3;
-    fill16(acc, make_float4(0.f, 0.f, 0.f, 0.f));
-    conv16<4, 1, 6, CS, 3, 8, 2>(smem + g * PATCH_FLOATS + OFF_A4P + pq * CS, wb, cq, 2 * ks, acc);
-    store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * (16 * CS) + pq * CS + 4 * cq, acc);
-  }
-  __syncthreads();
-  for (int i = tid; i < G * 512; i += THREADS) {
-    const int g = i >> 9, r = i & 511, pos = r >> 5, co = r & 31;
-    const float* part = smem + g * PATCH_FLOATS + OFF_B8 + pos * CS + co;
-    smem[g * PATCH_FLOATS + OFF_B4 + pos * CS + co] =
-        smem[OFF_BIAS + L_L2C2 * 32 + co] + (((part[0] + part[16 * CS]) + part[32 * CS]) + part[48 * CS]);
-  }
-  __syncthreads();
-  inorm<4, 4, 4>(smem + OFF_B4, smem + OFF_T2, true, p.eps, red, tid);
+    // ---- phase 2: layer1.conv1 (3x3 / 2) -> A8, layer1.downsample (1x1 / 2) -> T1: warp <-> (patch, two output rows)
+    {
+      const int g = warp >> 2, pg = warp & 3;
+      const float* xp = smem + g * PATCH_FLOATS + OFF_XP;
+      fill16(acc, bias4[L_L1C1 * 8 + cq]);
+      conv16<8, 2, XP_W, CS, 3, 8, 8>(xp + (4 * pg * XP_W + 2 * pq) * CS, wb, cq, 0, acc);
+      store16<8, 10>(smem + g * PATCH_FLOATS + OFF_A8P + ((2 * pg + 1) * 10 + 1 + pq) * CS + 4 * cq, acc);
+      fill16(acc, bias4[L_L1DN * 8 + cq]);
+      conv16<8, 2, XP_W, CS, 1, 8, 8>(xp + ((4 * pg + 1) * XP_W + 1 + 2 * pq) * CS, ws + WS_L1DN, cq, 0, acc);
+      store16<8, T1P_W>(smem + g * PATCH_FLOATS + OFF_T1P + ((2 * pg + 1) * T1P_W + 1 + pq) * CS + 4 * cq, acc);
+    }
+    __syncthreads();
+    stage(wb, pk + W_L1C2, 9216, tid);
+    cp_async_commit();
+    inorm<8, 10, 0>(smem + OFF_A8P + (10 + 1) * CS, nullptr, true, p.eps, red, tid);          // relu(norm1(conv1))
+    cp_async_wait_all();
+    inorm<8, T1P_W, 0>(smem + OFF_T1P + (T1P_W + 1) * CS, nullptr, false, p.eps, red, tid);   // norm3(downsample)
 
-  // ---- phase 6: x += up(T2);  out = conv2(x) + x (1x1) ---------------------------------------------------------------
-  upsample_add<4, 4>(smem + OFF_XP, smem + OFF_T2, warp, lane);
-  __syncthreads();
+    // ---- phase 3: layer1.conv2 (3x3) -> B8; T1 = relu(T1 + relu(norm2(B8))) -----------------------------------------
+    {
+      const int g = warp >> 2, pg = warp & 3;
+      fill16(acc, bias4[L_L1C2 * 8 + cq]);
+      conv16<8, 1, 10, CS, 3, 8, 8>(smem + g * PATCH_FLOATS + OFF_A8P + (2 * pg * 10 + pq) * CS, wb, cq, 0, acc);
+      store16<8, 8>(smem + g * PATCH_FLOATS + OFF_B8 + (2 * pg * 8 + pq) * CS + 4 * cq, acc);
+    }
+    __syncthreads();
+    stage(wb, pk + W_L2C1, 9216, tid);
+    cp_async_commit();
+    cp_async_wait_all();
+    inorm<8, 8, T1P_W>(smem + OFF_B8, smem + OFF_T1P + (T1P_W + 1) * CS, true, p.eps, red, tid);
+
+    // ---- phase 4: x += up(T1);  layer2.conv1 (3x3 / 2) four-way split over ci -> partial sums;  layer2.downsample -> T2
+    {
+      const int g = warp >> 2, ks = warp & 3;
+      const float* t1 = smem + g * PATCH_FLOATS + OFF_T1P;
+      fill16(acc, make_float4(0.f, 0.f, 0.f, 0.f));
+      conv16<4, 2, T1P_W, CS, 3, 8, 2>(t1 + 2 * pq * CS, wb, cq, 2 * ks, acc);
+      store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * (16 * CS) + pq * CS + 4 * cq, acc);
+      if (ks == 0) {
+        fill16(acc, bias4[L_L2DN * 8 + cq]);
+        conv16<4, 2, T1P_W, CS, 1, 8, 8>(t1 + (T1P_W + 1 + 2 * pq) * CS, ws + WS_L2DN, cq, 0, acc);
+        store16<4, 4>(smem + g * PATCH_FLOATS + OFF_T2 + pq * CS + 4 * cq, acc);
+      }
+      upsample_add<8, T1P_W>(smem + OFF_XP, smem + OFF_T1P + (T1P_W + 1) * CS, warp, pq, cq);
+    }
+    __syncthreads();
+    stage(wb, pk + W_L2C2, 9216, tid);
+    cp_async_commit();
+    for (int i = tid; i < G * 512; i += THREADS) {
+      const int g = i >> 9, r = i & 511, pos = r >> 5, co = r & 31;
+      const float* part = smem + g * PATCH_FLOATS + OFF_B8 + pos * CS + co;
+      smem[g * PATCH_FLOATS + OFF_A4P + (((pos >> 2) + 1) * 6 + (pos & 3) + 1) * CS + co] =
+          smem[OFF_BIAS + L_L2C1 * 32 + co] + (((part[0] + part[16 * CS]) + part[32 * CS]) + part[48 * CS]);
+    }
+    __syncthreads();
+    inorm<4, 6, 0>(smem + OFF_A4P + (6 + 1) * CS, nullptr, true, p.eps, red, tid);
+    cp_async_wait_all();
+    inorm<4, 4, 0>(smem + OFF_T2, nullptr, false, p.eps, red, tid);
+
+    // ---- phase 5: layer2.conv2 (3x3), same split -> B4; T2 = relu(T2 + relu(norm2(B4))) -----------------------------
+    {
+      const int g = warp >> 2, ks = warp & 3;
+      fill16(acc, make_float4(0.f, 0.f, 0.f, 0.f));
+      conv16<4, 1, 6, CS, 3, 8, 2>(smem + g * PATCH_FLOATS + OFF_A4P + pq * CS, wb, cq, 2 * ks, acc);
+      store16<4, 4>(smem + g * PATCH_FLOATS + OFF_B8 + ks * (16 * CS) + pq * CS + 4 * cq, acc);
+    }
+    __syncthreads();
+    if (has_next) {
+      // the 8x8 / 4x4 maps and the 3x3 weights are dead: next pair's pixels and first 3x3 layer move in
+      stage(wb, pk + W_L1C1, 9216, tid);
+      cp_async_commit();
+      zero_border<IN_W, 4, true>(smem + OFF_IN, tid);
+      store_pixels(smem, tid, pre);
+    }
+    for (int i = tid; i < G * 512; i += THREADS) {
+      const int g = i >> 9, r = i & 511, pos = r >> 5, co = r & 31;
+      const float* part = smem + g * PATCH_FLOATS + OFF_B8 + pos * CS + co;
+      smem[g * PATCH_FLOATS + OFF_B4 + pos * CS + co] =
+          smem[OFF_BIAS + L_L2C2 * 32 + co] + (((part[0] + part[16 * CS]) + part[32 * CS]) + part[48 * CS]);
+    }
+    __syncthreads();
+    inorm<4, 4, 4>(smem + OFF_B4, smem + OFF_T2, true, p.eps, red, tid);
+
+    // ---- phase 6: x += up(T2);  out = conv2(x) + x (1x1) -------------------------------------------------------------
+    upsample_add<4, 4>(smem + OFF_XP, smem + OFF_T2, warp, pq, cq);
+    __syncthreads();
 #pragma unroll 1
-  for (int t = warp; t < G * 16; t += 8) {
-    const int g = t >> 4, oy = t & 15;
-    const long long pi = (long long)blockIdx.x * G + g;
-    if (pi >= p.P) continue;
-    const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS;
-    fill16(acc, bias4[L_CONV2 * 8 + cq]);
-    conv16<16, 1, XP_W, CS, 1, 8, 8>(row, ws + WS_CONV2, cq, 0, acc);
-    float* o = p.out + (pi * 256 + oy * 16 + pq) * C + 4 * cq;
+    for (int t = warp; t < G * 16; t += 8) {
+      const int g = t >> 4, oy = t & 15;
+      const long long pi = pair * G + g;
+      if (pi >= p.P) continue;
+      const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS;
+      fill16(acc, bias4[L_CONV2 * 8 + cq]);
+      conv16<16, 1, XP_W, CS, 1, 8, 8>(row, ws + WS_CONV2, cq, 0, acc);
+      float* o = p.out + (pi * 256 + oy * 16 + pq) * C + 4 * cq;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const float4 x = *reinterpret_cast<const float4*>(row + jj * 4 * CS + 4 * cq);
-      *reinterpret_cast<float4*>(o + jj * 4 * C) = make_float4(acc[jj][0] + x.x, acc[jj][1] + x.y, acc[jj][2] + x.z, acc[jj][3] + x.w);
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 x = *reinterpret_cast<const float4*>(row + jj * 4 * CS + 4 * cq);
+        *reinterpret_cast<float4*>(o + jj * 4 * C) = make_float4(acc[jj][0] + x.x, acc[jj][1] + x.y, acc[jj][2] + x.z, acc[jj][3] + x.w);
+      }
     }
+    if (!has_next) break;
+    pair = next;
+    __syncthreads();   // conv1 of the next pair overwrites the map conv2 has just read
   }
 }
 
@@ -438,8 +496,9 @@ static int launch_shallow_encoder(const senc::Params& p, comet_stream_t stream) 
     COMET_CUDA(cudaFuncSetAttribute(senc::shallow_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, senc::SMEM_BYTES));
     configured[dev] = true;
   }
-  const long long ctas = (p.P + senc::G - 1) / senc::G;
-  COMET_REQUIRE(ctas <= 0x7fffffffLL, "too many patches");
+  const int sms = device_sm_count_if_sm100();
+  long long ctas = (p.P + senc::G - 1) / senc::G;
+  if (ctas > sms) ctas = sms;    // persistent: one CTA per SM, patch pairs strided over the grid
   senc::shallow_encoder_kernel<<<(unsigned)ctas, senc::THREADS, senc::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   return launch_status("shallow_encoder_kernel");
 }
