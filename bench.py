@@ -753,18 +753,37 @@ def main():
             with torch.no_grad():
                 return enc(rt.extract_patches(imgs, tl, 31), defer_upsample=defer)
 
+        def fused_from_images():
+            with torch.no_grad():
+                return enc.encode_patches_of(imgs, tl, defer_upsample=True)
+
         res = {}
-        for tag, flag, defer in (("library_kernels_half_res", True, True), ("library_kernels", True, False), ("aten_ops", False, False)):
+        res["fused"], _ = timed(fused_from_images, 5, 10)
+        res["fused_full_res"], _ = timed(lambda: producer(False), 5, 5)
+        rt.USE_FUSED_ENCODER = False
+        tf32 = torch.backends.cudnn.allow_tf32
+        for tag, flag, defer, t32 in (("per_op_half_res_fp32", True, True, False), ("per_op_half_res_tf32", True, True, True),
+                                      ("aten_ops", False, False, True)):
             rt.USE_LIBRARY_KERNELS = flag
+            torch.backends.cudnn.allow_tf32 = t32
             res[tag], _ = timed(lambda: producer(defer), 3, 2)
         rt.USE_LIBRARY_KERNELS = True
-        variants["patch_encoder"] = {"ms_per_sequence_half_res_output": res["library_kernels_half_res"],
-                                     "ms_per_sequence": res["library_kernels"],
+        rt.USE_FUSED_ENCODER = True
+        torch.backends.cudnn.allow_tf32 = tf32
+        macs = FINE["S"] * FINE["P"] * 2.0398e6     # multiply-adds of the encoder's convolutions per sequence
+        variants["patch_encoder"] = {"ms_per_sequence_half_res_output": res["fused"],
+                                     "ms_per_sequence": res["fused_full_res"],
+                                     "fp32_fma_frac_of_peak": macs / (res["fused"] * 1e-3) / (148 * 128 * 1.965e9),
+                                     "ms_per_sequence_per_operator_cudnn_fp32": res["per_op_half_res_fp32"],
+                                     "ms_per_sequence_per_operator_cudnn_tf32": res["per_op_half_res_tf32"],
                                      "ms_per_sequence_aten_ops": res["aten_ops"],
-                                     "what": "refine_track's producer of the fine tracker's input (extract_patches + "
-                                             "ShallowEncoder, channels-last, cuDNN convolutions) for one sequence: up to the "
-                                             "16x16 map the up2 layout consumes / with the final 31x31 up-sampling / with "
-                                             "the ATen resize + instance-norm ops"}
+                                     "what": "refine_track's producer of the fine tracker's input for one sequence (8192 "
+                                             "patches of 31x31): the one-kernel float32 encoder (csrc/shallow_encoder.cu, "
+                                             "patch gather fused) up to the 16x16 map the up2 layout consumes / "
+                                             "extract_patches + encoder + the final 31x31 up-sampling / the per-operator "
+                                             "path it replaced (gather kernel + cuDNN convolutions in strict float32 and "
+                                             "in TF32 + the library's norm / resize kernels) / the ATen resize + "
+                                             "instance-norm ops the reference calls"}
         del enc, imgs, tl
 
     # ---- end-to-end arm: host buffers, H2D + D2H inside the timed region ------------------------

@@ -128,6 +128,61 @@ __device__ __forceinline__ void fill16(float (&acc)[4][4], const float4 b) {
   for (int jj = 0; jj < 4; ++jj) { acc[jj][0] = b.x; acc[jj][1] = b.y; acc[jj][2] = b.z; acc[jj][3] = b.w; }
 }
 
+// The same for the layers with >= 128 positions per CTA: 32 positions x 32 channels per warp task, an 8 x 4 block per
+// lane (positions pq + 4 jj, channels 4 cq .. 4 cq + 3) with lane = 4 cq + pq: the four quarter-warps of an input load
+// then read identical addresses (2 shared wavefronts instead of 4), and a weight vector is reused for 8 positions:
+// 12 loads = 32 wavefronts per 128 FMA, against 8 loads = 24 wavefronts per 64 FMA of the 4 x 4 block.
+template <int OW, int STRIDE, int WP, int CPP, int KW, int CH, int NC>
+__device__ __forceinline__ void conv32(const float* __restrict__ in_lane, const float* __restrict__ w, int cq, int cb,
+                                       float (&acc)[8][4]) {
+  static_assert(OW % 4 == 0, "a lane's positions of one jj share a row");
+  const float4* w4 = reinterpret_cast<const float4*>(w) + cq;
+#pragma unroll 1
+  for (int tap = 0; tap < KW * KW; ++tap) {
+    const int ky = tap / KW, kx = tap - ky * KW;
+    const float* pt = in_lane + (ky * WP + kx) * CPP + cb * 4;
+    const float4* wt = w4 + (tap * CH + cb) * 32;
+#pragma unroll 2
+    for (int i = 0; i < NC; ++i) {
+      float4 wv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wv[k] = wt[i * 32 + k * 8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float4 x = *reinterpret_cast<const float4*>(pt + i * 4 + (((jj * 4) / OW) * STRIDE * WP + ((jj * 4) % OW) * STRIDE) * CPP);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[jj][k] = fmaf(x.x, wv[k].x, acc[jj][k]);
+          acc[jj][k] = fmaf(x.y, wv[k].y, acc[jj][k]);
+          acc[jj][k] = fmaf(x.z, wv[k].z, acc[jj][k]);
+          acc[jj][k] = fmaf(x.w, wv[k].w, acc[jj][k]);
+        }
+      }
+    }
+  }
+}
+
+// store (ADD = false) or add onto (ADD = true: the second half of a sum split over the input channels) the block:
+// position 4jj+pq -> out_lane + ((4jj / OW) * OWP + 4jj % OW) * CS, out_lane = out0 + pq * CS + 4 cq
+template <int OW, int OWP, bool ADD>
+__device__ __forceinline__ void store32(float* out_lane, const float (&acc)[8][4]) {
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    float4* o = reinterpret_cast<float4*>(out_lane + (((jj * 4) / OW) * OWP + (jj * 4) % OW) * CS);
+    float4 v = make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+    if (ADD) {
+      const float4 h = *o;
+      v = make_float4(h.x + v.x, h.y + v.y, h.z + v.z, h.w + v.w);
+    }
+    *o = v;
+  }
+}
+
+__device__ __forceinline__ void fill32(float (&acc)[8][4], const float4 b) {
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) { acc[jj][0] = b.x; acc[jj][1] = b.y; acc[jj][2] = b.z; acc[jj][3] = b.w; }
+}
+
 // nn.InstanceNorm2d(affine=False) over the OW x OW interior of a buffer whose rows are OWP positions wide, for both
 // patches of the CTA: thread <-> (patch g, position class q = positions q, q+4, .., channel).  Biased variance, two
 // passes.  `x0` / `acc0` point at patch 0 (patch g: + g * PATCH_FLOATS).  relu: y = max(y, 0).  With `acc0` the result
@@ -288,7 +343,9 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
   float* wb = smem + OFF_WB;
   const float* ws = smem + OFF_WS;
   const float4* bias4 = reinterpret_cast<const float4*>(smem + OFF_BIAS);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, pq = lane >> 3, cq = lane & 7;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pq = lane >> 3, cq = lane & 7;   // 4 x 4 blocks (conv16, up-sampling)
+  const int pw = lane & 3, cw = lane >> 2;   // 8 x 4 blocks (conv32)
   const float* __restrict__ pk = p.packed;
   const long long npairs = (p.P + G - 1) / G;
   long long pair = blockIdx.x;
@@ -316,17 +373,18 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
   __syncthreads();
 
   float acc[4][4];
+  float acw[8][4];
   while (true) {
     const long long next = pair + gridDim.x;
     const bool has_next = next < npairs;
 
-    // ---- phase 1: conv1 (3 -> 32, 3x3, stride 2): 32 row tasks (patch, output row) ----------------------------------
+    // ---- phase 1: conv1 (3 -> 32, 3x3, stride 2): 16 tasks (patch, two output rows) ---------------------------------
 #pragma unroll 1
-    for (int t = warp; t < G * 16; t += 8) {
-      const int g = t >> 4, oy = t & 15;
-      fill16(acc, bias4[L_CONV1 * 8 + cq]);
-      conv16<16, 2, IN_W, 4, 3, 1, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W + 2 * pq) * 4, ws + WS_CONV1, cq, 0, acc);
-      store16<16, XP_W>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS + 4 * cq, acc);
+    for (int t = warp; t < G * 8; t += 8) {
+      const int g = t >> 3, oy = 2 * (t & 7);
+      fill32(acw, bias4[L_CONV1 * 8 + cw]);
+      conv32<16, 2, IN_W, 4, 3, 1, 1>(smem + g * PATCH_FLOATS + OFF_IN + (2 * oy * IN_W + 2 * pw) * 4, ws + WS_CONV1, cw, 0, acw);
+      store32<16, XP_W, false>(smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pw) * CS + 4 * cw, acw);
     }
     __syncthreads();
     if (has_next) prefetch_pixels(p, next, tid, pre);   // in flight until this pair's convolutions are done
@@ -336,16 +394,25 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
     cp_async_wait_all();                                                                     // layer1.conv1 weights
     inorm<16, XP_W, 0>(smem + OFF_XP + (XP_W + 1) * CS, nullptr, true, p.eps, red, tid);     // x0 = relu(norm1(conv1))
 
-    // ---- phase 2: layer1.conv1 (3x3 / 2) -> A8, layer1.downsample (1x1 / 2) -> T1: warp <-> (patch, two output rows)
+    // ---- phase 2: layer1.conv1 (3x3 / 2) -> A8, layer1.downsample (1x1 / 2) -> T1: warp <-> (patch, four output rows,
+    // half of the input channels); the second halves are added once the first ones are stored
     {
-      const int g = warp >> 2, pg = warp & 3;
+      const int tk = warp >> 1, ks = warp & 1, g = tk >> 1, r0 = (tk & 1) * 4;
       const float* xp = smem + g * PATCH_FLOATS + OFF_XP;
-      fill16(acc, bias4[L_L1C1 * 8 + cq]);
-      conv16<8, 2, XP_W, CS, 3, 8, 8>(xp + (4 * pg * XP_W + 2 * pq) * CS, wb, cq, 0, acc);
-      store16<8, 10>(smem + g * PATCH_FLOATS + OFF_A8P + ((2 * pg + 1) * 10 + 1 + pq) * CS + 4 * cq, acc);
-      fill16(acc, bias4[L_L1DN * 8 + cq]);
-      conv16<8, 2, XP_W, CS, 1, 8, 8>(xp + ((4 * pg + 1) * XP_W + 1 + 2 * pq) * CS, ws + WS_L1DN, cq, 0, acc);
-      store16<8, T1P_W>(smem + g * PATCH_FLOATS + OFF_T1P + ((2 * pg + 1) * T1P_W + 1 + pq) * CS + 4 * cq, acc);
+      float* a8 = smem + g * PATCH_FLOATS + OFF_A8P + ((r0 + 1) * 10 + 1 + pw) * CS + 4 * cw;
+      float* t1 = smem + g * PATCH_FLOATS + OFF_T1P + ((r0 + 1) * T1P_W + 1 + pw) * CS + 4 * cw;
+      fill32(acw, ks ? make_float4(0.f, 0.f, 0.f, 0.f) : bias4[L_L1C1 * 8 + cw]);
+      conv32<8, 2, XP_W, CS, 3, 8, 4>(xp + (2 * r0 * XP_W + 2 * pw) * CS, wb, cw, 4 * ks, acw);
+      if (!ks) store32<8, 10, false>(a8, acw);
+      float acd[8][4];
+      fill32(acd, ks ? make_float4(0.f, 0.f, 0.f, 0.f) : bias4[L_L1DN * 8 + cw]);
+      conv32<8, 2, XP_W, CS, 1, 8, 4>(xp + ((2 * r0 + 1) * XP_W + 1 + 2 * pw) * CS, ws + WS_L1DN, cw, 4 * ks, acd);
+      if (!ks) store32<8, T1P_W, false>(t1, acd);
+      __syncthreads();
+      if (ks) {
+        store32<8, 10, true>(a8, acw);
+        store32<8, T1P_W, true>(t1, acd);
+      }
     }
     __syncthreads();
     stage(wb, pk + W_L1C2, 9216, tid);
@@ -354,12 +421,15 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
     cp_async_wait_all();
     inorm<8, T1P_W, 0>(smem + OFF_T1P + (T1P_W + 1) * CS, nullptr, false, p.eps, red, tid);   // norm3(downsample)
 
-    // ---- phase 3: layer1.conv2 (3x3) -> B8; T1 = relu(T1 + relu(norm2(B8))) -----------------------------------------
+    // ---- phase 3: layer1.conv2 (3x3) -> B8, same split; T1 = relu(T1 + relu(norm2(B8))) ------------------------------
     {
-      const int g = warp >> 2, pg = warp & 3;
-      fill16(acc, bias4[L_L1C2 * 8 + cq]);
-      conv16<8, 1, 10, CS, 3, 8, 8>(smem + g * PATCH_FLOATS + OFF_A8P + (2 * pg * 10 + pq) * CS, wb, cq, 0, acc);
-      store16<8, 8>(smem + g * PATCH_FLOATS + OFF_B8 + (2 * pg * 8 + pq) * CS + 4 * cq, acc);
+      const int tk = warp >> 1, ks = warp & 1, g = tk >> 1, r0 = (tk & 1) * 4;
+      float* b8 = smem + g * PATCH_FLOATS + OFF_B8 + (r0 * 8 + pw) * CS + 4 * cw;
+      fill32(acw, ks ? make_float4(0.f, 0.f, 0.f, 0.f) : bias4[L_L1C2 * 8 + cw]);
+      conv32<8, 1, 10, CS, 3, 8, 4>(smem + g * PATCH_FLOATS + OFF_A8P + (r0 * 10 + pw) * CS, wb, cw, 4 * ks, acw);
+      if (!ks) store32<8, 8, false>(b8, acw);
+      __syncthreads();
+      if (ks) store32<8, 8, true>(b8, acw);
     }
     __syncthreads();
     stage(wb, pk + W_L2C1, 9216, tid);
@@ -423,18 +493,19 @@ __global__ void __launch_bounds__(THREADS, 1) shallow_encoder_kernel(const Param
     upsample_add<4, 4>(smem + OFF_XP, smem + OFF_T2, warp, pq, cq);
     __syncthreads();
 #pragma unroll 1
-    for (int t = warp; t < G * 16; t += 8) {
-      const int g = t >> 4, oy = t & 15;
+    for (int t = warp; t < G * 8; t += 8) {
+      const int g = t >> 3, oy = 2 * (t & 7);
       const long long pi = pair * G + g;
       if (pi >= p.P) continue;
-      const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pq) * CS;
-      fill16(acc, bias4[L_CONV2 * 8 + cq]);
-      conv16<16, 1, XP_W, CS, 1, 8, 8>(row, ws + WS_CONV2, cq, 0, acc);
-      float* o = p.out + (pi * 256 + oy * 16 + pq) * C + 4 * cq;
+      const float* row = smem + g * PATCH_FLOATS + OFF_XP + ((oy + 1) * XP_W + 1 + pw) * CS;
+      fill32(acw, bias4[L_CONV2 * 8 + cw]);
+      conv32<16, 1, XP_W, CS, 1, 8, 8>(row, ws + WS_CONV2, cw, 0, acw);
+      float* o = p.out + (pi * 256 + oy * 16 + pw) * C + 4 * cw;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float4 x = *reinterpret_cast<const float4*>(row + jj * 4 * CS + 4 * cq);
-        *reinterpret_cast<float4*>(o + jj * 4 * C) = make_float4(acc[jj][0] + x.x, acc[jj][1] + x.y, acc[jj][2] + x.z, acc[jj][3] + x.w);
+      for (int jj = 0; jj < 8; ++jj) {
+        const float4 x = *reinterpret_cast<const float4*>(row + ((jj >> 2) * XP_W + (jj & 3) * 4) * CS + 4 * cw);
+        *reinterpret_cast<float4*>(o + ((jj >> 2) * 16 + (jj & 3) * 4) * C) =
+            make_float4(acw[jj][0] + x.x, acw[jj][1] + x.y, acw[jj][2] + x.z, acw[jj][3] + x.w);
       }
     }
     if (!has_next) break;
