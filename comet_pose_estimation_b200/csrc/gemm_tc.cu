@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     const bool vec_out = p.out && (p.out_ld % 4 == 0) && (((uintptr_t)p.out) % 16 == 0);
     const bool vec_res = p.resid && (p.resid_ld % 4 == 0) && (((uintptr_t)p.resid) % 16 == 0);
     const bool vec_pl = p.out_np > 0 && (p.outp_ld % 8 == 0);
+    const bool vec_bias = p.bias && (((uintptr_t)p.bias) % 16 == 0) && (p.bn % 32 == 0);   // n0 is then a multiple of 32
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
       const int m = mb * BM + 32 * wq + lane;
@@ -279,6 +280,15 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         const int n0 = nb * p.bn + 32 * c;
         if (n0 >= p.N) break;                      // warp-uniform
         float v[32];
+        // bias of a full chunk: eight 16-byte loads issued BEFORE the accumulator arrives (they do not depend on it);
+        // one scalar load + select per element cost a third of the epilogue's instructions (ncu r02, autocast fc1)
+        const bool full_chunk = n0 + 32 <= p.N;
+        const bool bias_vec = vec_bias && full_chunk;
+        float4 bv[8];
+        if (bias_vec) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+        }
         tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + 32 * c, v);
         if (p.np > 1) {
           float lo[32];
@@ -290,8 +300,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           tmem_ld_wait();
         }
         if (m < p.M) {
-          const bool full_chunk = n0 + 32 <= p.N;
-          if (p.bias) {
+          if (bias_vec) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w; }
+          } else if (p.bias) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += (full_chunk || n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
           }
@@ -330,7 +342,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           }
           for (int pl = 0; pl < p.out_np; ++pl) {
             __nv_bfloat16* o = p.outp[pl] + (long long)m * p.outp_ld + n0;
-            if (vec_pl && full_chunk) {
+            if (vec_pl && full_chunk && pl + 1 == p.out_np) {
+              // last (or only: autocast) plane: no residual to carry
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 2 * h], v[8 * i + 2 * h + 1]);
+                  w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                reinterpret_cast<uint4*>(o)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else if (vec_pl && full_chunk) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 uint32_t w[4];
