@@ -154,7 +154,10 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // GEMM (ncu r02: tensor pipe 13 %, issue slots 50 % busy with erff's ~25 instructions per element).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  // rcp.approx (one special-function instruction, 1 ulp): __frcp_rn expands to a Newton step plus a branch to a
+  // denormal slow path -- with BSSY / BSYNC a third of this function's instructions (ncu r02c); 1 + 0.33 z is in [1, inf)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
