@@ -148,6 +148,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32-byte global accesses (sm_100: ld / st .v8.f32): a lane of the epilogue owns one ROW of the tile, so every warp-wide
+// access touches 32 different rows; with 16-byte accesses each touched 32-byte sector is only half used and the epilogue
+// of a K = 384 GEMM (64 KB of float32 output per 1626 MMA clocks) is bound by sector operations in L1TEX.
+__device__ __forceinline__ void st_global_v8(float* ptr, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_v8_b32(void* ptr, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const float* ptr, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]),
+               "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(ptr));
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 // Same function with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) on the special-function unit: used when the
 // result is rounded to ONE bf16 plane anyway (autocast mode), where the epilogue, not the tensor pipe, bounds the fc1
@@ -268,9 +284,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     const int chalf = (warp - 2) >> 2;              // which 64 columns of the tile this warp owns
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
     uint32_t acc = 0, acc_phase = 0;
-    const bool vec_out = p.out && (p.out_ld % 4 == 0) && (((uintptr_t)p.out) % 16 == 0);
-    const bool vec_res = p.resid && (p.resid_ld % 4 == 0) && (((uintptr_t)p.resid) % 16 == 0);
-    const bool vec_pl = p.out_np > 0 && (p.outp_ld % 8 == 0);
+    const bool vec_out = p.out && (p.out_ld % 8 == 0) && (((uintptr_t)p.out) % 32 == 0);
+    const bool vec_res = p.resid && (p.resid_ld % 8 == 0) && (((uintptr_t)p.resid) % 32 == 0);
+    const bool vec_pl = p.out_np > 0 && (p.outp_ld % 16 == 0) && (((uintptr_t)p.outp[0]) % 32 == 0) &&
+                        (p.out_np < 2 || ((uintptr_t)p.outp[1]) % 32 == 0) && (p.out_np < 3 || ((uintptr_t)p.outp[2]) % 32 == 0);
     const bool vec_bias = p.bias && (((uintptr_t)p.bias) % 16 == 0) && (p.bn % 32 == 0);   // n0 is then a multiple of 32
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
@@ -323,9 +340,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             const float* r = p.resid + (long long)m * p.resid_ld + n0;
             if (vec_res && full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(r) + i);
-                v[4 * i] += g.x; v[4 * i + 1] += g.y; v[4 * i + 2] += g.z; v[4 * i + 3] += g.w;
+              for (int i = 0; i < 4; ++i) {
+                float g[8];
+                ld_global_nc_v8(r + 8 * i, g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[8 * i + e] += g[e];
               }
             } else {
 #pragma unroll
@@ -336,8 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             float* o = p.out + (long long)m * p.out_ld + n0;
             if (vec_out && full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              for (int i = 0; i < 4; ++i) st_global_v8(o + 8 * i, v + 8 * i);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) if (n0 + i < p.N) o[i] = v[i];
@@ -348,27 +366,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             if (vec_pl && full_chunk && pl + 1 == p.out_np) {
               // last (or only: autocast) plane: no residual to carry
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint32_t w[4];
+              for (int i = 0; i < 2; ++i) {
+                uint32_t w[8];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 2 * h], v[8 * i + 2 * h + 1]);
+                for (int h = 0; h < 8; ++h) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[16 * i + 2 * h], v[16 * i + 2 * h + 1]);
                   w[h] = *reinterpret_cast<const uint32_t*>(&b2);
                 }
-                reinterpret_cast<uint4*>(o)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                st_global_v8_b32(o + 16 * i, w);
               }
             } else if (vec_pl && full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint32_t w[4];
+              for (int i = 0; i < 2; ++i) {
+                uint32_t w[8];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 2 * h], v[8 * i + 2 * h + 1]);
+                for (int h = 0; h < 8; ++h) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[16 * i + 2 * h], v[16 * i + 2 * h + 1]);
                   w[h] = *reinterpret_cast<const uint32_t*>(&b2);
-                  v[8 * i + 2 * h] -= __low2float(b2);          // residual for the next plane (exact in float32)
-                  v[8 * i + 2 * h + 1] -= __high2float(b2);
+                  v[16 * i + 2 * h] -= __low2float(b2);          // residual for the next plane (exact in float32)
+                  v[16 * i + 2 * h + 1] -= __high2float(b2);
                 }
-                reinterpret_cast<uint4*>(o)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+                st_global_v8_b32(o + 16 * i, w);
               }
             } else {
 #pragma unroll
