@@ -32,11 +32,14 @@ constexpr int BM = 128, BN = 128, BK = 64;       // BN: widest tile (TMEM spacin
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB (A tile == B tile)
 constexpr int THREADS = 320;                     // 10 warps: TMA | MMA | 8 epilogue
 constexpr int MAX_NP = 3;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;          // operand ring (np = 3: two 96 KB stages; np = 1: six 32 KB stages)
+constexpr int OUT_STAGE_BYTES = 4096;            // per epilogue warp: one 32 x 32 float32 chunk (or two 32 x 32 bf16 chunks)
 
 struct Maps {
   CUtensorMap a[MAX_NP];   // X planes: {K, M} bf16, box {64, 128}
   CUtensorMap w[MAX_NP];   // W planes: {K, N} bf16, box {64, bn}
+  CUtensorMap o;           // float32 result: {N, M}, box {32, 32}, 128-byte swizzle (TMA store; valid if Params::tma_out)
+  CUtensorMap op[MAX_NP];  // result planes: {N, M} bf16, box {32, 32}, 64-byte swizzle (valid if Params::tma_pl)
 };
 
 struct Params {
@@ -56,6 +59,7 @@ struct Params {
   long long outp_ld;
   int out_np;
   int gelu;                // exact (erf) GELU, nn.GELU() default (modules.py:133)
+  int tma_out, tma_pl;     // results leave through shared memory and bulk tensor stores (row pitches allow a tensor map)
 };
 
 // ------------------------------------------------------------------ PTX helpers (see corr_tc.cu for the rationale)
@@ -105,6 +109,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+// shared -> global bulk tensor store of one box (coordinates {x = column, y = row}); rows / columns outside the tensor
+// are clipped by the copy engine
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -190,7 +204,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   const int ksteps = p.bk / 16;
   const int stage_bytes = p.np * (a_tile_bytes + b_tile_bytes);   // [A planes][B planes]
   const uint32_t idesc = IDESC_BASE | ((uint32_t)(p.bn >> 3) << 17);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.nstage * stage_bytes);
+  uint8_t* out_stage = smem + ((p.nstage * stage_bytes + 1023) & ~1023);   // [8 epilogue warps][OUT_STAGE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 8 * OUT_STAGE_BYTES);
   uint64_t* full = bars;                 // [nstage]  TMA -> MMA
   uint64_t* empty = full + p.nstage;     // [nstage]  MMA -> TMA
   uint64_t* acc_full = empty + p.nstage; // [2]       MMA -> epilogue
@@ -283,6 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     const int wq = warp & 3;                        // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;              // which 64 columns of the tile this warp owns
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
+    uint8_t* my_stage = out_stage + (warp - 2) * OUT_STAGE_BYTES;
     uint32_t acc = 0, acc_phase = 0;
     const bool vec_out = p.out && (p.out_ld % 8 == 0) && (((uintptr_t)p.out) % 32 == 0);
     const bool vec_res = p.resid && (p.resid_ld % 8 == 0) && (((uintptr_t)p.resid) % 32 == 0);
@@ -292,23 +308,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
       const int m = mb * BM + 32 * wq + lane;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tcgen05_fence_after();
-#pragma unroll 1
+      // Bias and residual of a chunk do not depend on the accumulator: they are requested before the wait for it (first
+      // chunk of the tile) / while the previous chunk's result is leaving (later chunks), so their DRAM latency -- a
+      // tile's epilogue is otherwise a serial chain "accumulator, residual load, add, store" per chunk -- is hidden.
       const int cph = p.bn >= 64 ? p.bn / 64 : 1;      // 32-column chunks per epilogue half
-      for (int c = cph * chalf; c < cph * (chalf + 1) && 32 * c < p.bn; ++c) {
+      float4 bv[8];
+      float rg[32];
+      bool bias_vec = false, res_vec = false;
+      auto prefetch = [&](int c) {
         const int n0 = nb * p.bn + 32 * c;
-        if (n0 >= p.N) break;                      // warp-uniform
-        float v[32];
-        // bias of a full chunk: eight 16-byte loads issued BEFORE the accumulator arrives (they do not depend on it);
-        // one scalar load + select per element cost a third of the epilogue's instructions (ncu r02, autocast fc1)
-        const bool full_chunk = n0 + 32 <= p.N;
-        const bool bias_vec = vec_bias && full_chunk;
-        float4 bv[8];
+        const bool full = n0 + 32 <= p.N;
+        bias_vec = vec_bias && full;
+        res_vec = vec_res && full && m < p.M;
         if (bias_vec) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
         }
+        if (res_vec) {
+          const float* r = p.resid + (long long)m * p.resid_ld + n0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ld_global_nc_v8(r + 8 * i, rg + 8 * i);
+        }
+      };
+      if (32 * cph * chalf < p.bn && nb * p.bn + 32 * cph * chalf < p.N) prefetch(cph * chalf);
+      mbar_wait(&acc_full[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = cph * chalf; c < cph * (chalf + 1) && 32 * c < p.bn; ++c) {
+        const int n0 = nb * p.bn + 32 * c;
+        if (n0 >= p.N) break;                      // warp-uniform
+        float v[32];
+        const bool full_chunk = n0 + 32 <= p.N;
         tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + 32 * c, v);
         if (p.np > 1) {
           float lo[32];
@@ -319,7 +349,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         } else {
           tmem_ld_wait();
         }
-        if (m < p.M) {
+        const bool row_ok = m < p.M;
+        if (row_ok) {
           if (bias_vec) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w; }
@@ -336,31 +367,68 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
             }
           }
-          if (p.resid) {
+          if (res_vec) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += rg[i];
+          } else if (p.resid) {
             const float* r = p.resid + (long long)m * p.resid_ld + n0;
-            if (vec_res && full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float g[8];
-                ld_global_nc_v8(r + 8 * i, g);
+            for (int i = 0; i < 32; ++i) if (n0 + i < p.N) v[i] += __ldg(r + i);
+          }
+        }
+        // operands of the next chunk on their way while this one is converted and stored
+        if (c + 1 < cph * (chalf + 1) && 32 * (c + 1) < p.bn && n0 + 32 < p.N) prefetch(c + 1);
+        // ---- float32 result
+        if (p.tma_out) {
+          // the warp's 32 x 32 chunk goes to shared memory in the box layout of the tensor map (rows of 128 bytes, 16-byte
+          // pieces XOR-swizzled with the row number: conflict-free for a lane-per-row writer) and leaves as ONE bulk
+          // tensor store of full 128-byte lines; rows >= M and columns >= N are clipped by the copy engine
+          if (lane == 0) bulk_wait_read();           // the previous box has been read out of the staging buffer
+          __syncwarp();
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[8 * i + e] += g[e];
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(my_stage + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&maps.o, my_stage, n0, mb * BM + 32 * wq); bulk_commit(); }
+        } else if (p.out && row_ok) {
+          float* o = p.out + (long long)m * p.out_ld + n0;
+          if (vec_out && full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st_global_v8(o + 8 * i, v + 8 * i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (n0 + i < p.N) o[i] = v[i];
+          }
+        }
+        // ---- result planes
+        if (p.tma_pl) {
+          for (int pl = 0; pl < p.out_np; ++pl) {
+            uint8_t* st = my_stage + (pl & 1) * 2048;          // two 32 x 32 bf16 boxes fit: planes alternate
+            if (pl != 1 || p.tma_out) {                        // (plane 1 follows plane 0 into the other half: no wait)
+              if (lane == 0) bulk_wait_read();
+              __syncwarp();
+            }
+            const bool last = pl + 1 == p.out_np;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t w[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * i + 2 * h], v[8 * i + 2 * h + 1]);
+                w[h] = *reinterpret_cast<const uint32_t*>(&b2);
+                if (!last) {
+                  v[8 * i + 2 * h] -= __low2float(b2);          // residual for the next plane (exact in float32)
+                  v[8 * i + 2 * h + 1] -= __high2float(b2);
+                }
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (n0 + i < p.N) v[i] += __ldg(r + i);
+              *reinterpret_cast<uint4*>(st + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&maps.op[pl], st, n0, mb * BM + 32 * wq); bulk_commit(); }
           }
-          if (p.out) {
-            float* o = p.out + (long long)m * p.out_ld + n0;
-            if (vec_out && full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) st_global_v8(o + 8 * i, v + 8 * i);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) if (n0 + i < p.N) o[i] = v[i];
-            }
-          }
+        } else if (row_ok) {
           for (int pl = 0; pl < p.out_np; ++pl) {
             __nv_bfloat16* o = p.outp[pl] + (long long)m * p.outp_ld + n0;
             if (vec_pl && full_chunk && pl + 1 == p.out_np) {
@@ -404,6 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_all();   // the bulk stores of this warp have been written before the CTA retires
   }
 
   tcgen05_fence_before();
@@ -427,6 +496,23 @@ static int encode_kmajor(CUtensorMap* tm, const void* base, long long rows, long
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled (gemm operand) failed with %d", (int)cr);
+  return COMET_OK;
+}
+
+// 2-D tensor map over a row-major result matrix [rows, ld]: dims {cols, rows}, box {32, 32}; rows of the box are 128
+// bytes (float32, 128-byte swizzle) or 64 bytes (bf16, 64-byte swizzle) -- the layouts the epilogue writes.
+static int encode_result(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, bool f32) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return fail(COMET_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult cr = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                    gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(COMET_ERR_CUDA, "cuTensorMapEncodeTiled (gemm result) failed with %d", (int)cr);
   return COMET_OK;
 }
 
@@ -514,7 +600,23 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
   __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(out_planes);
   for (int i = 0; i < out_np; ++i) p.outp[i] = op + i * out_plane_stride;
   p.outp_ld = outp_ld; p.out_np = out_planes ? out_np : 0; p.gelu = gelu;
-  const int smem = p.nstage * stage_bytes + (2 * p.nstage + 4) * 8 + 16;
+  // results through bulk tensor stores where the row pitches allow a tensor map (16-byte multiples, 16-byte aligned bases)
+  const int tma_mode = option(COMET_OPT_GEMM_TMA_STORE);   // bit 0: float32 result, bit 1: result planes
+  if (tma_mode) {
+    if ((tma_mode & 1) && out && out_ld % 4 == 0 && ((uintptr_t)out % 16) == 0) {
+      int rc = gemm::encode_result(&maps.o, out, M, N, out_ld, true);
+      if (rc != COMET_OK) return rc;
+      p.tma_out = 1;
+    }
+    if ((tma_mode & 2) && p.out_np > 0 && outp_ld % 8 == 0 && ((uintptr_t)out_planes % 16) == 0 && out_plane_stride % 8 == 0) {
+      for (int i = 0; i < out_np; ++i) {
+        int rc = gemm::encode_result(&maps.op[i], p.outp[i], M, N, outp_ld, false);
+        if (rc != COMET_OK) return rc;
+      }
+      p.tma_pl = 1;
+    }
+  }
+  const int smem = ((p.nstage * stage_bytes + 1023) & ~1023) + 8 * gemm::OUT_STAGE_BYTES + (2 * p.nstage + 4) * 8 + 16;
   COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const long long ntiles = (long long)p.tiles_m * p.tiles_n;
   const int grid = (int)(ntiles < sms ? ntiles : sms);

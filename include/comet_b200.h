@@ -79,7 +79,9 @@ int comet_has_tensor_path(void);
 #define COMET_OPT_TC_REDUCE_STORE 4 /* coarse tokens: the windows are added to the token rows by bulk reductions
                                       (cp.reduce.async.bulk add.f32, one per query and level) onto the position embedding the
                                       pre-kernel wrote there; off = per-entry stores by the stager warps.  ON by default */
-#define COMET_OPT_COUNT 5
+#define COMET_OPT_GEMM_TMA_STORE 5 /* transformer GEMM: results leave through shared memory and bulk tensor stores (full
+                                    128-byte lines) instead of per-lane row stores; on by default */
+#define COMET_OPT_COUNT 6
 int comet_set_option(int option, int value);
 int comet_get_option(int option);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */

@@ -22,6 +22,10 @@ def timed(fn, n=200):
     return e0.elapsed_time(e1) / n * 1e3
 
 
+from comet_pose_estimation_b200 import _lib
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+_lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_TMA_STORE, mode))   # bit 0: float32 result by TMA store, bit 1: planes
+print("tma store mode", mode)
 for np_ in (1, 3):
     run = tc._Run(tc._Weights(), np_, dev)
     M = 9216
