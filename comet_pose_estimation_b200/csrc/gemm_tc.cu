@@ -30,7 +30,12 @@ namespace gemm {
 constexpr int BM = 128, BN = 128, BK = 64;       // BN: widest tile (TMEM spacing); the tile actually used is Params::bn
                                                  // BK bf16 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB (A tile == B tile)
-constexpr int THREADS = 320;                     // 10 warps: TMA | MMA | 8 epilogue
+constexpr int THREADS = 320;                     // 10 warps: TMA | MMA | 8 epilogue (float32-grade mode)
+// Autocast mode (one MMA pass per K block) is bound by the epilogue's instruction issue -- GELU, conversion and staging are
+// ~35 instructions per element against 1626 MMA clocks per 128x128x384 tile -- and two epilogue warps per scheduler leave
+// half of the issue slots idle on dependency stalls: that mode runs SIXTEEN epilogue warps (four per TMEM lane quarter,
+// one 32-column chunk each; <= 112 registers, so no register prefetch of the residual) on a 128 KB operand ring.
+constexpr int THREADS_EW16 = 576;
 constexpr int MAX_NP = 3;
 constexpr int SMEM_BUDGET = 192 * 1024;          // operand ring (np = 3: two 96 KB stages; np = 1: six 32 KB stages)
 constexpr int OUT_STAGE_BYTES = 4096;            // per epilogue warp: one 32 x 32 float32 chunk (or two 32 x 32 bf16 chunks)
@@ -197,15 +202,19 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+template <int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  // sixteen epilogue warps serve the one-plane (autocast) mode only: let the compiler drop the multi-plane code there
+  const int NPK = EW == 16 ? 1 : p.np;
+  const int ONP = EW == 16 ? (p.out_np ? 1 : 0) : p.out_np;
   const int a_tile_bytes = BM * p.bk * 2, b_tile_bytes = p.bn * p.bk * 2;
   const uint32_t row_bytes = (uint32_t)p.bk * 2;
   const int ksteps = p.bk / 16;
-  const int stage_bytes = p.np * (a_tile_bytes + b_tile_bytes);   // [A planes][B planes]
+  const int stage_bytes = NPK * (a_tile_bytes + b_tile_bytes);   // [A planes][B planes]
   const uint32_t idesc = IDESC_BASE | ((uint32_t)(p.bn >> 3) << 17);
-  uint8_t* out_stage = smem + ((p.nstage * stage_bytes + 1023) & ~1023);   // [8 epilogue warps][OUT_STAGE_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + 8 * OUT_STAGE_BYTES);
+  uint8_t* out_stage = smem + ((p.nstage * stage_bytes + 1023) & ~1023);   // [EW epilogue warps][OUT_STAGE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + EW * OUT_STAGE_BYTES);
   uint64_t* full = bars;                 // [nstage]  TMA -> MMA
   uint64_t* empty = full + p.nstage;     // [nstage]  MMA -> TMA
   uint64_t* acc_full = empty + p.nstage; // [2]       MMA -> epilogue
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -239,9 +248,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = smem + stage * stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          for (int i = 0; i < p.np; ++i) {
+          for (int i = 0; i < NPK; ++i) {
             tma_load_2d(&maps.a[i], &full[stage], dst + i * a_tile_bytes, kb * p.bk, mb * BM);
-            tma_load_2d(&maps.w[i], &full[stage], dst + p.np * a_tile_bytes + i * b_tile_bytes, kb * p.bk, nb * p.bn);
+            tma_load_2d(&maps.w[i], &full[stage], dst + NPK * a_tile_bytes + i * b_tile_bytes, kb * p.bk, nb * p.bn);
           }
           if (++stage == (uint32_t)p.nstage) { stage = 0; phase ^= 1; }
         }
@@ -260,9 +269,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         mbar_wait(&full[stage], phase);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + p.np * a_tile_bytes;
+          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + NPK * a_tile_bytes;
           // plane pairs (i, j), i + j < np: (0,0) into the main accumulator, the low-order ones into their own
-          for (int sum = p.np - 1; sum >= 0; --sum) {
+          for (int sum = NPK - 1; sum >= 0; --sum) {
             for (int i = 0; i <= sum; ++i) {
               const int j = sum - i;
               const uint64_t ad = make_desc_kmajor(a0 + i * a_tile_bytes, row_bytes), bd = make_desc_kmajor(b0 + j * b_tile_bytes, row_bytes);
@@ -296,14 +305,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   } else {
     // ===================== epilogue warps (2..9) =====================
     const int wq = warp & 3;                        // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;              // which 64 columns of the tile this warp owns
+    const int chalf = (warp - 2) >> 2;              // which column group of the tile this warp owns (EW / 4 groups)
     const uint32_t lane_addr = ((uint32_t)(32 * wq) << 16);
     uint8_t* my_stage = out_stage + (warp - 2) * OUT_STAGE_BYTES;
     uint32_t acc = 0, acc_phase = 0;
     const bool vec_out = p.out && (p.out_ld % 8 == 0) && (((uintptr_t)p.out) % 32 == 0);
     const bool vec_res = p.resid && (p.resid_ld % 8 == 0) && (((uintptr_t)p.resid) % 32 == 0);
-    const bool vec_pl = p.out_np > 0 && (p.outp_ld % 16 == 0) && (((uintptr_t)p.outp[0]) % 32 == 0) &&
-                        (p.out_np < 2 || ((uintptr_t)p.outp[1]) % 32 == 0) && (p.out_np < 3 || ((uintptr_t)p.outp[2]) % 32 == 0);
+    const bool vec_pl = ONP > 0 && (p.outp_ld % 16 == 0) && (((uintptr_t)p.outp[0]) % 32 == 0) &&
+                        (ONP < 2 || ((uintptr_t)p.outp[1]) % 32 == 0) && (ONP < 3 || ((uintptr_t)p.outp[2]) % 32 == 0);
     const bool vec_bias = p.bias && (((uintptr_t)p.bias) % 16 == 0) && (p.bn % 32 == 0);   // n0 is then a multiple of 32
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
@@ -311,7 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       // Bias and residual of a chunk do not depend on the accumulator: they are requested before the wait for it (first
       // chunk of the tile) / while the previous chunk's result is leaving (later chunks), so their DRAM latency -- a
       // tile's epilogue is otherwise a serial chain "accumulator, residual load, add, store" per chunk -- is hidden.
-      const int cph = p.bn >= 64 ? p.bn / 64 : 1;      // 32-column chunks per epilogue half
+      const int cph = p.bn >= 8 * EW ? p.bn / (8 * EW) : 1;      // 32-column chunks per column group
       float4 bv[8];
       float rg[32];
       bool bias_vec = false, res_vec = false;
@@ -319,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         const int n0 = nb * p.bn + 32 * c;
         const bool full = n0 + 32 <= p.N;
         bias_vec = vec_bias && full;
-        res_vec = vec_res && full && m < p.M;
+        res_vec = EW == 8 && vec_res && full && m < p.M;     // (16 epilogue warps: no registers for it)
         if (bias_vec) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         float v[32];
         const bool full_chunk = n0 + 32 <= p.N;
         tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + 32 * c, v);
-        if (p.np > 1) {
+        if (NPK > 1) {
           float lo[32];
           tmem_ld32(tmem_base + lane_addr + acc * 2 * BN + BN + 32 * c, lo);
           tmem_ld_wait();
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             for (int i = 0; i < 32; ++i) v[i] += (full_chunk || n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
           }
           if (p.gelu) {
-            if (p.np == 1 && !p.out) {     // autocast mode, planes-only output (fc1): bf16 rounding dominates
+            if (NPK == 1 && !p.out) {     // autocast mode, planes-only output (fc1): bf16 rounding dominates
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
             } else {
@@ -372,8 +381,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             for (int i = 0; i < 32; ++i) v[i] += rg[i];
           } else if (p.resid) {
             const float* r = p.resid + (long long)m * p.resid_ld + n0;
+            if (EW == 16 && vec_res && full_chunk) {     // (8 epilogue warps: this case was prefetched into rg)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) if (n0 + i < p.N) v[i] += __ldg(r + i);
+              for (int i = 0; i < 4; ++i) {
+                float g[8];
+                ld_global_nc_v8(r + 8 * i, g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[8 * i + e] += g[e];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (n0 + i < p.N) v[i] += __ldg(r + i);
+            }
           }
         }
         // operands of the next chunk on their way while this one is converted and stored
@@ -403,13 +422,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         }
         // ---- result planes
         if (p.tma_pl) {
-          for (int pl = 0; pl < p.out_np; ++pl) {
+          for (int pl = 0; pl < ONP; ++pl) {
             uint8_t* st = my_stage + (pl & 1) * 2048;          // two 32 x 32 bf16 boxes fit: planes alternate
             if (pl != 1 || p.tma_out) {                        // (plane 1 follows plane 0 into the other half: no wait)
               if (lane == 0) bulk_wait_read();
               __syncwarp();
             }
-            const bool last = pl + 1 == p.out_np;
+            const bool last = pl + 1 == ONP;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint32_t w[4];
@@ -429,9 +448,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             if (lane == 0) { tma_store_2d(&maps.op[pl], st, n0, mb * BM + 32 * wq); bulk_commit(); }
           }
         } else if (row_ok) {
-          for (int pl = 0; pl < p.out_np; ++pl) {
+          for (int pl = 0; pl < ONP; ++pl) {
             __nv_bfloat16* o = p.outp[pl] + (long long)m * p.outp_ld + n0;
-            if (vec_pl && full_chunk && pl + 1 == p.out_np) {
+            if (vec_pl && full_chunk && pl + 1 == ONP) {
               // last (or only: autocast) plane: no residual to carry
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
@@ -592,7 +611,8 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
     if (rc != COMET_OK) return rc;
   }
   const int stage_bytes = np * (gemm::BM + p.bn) * p.bk * 2;
-  p.nstage = gemm::SMEM_BUDGET / stage_bytes;
+  const int ew = (np == 1 && out_np <= 1 && option(COMET_OPT_GEMM_EW16)) ? 16 : 8;   // epilogue warps (see THREADS_EW16)
+  p.nstage = (ew == 16 ? 128 * 1024 : gemm::SMEM_BUDGET) / stage_bytes;
   if (p.nstage > 12) p.nstage = 12;
   p.tiles_n = (N + p.bn - 1) / p.bn;
   p.ktiles = (K + p.bk - 1) / p.bk;
@@ -616,10 +636,15 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
       p.tma_pl = 1;
     }
   }
-  const int smem = ((p.nstage * stage_bytes + 1023) & ~1023) + 8 * gemm::OUT_STAGE_BYTES + (2 * p.nstage + 4) * 8 + 16;
-  COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = ((p.nstage * stage_bytes + 1023) & ~1023) + ew * gemm::OUT_STAGE_BYTES + (2 * p.nstage + 4) * 8 + 16;
   const long long ntiles = (long long)p.tiles_m * p.tiles_n;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  gemm::gemm_tc_kernel<<<grid, gemm::THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  if (ew == 16) {
+    COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm::gemm_tc_kernel<16><<<grid, gemm::THREADS_EW16, smem, (cudaStream_t)stream>>>(maps, p);
+  } else {
+    COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gemm::gemm_tc_kernel<8><<<grid, gemm::THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+  }
   return launch_status("gemm_tc_kernel");
 }
