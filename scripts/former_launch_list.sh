@@ -1,7 +1,8 @@
-python scripts/former_profile.py coarse 3 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/former_list.csv python scripts/former_profile.py coarse 3 > /dev/null 2>&1
+python scripts/former_profile.py coarse ${NP:-3} > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/former_list_np${NP:-3}.csv python scripts/former_profile.py coarse ${NP:-3} > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
-rows=[r for r in csv.reader(open("gpurun_out/former_list.csv")) if len(r)>10]
+import os
+rows=[r for r in csv.reader(open("gpurun_out/former_list_np" + os.environ.get("NP", "3") + ".csv")) if len(r)>10]
 h=rows[0]; i_n=h.index("Kernel Name"); i_v=h.index("Metric Value"); i_g=h.index("Grid Size")
 data=[(r[i_n][:48], r[i_g], float(r[i_v].replace(',',''))) for r in rows[1:]]
 # last forward = last quarter of launches
