@@ -320,7 +320,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
       // Bias and residual of a chunk do not depend on the accumulator: they are requested before the wait for it (first
       // chunk of the tile) / while the previous chunk's result is leaving (later chunks), so their DRAM latency -- a
       // tile's epilogue is otherwise a serial chain "accumulator, residual load, add, store" per chunk -- is hidden.
-      const int cph = p.bn >= 8 * EW ? p.bn / (8 * EW) : 1;      // 32-column chunks per column group
+      const int cph = ((p.bn >> 5) + EW / 4 - 1) / (EW / 4);     // 32-column chunks per column group (bn = 96: 2 + 1 or 1 + 1 + 1)
       float4 bv[8];
       float rg[32];
       bool bias_vec = false, res_vec = false;
@@ -599,11 +599,29 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
   gemm::Params p{};
   p.M = (int)M; p.N = N; p.K = K; p.np = np;
   p.tiles_m = (int)((M + gemm::BM - 1) / gemm::BM);
-  // output tile width: 128 unless that leaves most SMs without a tile (the virtual-track GEMMs have M = 1024 rows: 24
-  // tiles of 128x128 on 148 SMs, each MMA-bound for its whole K -- measured 27.6 us against 7 us of work per SM)
-  p.bn = 128;
+  // Output tile width: the one that needs the fewest rounds of persistent CTAs x tile cost.  128 columns by default; 64 /
+  // 32 when 128 would leave most SMs without a tile (the virtual-track GEMMs have M = 1024 rows: 24 tiles of 128x128 on
+  // 148 SMs, each MMA-bound for its whole K -- measured 27.6 us against 7 us of work per SM); 96 where it divides N and
+  // saves a round: the M = 9216 x N = 384 GEMMs (out-projection, fc2) are 216 tiles of 128 = 2 rounds of which the
+  // second is 46 % full, but 288 tiles of 96 = 2 rounds of 3/4 the cost.  The +24 columns stand for the per-tile fixed
+  // cost (A tile re-read per column block, accumulator hand-over).
   p.bk = (np == 3 && option(COMET_OPT_GEMM_BK32)) ? 32 : 64;
-  while (p.bn > 32 && (long long)p.tiles_m * ((N + p.bn - 1) / p.bn) * 10 < 7LL * sms) p.bn >>= 1;
+  if (np == 3) {
+    // float32-grade mode: the tile is operand-feed-bound and a narrower one re-reads the A planes more often -- measured
+    // slower at 96 and 64 columns (fc2: 71.8 us at 128, 80.3 at 96, 102.4 at 64): narrow only to fill the SMs
+    p.bn = 128;
+    while (p.bn > 32 && (long long)p.tiles_m * ((N + p.bn - 1) / p.bn) * 10 < 7LL * sms) p.bn >>= 1;
+  } else {
+    long long best_cost = -1;
+    const int widths[4] = {128, 96, 64, 32};
+    for (int i = 0; i < 4; ++i) {
+      const int bn = widths[i];
+      if (bn == 96 && (N % 96 != 0 || !option(COMET_OPT_GEMM_BN96))) continue;
+      const long long tiles = (long long)p.tiles_m * ((N + bn - 1) / bn);
+      const long long cost = ((tiles + sms - 1) / sms) * (bn + 24);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.bn = bn; }
+    }
+  }
   for (int i = 0; i < np; ++i) {
     int rc = gemm::encode_kmajor(&maps.a[i], xp + i * x_plane_stride, M, K, x_ld, gemm::BM, p.bk);
     if (rc != COMET_OK) return rc;

@@ -82,7 +82,8 @@ int comet_has_tensor_path(void);
 #define COMET_OPT_GEMM_TMA_STORE 5 /* transformer GEMM: results leave through shared memory and bulk tensor stores (full
                                     128-byte lines) instead of per-lane row stores; on by default */
 #define COMET_OPT_GEMM_EW16 6 /* transformer GEMM, one-plane (autocast) mode: sixteen epilogue warps instead of eight */
-#define COMET_OPT_COUNT 7
+#define COMET_OPT_GEMM_BN96 7 /* transformer GEMM: 96-column output tiles where they divide N and save a round of CTAs */
+#define COMET_OPT_COUNT 8
 int comet_set_option(int option, int value);
 int comet_get_option(int option);
 /* Number of kernel launches this library has issued since it was loaded (bench.py's `gpu_launches`). */

@@ -27,7 +27,9 @@ mode = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 _lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_TMA_STORE, mode))   # bit 0: float32 result by TMA store, bit 1: planes
 ew16 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 _lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_EW16, ew16))
-print("tma store mode", mode, "ew16", ew16)
+bn96 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+_lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_BN96, bn96))
+print("tma store mode", mode, "ew16", ew16, "bn96", bn96)
 for np_ in (1, 3):
     run = tc._Run(tc._Weights(), np_, dev)
     M = 9216
