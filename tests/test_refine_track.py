@@ -54,6 +54,21 @@ def test_shallow_encoder_matches_reference(golden):
     assert rel_to_max(y_cl.numpy(), g[NAME + "/enc_out"]) < 1e-5
 
 
+def test_fused_encoder_parameter_order_is_the_state_dict_order():
+    """comet_shallow_encoder_pack_f32 takes the 16 parameter tensors in state-dict order: the mirror's list must be it."""
+    from comet_pose_estimation_b200.refine_track import ShallowEncoder
+
+    fnet = ShallowEncoder(input_dim=3)
+    want = [f"{n}.{s}" for n in fnet._PARAM_ORDER for s in ("weight", "bias")]
+    assert want == list(fnet.state_dict().keys())
+    shapes = [tuple(fnet.state_dict()[k].shape) for k in want[::2]]
+    assert shapes == [(32, 3, 3, 3), (32, 32, 3, 3), (32, 32, 3, 3), (32, 32, 1, 1),
+                      (32, 32, 3, 3), (32, 32, 3, 3), (32, 32, 1, 1), (32, 32, 1, 1)]
+    # CPU tensors, other patch sizes, training: the per-operator path
+    x = torch.zeros(2, 3, 31, 31)
+    assert not fnet._fused_ok(x, 31, 31)
+
+
 def test_patch_extraction_order_and_layout():
     from comet_pose_estimation_b200.refine_track import extract_patches
 
