@@ -333,16 +333,25 @@ __global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const A
       reinterpret_cast<float4*>(Vs)[e] = vv;
     }
     float4 q4[DH4];
-    const bool active = lane < p.Lq;
+    // At most 16 queries (the T = 16 time attention): both half-warps take the same queries and split the KEYS -- lanes
+    // 0-15 the first half, lanes 16-31 the second -- and merge their running (max, sum, output row) with the online-softmax
+    // rescale through 16-lane shuffles; otherwise half of the warp would idle through the whole (batch item, head).
+    const bool split = p.Lq <= 16;
+    const int qrow = split ? (lane & 15) : lane;
+    const int khalf = (p.Lk + 1) >> 1;
+    const int j0 = split ? (lane >> 4) * khalf : 0, jn = split ? khalf : p.Lk;
+    const bool active = qrow < p.Lq;
 #pragma unroll
     for (int t = 0; t < DH4; ++t) {
-      q4[t] = (active && t < dh4) ? __ldg(reinterpret_cast<const float4*>(qp + (long long)lane * p.q_si) + t)
+      q4[t] = (active && t < dh4) ? __ldg(reinterpret_cast<const float4*>(qp + (long long)qrow * p.q_si) + t)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       q4[t].x *= p.scale; q4[t].y *= p.scale; q4[t].z *= p.scale; q4[t].w *= p.scale;   // MHA scales q before q k^T
     }
     __syncwarp();
     float mx = -INFINITY;
-    for (int j = 0; j < p.Lk; ++j) {
+    for (int jj = 0; jj < jn; ++jj) {
+      const int j = j0 + jj;
+      if (j >= p.Lk) break;              // (odd Lk: the second half is one key shorter)
       const float4* kr = reinterpret_cast<const float4*>(Ks + j * DH);
       float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f;      // four independent chains: one serial chain of dh FMAs is latency-bound
 #pragma unroll
@@ -358,7 +367,9 @@ __global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const A
 #pragma unroll
     for (int t = 0; t < DH4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum = 0.f;
-    for (int j = 0; j < p.Lk; ++j) {
+    for (int jj = 0; jj < jn; ++jj) {
+      const int j = j0 + jj;
+      if (j >= p.Lk) break;
       const float pj = expf(Ss[j * 33 + lane] - mx);
       sum += pj;
       const float4* vr = reinterpret_cast<const float4*>(Vs + j * DH);
@@ -369,10 +380,24 @@ __global__ void __launch_bounds__(ATS_WARPS * 32) attention_small_kernel(const A
         acc[t].z = fmaf(pj, vv.z, acc[t].z); acc[t].w = fmaf(pj, vv.w, acc[t].w);
       }
     }
+    __syncwarp();
+    if (split) {
+      const float mo = __shfl_xor_sync(0xffffffffu, mx, 16), so = __shfl_xor_sync(0xffffffffu, sum, 16);
+      const float m = fmaxf(mx, mo);
+      const float e1 = expf(mx - m), e2 = expf(mo - m);      // a half without keys has max -inf and weight 0
+      sum = sum * e1 + so * e2;
+#pragma unroll
+      for (int t = 0; t < DH4; ++t) {
+        acc[t].x = acc[t].x * e1 + __shfl_xor_sync(0xffffffffu, acc[t].x, 16) * e2;
+        acc[t].y = acc[t].y * e1 + __shfl_xor_sync(0xffffffffu, acc[t].y, 16) * e2;
+        acc[t].z = acc[t].z * e1 + __shfl_xor_sync(0xffffffffu, acc[t].z, 16) * e2;
+        acc[t].w = acc[t].w * e1 + __shfl_xor_sync(0xffffffffu, acc[t].w, 16) * e2;
+      }
+    }
     const float inv = 1.f / sum;
     __syncwarp();                          // every lane is done reading V before its rows are overwritten
     float* Os = Vs;                        // [32][OLD]
-    if (active) {
+    if (active && (!split || lane < 16)) {
 #pragma unroll
       for (int t = 0; t < DH4; ++t)
         *reinterpret_cast<float4*>(Os + lane * OLD + 4 * t) = make_float4(acc[t].x * inv, acc[t].y * inv, acc[t].z * inv, acc[t].w * inv);
