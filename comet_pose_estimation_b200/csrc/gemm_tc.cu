@@ -317,22 +317,17 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
       const int m = mb * BM + 32 * wq + lane;
-      // Bias and residual of a chunk do not depend on the accumulator: they are requested before the wait for it (first
-      // chunk of the tile) / while the previous chunk's result is leaving (later chunks), so their DRAM latency -- a
-      // tile's epilogue is otherwise a serial chain "accumulator, residual load, add, store" per chunk -- is hidden.
+      // The residual of a chunk does not depend on the accumulator: it is requested before the wait for it (first chunk
+      // of the tile) / while the previous chunk's result is leaving (later chunks), so its DRAM latency -- a tile's
+      // epilogue is otherwise a serial chain "accumulator, residual load, add, store" per chunk -- is hidden.  Only with 8
+      // epilogue warps: 16 warps have 96 registers each.  (The bias, an L1 hit, is loaded where it is added: holding it
+      // in registers across the wait made the 16-warp variant spill 174 bytes and cost fc1 4 us of 29.)
       const int cph = ((p.bn >> 5) + EW / 4 - 1) / (EW / 4);     // 32-column chunks per column group (bn = 96: 2 + 1 or 1 + 1 + 1)
-      float4 bv[8];
       float rg[32];
-      bool bias_vec = false, res_vec = false;
+      bool res_vec = false;
       auto prefetch = [&](int c) {
         const int n0 = nb * p.bn + 32 * c;
-        const bool full = n0 + 32 <= p.N;
-        bias_vec = vec_bias && full;
-        res_vec = EW == 8 && vec_res && full && m < p.M;     // (16 epilogue warps: no registers for it)
-        if (bias_vec) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
-        }
+        res_vec = EW == 8 && vec_res && n0 + 32 <= p.N && m < p.M;
         if (res_vec) {
           const float* r = p.resid + (long long)m * p.resid_ld + n0;
 #pragma unroll
@@ -360,9 +355,12 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
         }
         const bool row_ok = m < p.M;
         if (row_ok) {
-          if (bias_vec) {
+          if (vec_bias && full_chunk) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w; }
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
           } else if (p.bias) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += (full_chunk || n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
