@@ -43,6 +43,7 @@ constexpr int OUT_STAGE_BYTES = 4096;            // per epilogue warp: one 32 x 
 struct Maps {
   CUtensorMap a[MAX_NP];   // X planes: {K, M} bf16, box {64, 128}
   CUtensorMap w[MAX_NP];   // W planes: {K, N} bf16, box {64, bn}
+  CUtensorMap wh[MAX_NP];  // W planes with box {64, bn / 2}: the half tile a CTA of a pair loads and multicasts (Params::cluster)
   CUtensorMap o;           // float32 result: {N, M}, box {32, 32}, 128-byte swizzle (TMA store; valid if Params::tma_out)
   CUtensorMap op[MAX_NP];  // result planes: {N, M} bf16, box {32, 32}, 64-byte swizzle (valid if Params::tma_pl)
 };
@@ -65,6 +66,8 @@ struct Params {
   int out_np;
   int gelu;                // exact (erf) GELU, nn.GELU() default (modules.py:133)
   int tma_out, tma_pl;     // results leave through shared memory and bulk tensor stores (row pitches allow a tensor map)
+  int cluster;             // launched as clusters of two CTAs that share every W tile (see the kernel)
+  int pairs_m;             // ceil(tiles_m / 2)
 };
 
 // ------------------------------------------------------------------ PTX helpers (see corr_tc.cu for the rationale)
@@ -124,6 +127,26 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the same load delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) of every
+// CTA of the cluster in `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask) : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void tcgen05_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -222,10 +245,17 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = p.tiles_m * p.tiles_n;
+  // Work list.  Alone: CTA b takes tiles b, b + grid, ... (m fastest).  As a PAIR (Params::cluster): cluster c takes units
+  // c, c + clusters, ...; a unit is one column block and two neighbouring row blocks, one per CTA -- both CTAs need the
+  // same W tile at the same time, so each loads HALF of it and multicasts it into both shared memories: the operand
+  // traffic per CTA drops from A + W to A + W / 2 (the float32-grade mode is bound by that traffic).
+  const int crank = p.cluster ? (int)cluster_ctarank() : 0;
+  const int csz = p.cluster ? 2 : 1;
+  const int ntiles = p.cluster ? p.pairs_m * p.tiles_n : p.tiles_m * p.tiles_n;
+  const int t_first = blockIdx.x / csz, t_step = gridDim.x / csz, t_div = p.cluster ? p.pairs_m : p.tiles_m;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], csz); }   // a stage is free when both CTAs are done with it
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -235,6 +265,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();     // the peer's barriers exist before anything is sent to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -242,15 +273,19 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
     // ===================== TMA producer =====================
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
+      for (int tile = t_first; tile < ntiles; tile += t_step) {
+        const int mb = (tile % t_div) * csz + crank, nb = tile / t_div;
         for (int kb = 0; kb < p.ktiles; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = smem + stage * stage_bytes;
-          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);      // A from this CTA, W half from each CTA of the pair
           for (int i = 0; i < NPK; ++i) {
             tma_load_2d(&maps.a[i], &full[stage], dst + i * a_tile_bytes, kb * p.bk, mb * BM);
-            tma_load_2d(&maps.w[i], &full[stage], dst + NPK * a_tile_bytes + i * b_tile_bytes, kb * p.bk, nb * p.bn);
+            if (p.cluster)
+              tma_load_2d_multicast(&maps.wh[i], &full[stage], dst + NPK * a_tile_bytes + i * b_tile_bytes + crank * (b_tile_bytes / 2),
+                                    kb * p.bk, nb * p.bn + crank * (p.bn / 2), (uint16_t)3);
+            else
+              tma_load_2d(&maps.w[i], &full[stage], dst + NPK * a_tile_bytes + i * b_tile_bytes, kb * p.bk, nb * p.bn);
           }
           if (++stage == (uint32_t)p.nstage) { stage = 0; phase ^= 1; }
         }
@@ -259,7 +294,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = t_first; tile < ntiles; tile += t_step) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       // TMEM columns of tile buffer `acc`: [main 128 | low-order pairs 128]
@@ -294,7 +329,8 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
               }
             }
           }
-          tcgen05_commit(&empty[stage]);                       // smem stage free once these MMAs retire
+          if (p.cluster) tcgen05_commit_multicast(&empty[stage], (uint16_t)3);   // ... in both CTAs: the peer's W half lives here too
+          else tcgen05_commit(&empty[stage]);                  // smem stage free once these MMAs retire
           if (kb + 1 == p.ktiles) tcgen05_commit(&acc_full[acc]);   // accumulator complete
         }
         __syncwarp();
@@ -314,8 +350,8 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
     const bool vec_pl = ONP > 0 && (p.outp_ld % 16 == 0) && (((uintptr_t)p.outp[0]) % 32 == 0) &&
                         (ONP < 2 || ((uintptr_t)p.outp[1]) % 32 == 0) && (ONP < 3 || ((uintptr_t)p.outp[2]) % 32 == 0);
     const bool vec_bias = p.bias && (((uintptr_t)p.bias) % 16 == 0) && (p.bn % 32 == 0);   // n0 is then a multiple of 32
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int mb = tile % p.tiles_m, nb = tile / p.tiles_m;
+    for (int tile = t_first; tile < ntiles; tile += t_step) {
+      const int mb = (tile % t_div) * csz + crank, nb = tile / t_div;
       const int m = mb * BM + 32 * wq + lane;
       // The residual of a chunk does not depend on the accumulator: it is requested before the wait for it (first chunk
       // of the tile) / while the previous chunk's result is leaving (later chunks), so its DRAM latency -- a tile's
@@ -494,6 +530,7 @@ __global__ void __launch_bounds__((2 + EW) * 32, 1) gemm_tc_kernel(const __grid_
 
   tcgen05_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();     // no CTA retires while its peer may still arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * BN));
   }
@@ -653,14 +690,40 @@ extern "C" int comet_linear_tc(const void* x_planes, long long x_plane_stride, l
     }
   }
   const int smem = ((p.nstage * stage_bytes + 1023) & ~1023) + ew * gemm::OUT_STAGE_BYTES + (2 * p.nstage + 4) * 8 + 16;
-  const long long ntiles = (long long)p.tiles_m * p.tiles_n;
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  // CTA pairs sharing the W tile (COMET_OPT_GEMM_PAIR: 1 = float32-grade mode for K >= 1024, 2 = autocast mode, 4 = any K).
+  // Measured at M = 9216 (scripts/gemm_time.py): the long-K GEMM of the float32-grade mode gains (fc2, K = 1536:
+  // 76.2 -> 69.9 us) -- its 24 K blocks per tile are where the operand feed binds --; the K = 384 GEMMs do not
+  // (43.3 -> 43.8, 23.0 -> 24.7, 64.3 -> 65.7 us: six K blocks per tile leave them bound by pipeline fill and epilogue, and
+  // the pair runs in lock-step), nor does the autocast mode (20.6 -> 22.6, 22.7 -> 24.3 us).  Needs at least as many
+  // (row-block pair, column block) units as clusters, and a half tile of whole swizzle atoms.
+  p.pairs_m = (p.tiles_m + 1) / 2;
+  const int pair_mode = option(COMET_OPT_GEMM_PAIR);
+  p.cluster = ((np == 3 ? (pair_mode & 1) : (pair_mode & 2)) && (K >= 1024 || (pair_mode & 4)) && p.tiles_m >= 2 &&
+               p.bn % 16 == 0 && (long long)p.pairs_m * p.tiles_n >= sms / 2) ? 1 : 0;
+  if (p.cluster) {
+    for (int i = 0; i < np; ++i) {
+      int rc = gemm::encode_kmajor(&maps.wh[i], wp + i * w_plane_stride, N, K, w_ld, p.bn / 2, p.bk);
+      if (rc != COMET_OK) return rc;
+    }
+  }
+  const long long ntiles = p.cluster ? (long long)p.pairs_m * p.tiles_n : (long long)p.tiles_m * p.tiles_n;
+  const int grid = p.cluster ? (int)(ntiles < sms / 2 ? ntiles : sms / 2) * 2 : (int)(ntiles < sms ? ntiles : sms);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(ew == 16 ? gemm::THREADS_EW16 : gemm::THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.cluster ? 1 : 0;
   if (ew == 16) {
     COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm::gemm_tc_kernel<16><<<grid, gemm::THREADS_EW16, smem, (cudaStream_t)stream>>>(maps, p);
+    COMET_CUDA(cudaLaunchKernelEx(&cfg, gemm::gemm_tc_kernel<16>, maps, p));
   } else {
     COMET_CUDA(cudaFuncSetAttribute(gemm::gemm_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    gemm::gemm_tc_kernel<8><<<grid, gemm::THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    COMET_CUDA(cudaLaunchKernelEx(&cfg, gemm::gemm_tc_kernel<8>, maps, p));
   }
   return launch_status("gemm_tc_kernel");
 }

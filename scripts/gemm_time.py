@@ -29,7 +29,9 @@ ew16 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 _lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_EW16, ew16))
 bn96 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 _lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_BN96, bn96))
-print("tma store mode", mode, "ew16", ew16, "bn96", bn96)
+pair = int(sys.argv[4]) if len(sys.argv) > 4 else int(_lib.lib.comet_get_option(_lib.OPT_GEMM_PAIR))
+_lib.check(_lib.lib.comet_set_option(_lib.OPT_GEMM_PAIR, pair))
+print("tma store mode", mode, "ew16", ew16, "bn96", bn96, "pair", pair)
 for np_ in (1, 3):
     run = tc._Run(tc._Weights(), np_, dev)
     M = 9216

@@ -153,3 +153,43 @@ def test_weight_update_invalidates_cached_planes_and_graphs():
         sd["input_transform.weight"] = sd["input_transform.weight"] * 0.5
         m.load_state_dict(sd)
         assert rel(m(x), m._forward_torch(x)) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("np_", [3, 1])
+def test_gemm_data_path_variants_are_bit_identical(np_):
+    """Per-lane stores vs bulk tensor stores from the swizzled staging buffers, 8 vs 16 epilogue warps, 128- vs 96-column
+    tiles, single CTAs vs CTA pairs that multicast the W tile (an odd number of row blocks: the last pair has a phantom
+    tile): the same sums in the same order, so the results must agree bit for bit."""
+    from comet_pose_estimation_b200 import _lib
+    from comet_pose_estimation_b200 import update_former_tc as tc
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(3)
+    run = tc._Run(tc._Weights(), np_, dev)
+    opts = (_lib.OPT_GEMM_TMA_STORE, _lib.OPT_GEMM_EW16, _lib.OPT_GEMM_BN96, _lib.OPT_GEMM_PAIR)
+    saved = [_lib.lib.comet_get_option(o) for o in opts]
+    try:
+        for (M, K, N, kw) in ((9088, 1536, 384, dict(resid=True)), (9216, 384, 1152, dict()),
+                              (9216, 384, 1536, dict(gelu=True, want_planes=True)), (300, 664, 130, dict(want_planes=True))):
+            x = torch.randn(M, K, device=dev, generator=g)
+            w = torch.randn(N, K, device=dev, generator=g) / K ** 0.5
+            b = torch.randn(N, device=dev, generator=g)
+            r = torch.randn(M, N, device=dev, generator=g) if kw.get("resid") else None
+            kw2 = {k: v for k, v in kw.items() if k != "resid"}
+            xp = run.split(x)
+            ref = None
+            for cfg in ((0, 0, 0, 0), (3, 0, 0, 0), (3, 1, 0, 0), (3, 1, 1, 0), (3, 1, 1, 7), (1, 0, 1, 7), (2, 1, 0, 5)):
+                for o, v in zip(opts, cfg):
+                    _lib.check(_lib.lib.comet_set_option(o, v))
+                out, planes = run.linear(xp, w, b, resid=r, **kw2)
+                torch.cuda.synchronize()
+                got = (out.clone(), None if planes is None else planes[..., :N].clone())
+                if ref is None:
+                    ref = got
+                else:
+                    assert torch.equal(got[0], ref[0]), (M, K, N, cfg)
+                    assert ref[1] is None or torch.equal(got[1], ref[1]), (M, K, N, cfg)
+    finally:
+        for o, v in zip(opts, saved):
+            _lib.check(_lib.lib.comet_set_option(o, v))
