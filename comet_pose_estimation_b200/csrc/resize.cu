@@ -105,7 +105,7 @@ extern "C" int comet_upsample_bilinear_ac_f32(const float* in, float* out, long 
 // patches, the largest item of the encoder once the resizes are fixed).  Two passes over a plane that stays in L1/L2.
 namespace comet {
 
-// NCHW: one warp per (n, c) plane of HW contiguous elements
+// NCHW, small planes (the patch encoder's 16x16 .. 4x4 maps): one warp per (n, c) plane of HW contiguous elements
 __global__ void __launch_bounds__(256) instance_norm_nchw_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                  long long planes, int HW, float eps, int relu) {
   const int lane = threadIdx.x & 31;
@@ -127,6 +127,61 @@ __global__ void __launch_bounds__(256) instance_norm_nchw_kernel(const float* __
       float y = (__ldg(p + i) - mean) * rstd;
       q[i] = relu ? fmaxf(y, 0.f) : y;
     }
+  }
+}
+
+// NCHW, large planes (BasicEncoder: 1024 .. 4096 planes of 128x128 .. 16x16 positions per 16-frame sequence): one CTA per
+// plane.  A warp per plane leaves ~7 warps per SM walking 64 KB each -- 3.7 ms per sequence at 512x512 frames, a third of
+// the encoder.  The plane is read from HBM once: it is parked in shared memory (float32, up to 128x128 positions) for the
+// second and third pass; larger planes re-read global memory (L2).  T = float or __nv_bfloat16 (the encoder under
+// torch.autocast: statistics in float32 of the bf16 values, result rounded to bf16 -- what ATen's batch-norm kernel does
+// for a bf16 input -- without the two cast passes around a float32 kernel).
+constexpr int INORM_SMEM_ELEMS = 16384;
+__device__ __forceinline__ float inorm_load(const float* p, long long i) { return __ldg(p + i); }
+__device__ __forceinline__ float inorm_load(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void inorm_store(float* p, long long i, float v) { p[i] = v; }
+__device__ __forceinline__ void inorm_store(__nv_bfloat16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                 // red[] of the previous reduction has been read
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) instance_norm_plane_kernel(const T* __restrict__ in, T* __restrict__ out, long long planes,
+                                                                  int HW, float eps, int relu) {
+  extern __shared__ __align__(16) float plane_smem[];
+  __shared__ float red[8];
+  const bool parked = HW <= INORM_SMEM_ELEMS;
+  for (long long pl = blockIdx.x; pl < planes; pl += gridDim.x) {
+    const T* p = in + pl * HW;
+    T* q = out + pl * HW;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const float x = inorm_load(p, i);
+      if (parked) plane_smem[i] = x;
+      s += x;
+    }
+    const float mean = block_sum_256(s, red) / (float)HW;
+    float v = 0.f;
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const float d = (parked ? plane_smem[i] : inorm_load(p, i)) - mean;
+      v = fmaf(d, d, v);
+    }
+    const float rstd = rsqrtf(block_sum_256(v, red) / (float)HW + eps);
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const float y = ((parked ? plane_smem[i] : inorm_load(p, i)) - mean) * rstd;
+      inorm_store(q, i, relu ? fmaxf(y, 0.f) : y);
+    }
+    __syncthreads();               // the parked plane is dead before the next one moves in
   }
 }
 
@@ -155,6 +210,23 @@ __global__ void __launch_bounds__(256) instance_norm_cl_kernel(const float* __re
 
 }  // namespace comet
 
+namespace comet {
+template <typename T>
+static int launch_instance_norm_planes(const T* in, T* out, long long planes, int HW, float eps, int relu, comet_stream_t stream) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  COMET_CUDA(cudaGetDevice(&dev));
+  const int smem = HW <= INORM_SMEM_ELEMS ? HW * 4 : 0;
+  if (dev < 64 && !configured[dev]) {
+    COMET_CUDA(cudaFuncSetAttribute(instance_norm_plane_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, INORM_SMEM_ELEMS * 4));
+    configured[dev] = true;
+  }
+  long long blocks = planes < 148LL * 16 ? planes : 148LL * 16;
+  instance_norm_plane_kernel<T><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(in, out, planes, HW, eps, relu);
+  return launch_status("instance_norm_plane_kernel");
+}
+}  // namespace comet
+
 extern "C" int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int HW, int layout, int relu,
                                        float eps, comet_stream_t stream) {
   COMET_REQUIRE(N >= 0 && C >= 0 && HW >= 1, "bad shape");
@@ -167,10 +239,20 @@ extern "C" int comet_instance_norm_f32(const float* in, float* out, long long N,
     comet::instance_norm_cl_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N, C, HW, eps, relu);
     return comet::launch_status("instance_norm_cl_kernel");
   }
+  if (HW >= 1024) return comet::launch_instance_norm_planes<float>(in, out, N * C, HW, eps, relu, stream);
   long long blocks = (N * C + 7) / 8;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   comet::instance_norm_nchw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N * C, HW, eps, relu);
   return comet::launch_status("instance_norm_nchw_kernel");
+}
+
+extern "C" int comet_instance_norm_bf16(const void* in, void* out, long long N, int C, int HW, int relu, float eps,
+                                        comet_stream_t stream) {
+  COMET_REQUIRE(N >= 0 && C >= 0 && HW >= 1, "bad shape");
+  if (N * C == 0) return COMET_OK;
+  COMET_REQUIRE(in && out, "null pointer");
+  return comet::launch_instance_norm_planes<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                           reinterpret_cast<__nv_bfloat16*>(out), N * C, HW, eps, relu, stream);
 }
 
 // ---- patch gather of refine_track (comet/models/refine_track.py:71-111) ----------------------------------------------

@@ -65,9 +65,7 @@ def _inorm(norm: nn.InstanceNorm2d, x: torch.Tensor, relu: bool) -> torch.Tensor
     if _library_ok(x):
         from .utils import instance_norm
 
-        if x.dtype != torch.float32:
-            return instance_norm(x.float(), relu=relu, eps=norm.eps).to(x.dtype)
-        return instance_norm(x, relu=relu, eps=norm.eps)
+        return instance_norm(x, relu=relu, eps=norm.eps)      # dtype kept; bf16 (autocast) large planes: one bf16 kernel
     y = norm(x)
     return F.relu(y) if relu else y
 

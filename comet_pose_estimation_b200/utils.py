@@ -168,17 +168,27 @@ def upsample_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
 
 
 def instance_norm(x: torch.Tensor, relu: bool = False, eps: float = 1e-5) -> torch.Tensor:
-    """``nn.InstanceNorm2d(C)(x)`` (affine=False, no running stats; optionally followed by ReLU) for a 4-D float32 CUDA
-    tensor, contiguous or channels-last (memory format preserved)."""
+    """``nn.InstanceNorm2d(C)(x)`` (affine=False, no running stats; optionally followed by ReLU) for a 4-D float32 or
+    bfloat16 CUDA tensor, contiguous or channels-last (dtype kept; memory format kept except for large bf16 planes)."""
     require_cuda(x, "x")
     require_no_grad(x)
     assert x.dim() == 4
     N, C, H, W = x.shape
+    if x.dtype == torch.bfloat16 and (x.is_contiguous() or H * W >= 1024):
+        # bf16 in, bf16 out (the encoders under torch.autocast): float32 statistics of the bf16 values, one kernel, no
+        # cast passes; NCHW (large channels-last planes are re-laid out: the per-plane kernel reads a plane once)
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.comet_instance_norm_bf16(x.data_ptr(), out.data_ptr(), N, C, H * W, int(relu), float(eps),
+                                                    stream_ptr(x.device)))
+        return out
+    in_dtype = x.dtype
     x = x if x.dtype == torch.float32 else x.float()
     cl = C > 1 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
     if cl and H * W > 4096 and N * C < 148 * 256:
         # few large planes: the channels-last kernel (one thread per (sample, channel), built for the patch encoder's
-        # 262144 planes of <= 256 positions) would serialise over H*W; the NCHW kernel (one warp per plane) does not
+        # 262144 planes of <= 256 positions) would serialise over H*W; the NCHW kernel (one CTA per plane) does not
         cl = False
     if not cl:
         x = x.contiguous()
@@ -187,4 +197,4 @@ def instance_norm(x: torch.Tensor, relu: bool = False, eps: float = 1e-5) -> tor
         _lib.check(lib.comet_instance_norm_f32(x.data_ptr(), out.data_ptr(), N, C, H * W,
                                                _lib.FMAPS_CHANNEL_LAST if cl else _lib.FMAPS_NCHW, int(relu), float(eps),
                                                stream_ptr(x.device)))
-    return out
+    return out if in_dtype == torch.float32 else out.to(in_dtype)

@@ -184,6 +184,10 @@ int comet_upsample_bilinear_ac_f32(const float* in, float* out, long long N, int
 int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int HW, int layout, int relu, float eps,
                             comet_stream_t stream);
 
+/* The same for bf16 tensors in NCHW layout (the encoders under torch.autocast: statistics in float32 of the bf16 values,
+ * result rounded to bf16). */
+int comet_instance_norm_bf16(const void* in, void* out, long long N, int C, int HW, int relu, float eps, comet_stream_t stream);
+
 /* Patch gather of refine_track (comet/models/refine_track.py:71-111): images (B,S,C,H,W) contiguous, topleft (B,S,N,2)
  * int32 (x, y) corners already clamped to [0, W-P] x [0, H-P] -> out (B*N*S, P, P, C) channel-last, patches in
  * (b, n, s) order. */

@@ -747,3 +747,26 @@ def test_tensor_path_output_modes_agree(cb):
         assert torch.equal(red.nan_to_num(1234.5), stored.nan_to_num(1234.5))
         assert torch.equal(red.nan_to_num(1234.5), off.nan_to_num(1234.5))
         assert cb._lib.lib.comet_tc_status() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(3, 64, 128, 128), (2, 5, 40, 30), (1, 2, 200, 200)])
+def test_instance_norm_large_planes_and_bf16(cb, shape):
+    """One CTA per plane (parked in shared memory up to 128x128 positions, re-read beyond): float32 against torch, and
+    the bf16 in / bf16 out form (float32 statistics of the bf16 values) against torch's own bf16 instance norm."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(*shape, device="cuda", generator=g) * 2.5 + 0.7
+    norm = torch.nn.InstanceNorm2d(shape[1])
+    for relu in (False, True):
+        want = norm(x.double())
+        want = torch.relu(want) if relu else want
+        got = cb.instance_norm(x, relu=relu)
+        assert got.dtype == torch.float32 and rel_to_max(host(got), host(want)) < 2e-6
+        xb = x.to(torch.bfloat16)
+        wb = norm(xb.double())
+        wb = torch.relu(wb) if relu else wb
+        gb = cb.instance_norm(xb, relu=relu)
+        assert gb.dtype == torch.bfloat16 and gb.shape == xb.shape
+        assert rel_to_max(host(gb.float()), host(wb)) < 5e-3          # one bf16 rounding of the result
+        gcl = cb.instance_norm(xb.contiguous(memory_format=torch.channels_last), relu=relu)
+        assert gcl.dtype == torch.bfloat16 and rel_to_max(host(gcl.float()), host(wb)) < 5e-3
