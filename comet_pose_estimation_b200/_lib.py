@@ -47,6 +47,7 @@ SIGNATURES = {
     "comet_sample_features4d_f32": (_i, [_p, _ll, _p, _ll, _ll, _p, _i, _i, _i, _i, _i, _p]),
     "comet_sample_features4d_cl_f32": (_i, [_p, _ll, _p, _ll, _ll, _p, _i, _i, _i, _i, _i, _p]),
     "comet_upsample_bilinear_ac_f32": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _i, _p]),
+    "comet_upsample_bilinear_ac_bf16": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _p]),
     "comet_instance_norm_f32": (_i, [_p, _p, _ll, _i, _i, _i, _i, C.c_float, _p]),
     "comet_instance_norm_bf16": (_i, [_p, _p, _ll, _i, _i, _i, C.c_float, _p]),
     "comet_extract_patches_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

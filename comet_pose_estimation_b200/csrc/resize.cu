@@ -22,7 +22,15 @@ struct ResizeTap {
   }
 };
 
-__global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restrict__ in, float* __restrict__ out,
+__device__ __forceinline__ float rs_load(const float* p, int i) { return __ldg(p + i); }
+__device__ __forceinline__ float rs_load(const __nv_bfloat16* p, int i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void rs_store(float* p, long long i, float v) { p[i] = v; }
+__device__ __forceinline__ void rs_store(__nv_bfloat16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+// T = float, or __nv_bfloat16 (the encoders under torch.autocast: float32 arithmetic on the bf16 values, result rounded
+// to bf16 -- the same values as a float32 resize between two casts, without the two cast passes)
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_nchw_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                             long long planes, int Hi, int Wi, int Ho, int Wo, float sy,
                                                             float sx) {
   const long long total = planes * Ho * Wo;
@@ -35,10 +43,10 @@ __global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restr
     ResizeTap ty, tx;
     ty.init(yo, sy, Hi);
     tx.init(xo, sx, Wi);
-    const float* p = in + pl * Hi * Wi;
-    const float v00 = __ldg(p + ty.i0 * Wi + tx.i0), v01 = __ldg(p + ty.i0 * Wi + tx.i1);
-    const float v10 = __ldg(p + ty.i1 * Wi + tx.i0), v11 = __ldg(p + ty.i1 * Wi + tx.i1);
-    out[idx] = ty.w0 * (tx.w0 * v00 + tx.w1 * v01) + ty.w1 * (tx.w0 * v10 + tx.w1 * v11);
+    const T* p = in + pl * Hi * Wi;
+    const float v00 = rs_load(p, ty.i0 * Wi + tx.i0), v01 = rs_load(p, ty.i0 * Wi + tx.i1);
+    const float v10 = rs_load(p, ty.i1 * Wi + tx.i0), v11 = rs_load(p, ty.i1 * Wi + tx.i1);
+    rs_store(out, idx, ty.w0 * (tx.w0 * v00 + tx.w1 * v01) + ty.w1 * (tx.w0 * v10 + tx.w1 * v11));
   }
 }
 
@@ -94,8 +102,23 @@ extern "C" int comet_upsample_bilinear_ac_f32(const float* in, float* out, long 
         reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), N, C / 4, Hi, Wi, Ho, Wo, sy, sx);
     return launch_status("upsample_cl_kernel");
   }
-  upsample_nchw_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(in, out, N * C, Hi, Wi, Ho, Wo, sy, sx);
+  upsample_nchw_kernel<float><<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(in, out, N * C, Hi, Wi, Ho, Wo, sy, sx);
   return launch_status("upsample_nchw_kernel");
+}
+
+extern "C" int comet_upsample_bilinear_ac_bf16(const void* in, void* out, long long N, int C, int Hi, int Wi, int Ho, int Wo,
+                                               comet_stream_t stream) {
+  COMET_REQUIRE(N >= 0 && C >= 0 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "bad shape");
+  const long long total = N * C * (long long)Ho * Wo;
+  if (total == 0) return COMET_OK;
+  COMET_REQUIRE(in && out, "null pointer");
+  const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  long long b = (total + 255) / 256;
+  if (b > 148LL * 64) b = 148LL * 64;
+  upsample_nchw_kernel<__nv_bfloat16><<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), N * C, Hi, Wi, Ho, Wo, sy, sx);
+  return launch_status("upsample_nchw_kernel<bf16>");
 }
 
 // ---- instance normalisation (+ optional ReLU) of the patch encoder ---------------------------------------------------

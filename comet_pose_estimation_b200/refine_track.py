@@ -53,9 +53,9 @@ def _resize(x: torch.Tensor, size) -> torch.Tensor:
     if _library_ok(x):
         from .utils import upsample_bilinear_align_corners
 
-        if x.dtype != torch.float32:
-            return upsample_bilinear_align_corners(x.float(), size).to(x.dtype)
-        return upsample_bilinear_align_corners(x, size)
+        if x.dtype == torch.float32 or (x.dtype == torch.bfloat16 and x.is_contiguous()):
+            return upsample_bilinear_align_corners(x, size)        # (bf16 NCHW: one kernel, bf16 in / bf16 out)
+        return upsample_bilinear_align_corners(x.float(), size).to(x.dtype)
     return F.interpolate(x, size, mode="bilinear", align_corners=True)
 
 

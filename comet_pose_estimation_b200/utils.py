@@ -153,6 +153,11 @@ def upsample_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
     assert x.dim() == 4
     N, C, Hi, Wi = x.shape
     Ho, Wo = (size, size) if isinstance(size, int) else tuple(size)
+    if x.dtype == torch.bfloat16 and x.is_contiguous():
+        out = torch.empty((N, C, Ho, Wo), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.comet_upsample_bilinear_ac_bf16(x.data_ptr(), out.data_ptr(), N, C, Hi, Wi, Ho, Wo, stream_ptr(x.device)))
+        return out
     x = x if x.dtype == torch.float32 else x.float()
     cl = (C % 4 == 0 and C > 1 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
           and x.data_ptr() % 16 == 0)

@@ -179,6 +179,10 @@ int comet_sample_features4d_cl_f32(const float* input, long long in_sb, const fl
 int comet_upsample_bilinear_ac_f32(const float* in, float* out, long long N, int C, int Hi, int Wi, int Ho, int Wo,
                                    int layout, comet_stream_t stream);
 
+/* The same for bf16 tensors in NCHW layout (float32 arithmetic, result rounded to bf16). */
+int comet_upsample_bilinear_ac_bf16(const void* in, void* out, long long N, int C, int Hi, int Wi, int Ho, int Wo,
+                                    comet_stream_t stream);
+
 /* nn.InstanceNorm2d(affine=False, eps) (+ ReLU when relu != 0) of the same encoder (blocks.py:128-131,
  * comet/models/modules.py:86-90): per (sample, channel) plane of HW elements, biased variance. */
 int comet_instance_norm_f32(const float* in, float* out, long long N, int C, int HW, int layout, int relu, float eps,

@@ -770,3 +770,12 @@ def test_instance_norm_large_planes_and_bf16(cb, shape):
         assert rel_to_max(host(gb.float()), host(wb)) < 5e-3          # one bf16 rounding of the result
         gcl = cb.instance_norm(xb.contiguous(memory_format=torch.channels_last), relu=relu)
         assert gcl.dtype == torch.bfloat16 and rel_to_max(host(gcl.float()), host(wb)) < 5e-3
+
+
+@pytest.mark.gpu
+def test_bf16_resize_equals_float32_resize_between_casts(cb):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = (torch.randn(3, 7, 20, 33, device="cuda", generator=g) * 3).to(torch.bfloat16)
+    got = cb.upsample_bilinear_align_corners(x, (41, 50))
+    want = cb.upsample_bilinear_align_corners(x.float(), (41, 50)).to(torch.bfloat16)
+    assert got.dtype == torch.bfloat16 and torch.equal(got, want)
