@@ -773,9 +773,17 @@ def test_instance_norm_large_planes_and_bf16(cb, shape):
 
 
 @pytest.mark.gpu
-def test_bf16_resize_equals_float32_resize_between_casts(cb):
+def test_bf16_resize_is_one_rounding_away_from_the_exact_resize(cb):
+    """bf16 in / bf16 out resize: float32 arithmetic on the bf16 values, one rounding of the result (the float32 kernel
+    between two casts gives the same values up to the contraction of the interpolation's multiply-adds)."""
+    import torch.nn.functional as F
+
     g = torch.Generator(device="cuda").manual_seed(9)
     x = (torch.randn(3, 7, 20, 33, device="cuda", generator=g) * 3).to(torch.bfloat16)
     got = cb.upsample_bilinear_align_corners(x, (41, 50))
-    want = cb.upsample_bilinear_align_corners(x.float(), (41, 50)).to(torch.bfloat16)
-    assert got.dtype == torch.bfloat16 and torch.equal(got, want)
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == (3, 7, 41, 50)
+    exact = F.interpolate(x.double(), (41, 50), mode="bilinear", align_corners=True)
+    err = (got.double() - exact).abs()
+    assert bool((err <= exact.abs() * 2.0 ** -8 + 1e-6).all())               # half a bf16 ulp + float32 noise
+    between = cb.upsample_bilinear_align_corners(x.float(), (41, 50)).to(torch.bfloat16)
+    assert float((got != between).float().mean()) < 0.01                      # the odd tie broken the other way
