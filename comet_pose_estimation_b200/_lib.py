@@ -17,7 +17,7 @@ PREC_F32, PREC_BF16_AUTOCAST = 0, 1
 PYR_NCHW, PYR_CHANNEL_LAST, PYR_ALL_CHANNEL_LAST, PYR_UP2_SOURCE = 0, 1, 2, 3
 FMAPS_NCHW, FMAPS_CHANNEL_LAST = 0, 1
 MAX_LEVELS, MAX_RADIUS = 8, 7
-OPT_TENSOR_PATH, OPT_TMA_LOOKUP, OPT_GEMM_BK32, OPT_TC_OVERLAP_MISC, OPT_TC_REDUCE_STORE, OPT_GEMM_TMA_STORE, OPT_GEMM_EW16, OPT_GEMM_BN96, OPT_GEMM_PAIR = 0, 1, 2, 3, 4, 5, 6, 7, 8
+OPT_TENSOR_PATH, OPT_TMA_LOOKUP, OPT_GEMM_BK32, OPT_TC_OVERLAP_MISC, OPT_TC_REDUCE_STORE, OPT_GEMM_TMA_STORE, OPT_GEMM_EW16, OPT_GEMM_BN96, OPT_GEMM_PAIR, OPT_ATTN_MMA = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 _p = C.c_void_p
 _i = C.c_int

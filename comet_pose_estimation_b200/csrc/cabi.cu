@@ -10,7 +10,7 @@ char* last_error_buf() {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-static std::atomic<int> g_options[COMET_OPT_COUNT] = {{1}, {1}, {0}, {0}, {1}, {3}, {1}, {1}, {1}};   // specialised paths on; the two measured-slower experiments off
+static std::atomic<int> g_options[COMET_OPT_COUNT] = {{1}, {1}, {0}, {0}, {1}, {3}, {1}, {1}, {1}, {1}};   // specialised paths on; the two measured-slower experiments off
 int option(int which) { return (which >= 0 && which < COMET_OPT_COUNT) ? g_options[which].load(std::memory_order_relaxed) : 0; }
 }  // namespace comet
 

@@ -513,6 +513,149 @@ __global__ void __launch_bounds__(ATR_WARPS * 32) attention_rows_kernel(const At
   }
 }
 
+// At least 64 queries in AUTOCAST mode, any number of keys (tiles of 64 with the online-softmax rescale), on the tensor cores: under torch.autocast the reference's
+// q / k / v are bf16 and its attention kernel multiplies in bf16 with float32 accumulation, so S = q k^T and O = P v run
+// as mma.sync.m16n8k16 (bf16 x bf16 -> float32).  A warp owns 16 queries: S (16 x 64) stays in the accumulator
+// registers, the softmax runs on them (a row lives in the four lanes of a quad: two shuffles per reduction), and the
+// probabilities are repacked in registers into the A fragments of the second product -- the accumulator layout of two
+// neighbouring 8-key tiles IS the A layout of one 16-key step.  K is staged as bf16 rows [key][dh + 8], V transposed
+// [dim][64 + 8] (both pitches conflict-free for the 32-bit fragment loads).  The float32 lane-per-query kernel above
+// spends ~250 instructions per query and head on this; here a warp issues 48 MMAs per 16 queries.
+constexpr int ATM_WARPS = 8;
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <int DH>   // head dimension, a multiple of 16
+__global__ void __launch_bounds__(ATM_WARPS * 32) attention_rows_mma_kernel(const AttnParams p) {
+  constexpr int KLD = DH + 8, VLD = 64 + 8, KS = DH / 16, DT = DH / 8;
+  __shared__ __align__(16) __nv_bfloat16 Ks[64 * KLD];    // [key][dh]
+  __shared__ __align__(16) __nv_bfloat16 Vt[DH * VLD];    // [dim][key]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int qchunks = (p.Lq + ATM_WARPS * 16 - 1) / (ATM_WARPS * 16);
+  const int ktiles = (p.Lk + 63) / 64;          // more than 64 keys: tiles of 64 with the online-softmax rescale
+  const long long nblocks = (long long)p.B * p.H * qchunks;
+  for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int qc = (int)(blk % qchunks);
+    const int h = (int)((blk / qchunks) % p.H);
+    const int b = (int)(blk / ((long long)qchunks * p.H));
+    const float* qp = p.q + b * p.q_sb + h * DH;
+    const float* kp = p.k + b * p.k_sb + h * DH;
+    const float* vp = p.v + b * p.v_sb + h * DH;
+    // this warp's 16 queries as A fragments (rows g and g + 8; MHA scales q before the product)
+    const int q0 = qc * (ATM_WARPS * 16) + warp * 16;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      float2 x00 = make_float2(0.f, 0.f), x01 = x00, x10 = x00, x11 = x00;
+      if (r0 < p.Lq) {
+        x00 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r0 * p.q_si + ks * 16 + 2 * t));
+        x01 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r0 * p.q_si + ks * 16 + 2 * t + 8));
+      }
+      if (r1 < p.Lq) {
+        x10 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r1 * p.q_si + ks * 16 + 2 * t));
+        x11 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r1 * p.q_si + ks * 16 + 2 * t + 8));
+      }
+      qa[ks][0] = pack_bf16(x00.x * p.scale, x00.y * p.scale);
+      qa[ks][1] = pack_bf16(x10.x * p.scale, x10.y * p.scale);
+      qa[ks][2] = pack_bf16(x01.x * p.scale, x01.y * p.scale);
+      qa[ks][3] = pack_bf16(x11.x * p.scale, x11.y * p.scale);
+    }
+    float oacc[DT][4];
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // running max / sum of rows g and g + 8
+#pragma unroll 1
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const int key0 = kt * 64;
+      __syncthreads();                          // the previous tile / block is fully consumed
+      for (int e = threadIdx.x; e < 64 * (DH / 4); e += blockDim.x) {
+        const int r = e / (DH / 4), c4 = e - r * (DH / 4);
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (key0 + r < p.Lk) {
+          kk = __ldg(reinterpret_cast<const float4*>(kp + (long long)(key0 + r) * p.k_si) + c4);
+          vv = __ldg(reinterpret_cast<const float4*>(vp + (long long)(key0 + r) * p.v_si) + c4);
+        }
+        *reinterpret_cast<uint2*>(Ks + r * KLD + 4 * c4) = make_uint2(pack_bf16(kk.x, kk.y), pack_bf16(kk.z, kk.w));
+        Vt[(4 * c4 + 0) * VLD + r] = __float2bfloat16_rn(vv.x);
+        Vt[(4 * c4 + 1) * VLD + r] = __float2bfloat16_rn(vv.y);
+        Vt[(4 * c4 + 2) * VLD + r] = __float2bfloat16_rn(vv.z);
+        Vt[(4 * c4 + 3) * VLD + r] = __float2bfloat16_rn(vv.w);
+      }
+      __syncthreads();
+      if (q0 >= p.Lq) continue;                 // warp-uniform: this warp only helps with the staging
+      // S = q k^T: 8 key tiles of 8
+      float sacc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const __nv_bfloat16* kr = Ks + (nt * 8 + g) * KLD + ks * 16 + 2 * t;
+          mma_bf16_16816(sacc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+        }
+      }
+      // softmax over the keys of rows g (c0, c1) and g + 8 (c2, c3); keys >= Lk are masked (every tile has a valid key)
+      float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = key0 + nt * 8 + 2 * t;
+        if (key >= p.Lk) { sacc[nt][0] = -INFINITY; sacc[nt][2] = -INFINITY; }
+        if (key + 1 >= p.Lk) { sacc[nt][1] = -INFINITY; sacc[nt][3] = -INFINITY; }
+        t0 = fmaxf(t0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        t1 = fmaxf(t1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+      const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+      const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);      // 0 on the first tile (running max -inf)
+      m0 = n0; m1 = n1;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = __expf(sacc[nt][0] - m0); sacc[nt][1] = __expf(sacc[nt][1] - m0);
+        sacc[nt][2] = __expf(sacc[nt][2] - m1); sacc[nt][3] = __expf(sacc[nt][3] - m1);
+        s0 += sacc[nt][0] + sacc[nt][1];
+        s1 += sacc[nt][2] + sacc[nt][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      l0 = l0 * c0 + s0; l1 = l1 * c1 + s1;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) { oacc[dt][0] *= c0; oacc[dt][1] *= c0; oacc[dt][2] *= c1; oacc[dt][3] *= c1; }
+      // O += P v: 4 steps of 16 keys, DT tiles of 8 dims
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+        pa[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+        pa[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+        pa[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt) {
+          const __nv_bfloat16* vr = Vt + (dt * 8 + g) * VLD + kk * 16 + 2 * t;
+          mma_bf16_16816(oacc[dt], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+        }
+      }
+    }
+    if (q0 < p.Lq) {
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      __nv_bfloat16* o0 = p.out + b * p.o_sb + (long long)r0 * p.o_si + h * DH + 2 * t;
+      __nv_bfloat16* o1 = p.out + b * p.o_sb + (long long)r1 * p.o_si + h * DH + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16(oacc[dt][0] * i0, oacc[dt][1] * i0);
+        if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16(oacc[dt][2] * i1, oacc[dt][3] * i1);
+      }
+    }
+  }
+}
+
 // Few queries, many keys (the 64 virtual tracks attending to all N point tracks): one CTA per (batch item, head,
 // 64-query chunk), 8 warps = 2 query groups of 32 (lane = query, as in attention_rows_kernel) x 4 KEY SPLITS.  Every split
 // walks its quarter of the keys in 64-key tiles (4 tiles staged at a time) with a per-lane online softmax; the four partial
@@ -738,6 +881,15 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
     else COMET_ATS_LAUNCH(16);
 #undef COMET_ATS_LAUNCH
     return launch_status("attention_small_kernel");
+  }
+  if (np == 1 && Lq >= 64 && (dh == 32 || dh == 48 || dh == 64) && option(COMET_OPT_ATTN_MMA) &&
+      o_sb % 2 == 0 && o_si % 2 == 0 && ((uintptr_t)out_planes % 4) == 0 && q_si % 2 == 0 && q_sb % 2 == 0) {
+    long long nb = (long long)B * H * ((Lq + ATM_WARPS * 16 - 1) / (ATM_WARPS * 16));
+    if (nb > 148LL * 16) nb = 148LL * 16;
+    if (dh == 32) attention_rows_mma_kernel<32><<<(unsigned)nb, ATM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    else if (dh == 48) attention_rows_mma_kernel<48><<<(unsigned)nb, ATM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    else attention_rows_mma_kernel<64><<<(unsigned)nb, ATM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    return launch_status("attention_rows_mma_kernel");
   }
   if (Lk <= ATR_KMAX && Lq >= 64) {
     long long nb = (long long)B * H * ((Lq + ATR_WARPS * 32 - 1) / (ATR_WARPS * 32));

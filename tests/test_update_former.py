@@ -193,3 +193,40 @@ def test_gemm_data_path_variants_are_bit_identical(np_):
     finally:
         for o, v in zip(opts, saved):
             _lib.check(_lib.lib.comet_set_option(o, v))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(16, 8, 512, 64, 48), (16, 8, 64, 512, 48), (2, 8, 100, 37, 32), (3, 4, 200, 5, 64),
+                                   (2, 8, 130, 150, 32)])
+def test_autocast_attention_on_tensor_cores(shape):
+    """Autocast mode, at least 64 queries: S = q k^T and O = P v as bf16 mma.sync with float32 accumulation and a float32
+    softmax on the accumulator registers (what the reference's attention does under torch.autocast) -- within the bf16
+    bar of the float64 result, next to the float32 lane-per-query kernels; key counts that are not multiples of 64 and
+    the multi-tile online softmax included."""
+    from comet_pose_estimation_b200 import _lib
+    from comet_pose_estimation_b200 import update_former_tc as tc
+
+    Bq, H, Lq, Lk, dh = shape
+    D = H * dh
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(4)
+    q = torch.randn(Bq, Lq, D, device=dev, generator=g)
+    k = torch.randn(Bq, Lk, D, device=dev, generator=g)
+    v = torch.randn(Bq, Lk, D, device=dev, generator=g)
+    qq, kk, vv = (z.double().view(Bq, -1, H, dh).transpose(1, 2) for z in (q, k, v))
+    ref = (torch.softmax(qq @ kk.transpose(-1, -2) / dh ** 0.5, -1) @ vv).transpose(1, 2).reshape(Bq * Lq, D)
+    run = tc._Run(tc._Weights(), 1, dev)
+    saved = _lib.lib.comet_get_option(_lib.OPT_ATTN_MMA)
+    errs = []
+    try:
+        for on in (0, 1):
+            _lib.check(_lib.lib.comet_set_option(_lib.OPT_ATTN_MMA, on))
+            n0 = _lib.lib.comet_launch_count()
+            op = run.attention(q.view(-1, D), k.view(-1, D), v.view(-1, D), Bq, H, Lq, Lk, dh, Lq * D, D, Lk * D, D, Bq * Lq, D,
+                               Lq * D, D)
+            torch.cuda.synchronize()
+            assert _lib.lib.comet_launch_count() == n0 + 1
+            errs.append(rel(op.float().sum(0)[:, :D], ref))
+    finally:
+        _lib.check(_lib.lib.comet_set_option(_lib.OPT_ATTN_MMA, saved))
+    assert errs[0] < 1e-2 and errs[1] < 2e-2, errs          # one bf16 rounding / bf16 operands: the bar of BASELINE.md 5
