@@ -10,14 +10,14 @@ char* last_error_buf() {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-static std::atomic<int> g_options[COMET_OPT_COUNT] = {{1}, {1}, {0}, {0}, {1}, {3}, {1}, {1}, {1}, {1}};   // specialised paths on; the two measured-slower experiments off
+static std::atomic<int> g_options[COMET_OPT_COUNT] = {{1}, {1}, {0}, {0}, {1}, {3}, {1}, {1}, {1}, {3}};   // specialised paths on; the two measured-slower experiments off
 int option(int which) { return (which >= 0 && which < COMET_OPT_COUNT) ? g_options[which].load(std::memory_order_relaxed) : 0; }
 }  // namespace comet
 
 extern "C" int comet_set_option(int option, int value) {
   COMET_REQUIRE(option >= 0 && option < COMET_OPT_COUNT, "unknown option %d", option);
   // boolean switches, except COMET_OPT_GEMM_TMA_STORE / COMET_OPT_GEMM_PAIR whose values are bit masks
-  comet::g_options[option].store(option == COMET_OPT_GEMM_TMA_STORE ? (value & 3) : option == COMET_OPT_GEMM_PAIR ? (value & 7) : (value ? 1 : 0), std::memory_order_relaxed);
+  comet::g_options[option].store((option == COMET_OPT_GEMM_TMA_STORE || option == COMET_OPT_ATTN_MMA) ? (value & 3) : option == COMET_OPT_GEMM_PAIR ? (value & 7) : (value ? 1 : 0), std::memory_order_relaxed);
   return COMET_OK;
 }
 extern "C" int comet_get_option(int option) { return comet::option(option); }

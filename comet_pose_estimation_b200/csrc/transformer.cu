@@ -656,6 +656,117 @@ __global__ void __launch_bounds__(ATM_WARPS * 32) attention_rows_mma_kernel(cons
   }
 }
 
+// Short sequences (at most 16 queries, at most 32 keys: the T = 16 time attention) in AUTOCAST mode: one WARP per (batch
+// item, head) as in attention_small_kernel, with the two products on the tensor cores as in attention_rows_mma_kernel --
+// 12 + 12 MMAs instead of ~2000 FMA-pipe instructions.  K / V of the (batch, head) sit in the warp's own shared-memory
+// slice (bf16; V transposed); no block-wide barrier.
+constexpr int ATSM_WARPS = 4;
+template <int DH>
+__global__ void __launch_bounds__(ATSM_WARPS * 32) attention_small_mma_kernel(const AttnParams p) {
+  constexpr int KLD = DH + 8, VLD = 32 + 8, KS = DH / 16, DT = DH / 8;
+  __shared__ __align__(16) __nv_bfloat16 Ks_all[ATSM_WARPS][32 * KLD];    // [key][dh]
+  __shared__ __align__(16) __nv_bfloat16 Vt_all[ATSM_WARPS][DH * VLD];    // [dim][key]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __nv_bfloat16* Ks = Ks_all[warp];
+  __nv_bfloat16* Vt = Vt_all[warp];
+  const long long total = (long long)p.B * p.H;
+  for (long long w = (long long)blockIdx.x * ATSM_WARPS + warp; w < total; w += (long long)gridDim.x * ATSM_WARPS) {
+    const int h = (int)(w % p.H);
+    const long long b = w / p.H;
+    const float* qp = p.q + b * p.q_sb + h * DH;
+    const float* kp = p.k + b * p.k_sb + h * DH;
+    const float* vp = p.v + b * p.v_sb + h * DH;
+    __syncwarp();                               // the previous (batch, head) is fully consumed
+    for (int e = lane; e < 32 * (DH / 4); e += 32) {
+      const int r = e / (DH / 4), c4 = e - r * (DH / 4);
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (r < p.Lk) {
+        kk = __ldg(reinterpret_cast<const float4*>(kp + (long long)r * p.k_si) + c4);
+        vv = __ldg(reinterpret_cast<const float4*>(vp + (long long)r * p.v_si) + c4);
+      }
+      *reinterpret_cast<uint2*>(Ks + r * KLD + 4 * c4) = make_uint2(pack_bf16(kk.x, kk.y), pack_bf16(kk.z, kk.w));
+      Vt[(4 * c4 + 0) * VLD + r] = __float2bfloat16_rn(vv.x);
+      Vt[(4 * c4 + 1) * VLD + r] = __float2bfloat16_rn(vv.y);
+      Vt[(4 * c4 + 2) * VLD + r] = __float2bfloat16_rn(vv.z);
+      Vt[(4 * c4 + 3) * VLD + r] = __float2bfloat16_rn(vv.w);
+    }
+    const int r0 = g, r1 = g + 8;
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      float2 x00 = make_float2(0.f, 0.f), x01 = x00, x10 = x00, x11 = x00;
+      if (r0 < p.Lq) {
+        x00 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r0 * p.q_si + ks * 16 + 2 * t));
+        x01 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r0 * p.q_si + ks * 16 + 2 * t + 8));
+      }
+      if (r1 < p.Lq) {
+        x10 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r1 * p.q_si + ks * 16 + 2 * t));
+        x11 = __ldg(reinterpret_cast<const float2*>(qp + (long long)r1 * p.q_si + ks * 16 + 2 * t + 8));
+      }
+      qa[ks][0] = pack_bf16(x00.x * p.scale, x00.y * p.scale);
+      qa[ks][1] = pack_bf16(x10.x * p.scale, x10.y * p.scale);
+      qa[ks][2] = pack_bf16(x01.x * p.scale, x01.y * p.scale);
+      qa[ks][3] = pack_bf16(x11.x * p.scale, x11.y * p.scale);
+    }
+    __syncwarp();
+    float sacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const __nv_bfloat16* kr = Ks + (nt * 8 + g) * KLD + ks * 16 + 2 * t;
+        mma_bf16_16816(sacc[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+      }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int key = nt * 8 + 2 * t;
+      if (key >= p.Lk) { sacc[nt][0] = -INFINITY; sacc[nt][2] = -INFINITY; }
+      if (key + 1 >= p.Lk) { sacc[nt][1] = -INFINITY; sacc[nt][3] = -INFINITY; }
+      m0 = fmaxf(m0, fmaxf(sacc[nt][0], sacc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sacc[nt][2], sacc[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      sacc[nt][0] = __expf(sacc[nt][0] - m0); sacc[nt][1] = __expf(sacc[nt][1] - m0);
+      sacc[nt][2] = __expf(sacc[nt][2] - m1); sacc[nt][3] = __expf(sacc[nt][3] - m1);
+      s0 += sacc[nt][0] + sacc[nt][1];
+      s1 += sacc[nt][2] + sacc[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    float oacc[DT][4];
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(sacc[2 * kk][0], sacc[2 * kk][1]);
+      pa[1] = pack_bf16(sacc[2 * kk][2], sacc[2 * kk][3]);
+      pa[2] = pack_bf16(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+      pa[3] = pack_bf16(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const __nv_bfloat16* vr = Vt + (dt * 8 + g) * VLD + kk * 16 + 2 * t;
+        mma_bf16_16816(oacc[dt], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+      }
+    }
+    const float i0 = 1.f / s0, i1 = 1.f / s1;
+    __nv_bfloat16* o0 = p.out + b * p.o_sb + (long long)r0 * p.o_si + h * DH + 2 * t;
+    __nv_bfloat16* o1 = p.out + b * p.o_sb + (long long)r1 * p.o_si + h * DH + 2 * t;
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      if (r0 < p.Lq) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_bf16(oacc[dt][0] * i0, oacc[dt][1] * i0);
+      if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(o1 + dt * 8) = pack_bf16(oacc[dt][2] * i1, oacc[dt][3] * i1);
+    }
+  }
+}
+
 // Few queries, many keys (the 64 virtual tracks attending to all N point tracks): one CTA per (batch item, head,
 // 64-query chunk), 8 warps = 2 query groups of 32 (lane = query, as in attention_rows_kernel) x 4 KEY SPLITS.  Every split
 // walks its quarter of the keys in 64-key tiles (4 tiles staged at a time) with a per-lane online softmax; the four partial
@@ -864,6 +975,14 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
   AttnParams p{q, q_sb, q_si, k, k_sb, k_si, v, v_sb, v_si, reinterpret_cast<__nv_bfloat16*>(out_planes),
                o_plane_stride, o_sb, o_si, np, B, H, Lq, Lk, dh, 1.0f / sqrtf((float)dh),
                (o_sb % 4 == 0 && o_si % 4 == 0 && o_plane_stride % 4 == 0 && ((uintptr_t)out_planes % 8) == 0) ? 1 : 0};
+  if (np == 1 && Lq <= 16 && Lk <= 32 && (dh == 32 || dh == 48) && (option(COMET_OPT_ATTN_MMA) & 2) && o_sb % 2 == 0 &&
+      o_si % 2 == 0 && ((uintptr_t)out_planes % 4) == 0 && q_si % 2 == 0 && q_sb % 2 == 0) {
+    long long nb = ((long long)B * H + ATSM_WARPS - 1) / ATSM_WARPS;
+    if (nb > 148LL * 16) nb = 148LL * 16;
+    if (dh == 32) attention_small_mma_kernel<32><<<(unsigned)nb, ATSM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    else attention_small_mma_kernel<48><<<(unsigned)nb, ATSM_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+    return launch_status("attention_small_mma_kernel");
+  }
   if (Lq <= 32 && Lk <= 32) {
     long long nb = ((long long)B * H + ATS_WARPS - 1) / ATS_WARPS;
     if (nb > 148LL * 16) nb = 148LL * 16;
@@ -882,7 +1001,7 @@ extern "C" int comet_attention_planes_f32(const float* q, long long q_sb, long l
 #undef COMET_ATS_LAUNCH
     return launch_status("attention_small_kernel");
   }
-  if (np == 1 && Lq >= 64 && (dh == 32 || dh == 48 || dh == 64) && option(COMET_OPT_ATTN_MMA) &&
+  if (np == 1 && Lq >= 64 && (dh == 32 || dh == 48 || dh == 64) && (option(COMET_OPT_ATTN_MMA) & 1) &&
       o_sb % 2 == 0 && o_si % 2 == 0 && ((uintptr_t)out_planes % 4) == 0 && q_si % 2 == 0 && q_sb % 2 == 0) {
     long long nb = (long long)B * H * ((Lq + ATM_WARPS * 16 - 1) / (ATM_WARPS * 16));
     if (nb > 148LL * 16) nb = 148LL * 16;

@@ -85,7 +85,8 @@ int comet_has_tensor_path(void);
 #define COMET_OPT_GEMM_BN96 7 /* transformer GEMM: 96-column output tiles where they divide N and save a round of CTAs */
 #define COMET_OPT_GEMM_PAIR 8 /* transformer GEMM: clusters of two CTAs share every W tile (each loads half and multicasts it);
                                 bit mask: 1 float32-grade mode (K >= 1024: the default), 2 autocast mode, 4 any K */
-#define COMET_OPT_ATTN_MMA 9 /* autocast mode: attention with at most 64 keys on the tensor cores (mma.sync bf16) */
+#define COMET_OPT_ATTN_MMA 9 /* autocast mode: attention on the tensor cores (mma.sync bf16); bit mask: 1 = at least 64 queries,
+                                 2 = the short time attention (at most 16 queries, 32 keys) */
 #define COMET_OPT_COUNT 10
 int comet_set_option(int option, int value);
 int comet_get_option(int option);

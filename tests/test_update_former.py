@@ -197,9 +197,9 @@ def test_gemm_data_path_variants_are_bit_identical(np_):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(16, 8, 512, 64, 48), (16, 8, 64, 512, 48), (2, 8, 100, 37, 32), (3, 4, 200, 5, 64),
-                                   (2, 8, 130, 150, 32)])
+                                   (2, 8, 130, 150, 32), (576, 8, 16, 16, 48), (40, 8, 16, 16, 32), (5, 8, 7, 11, 48)])
 def test_autocast_attention_on_tensor_cores(shape):
-    """Autocast mode, at least 64 queries: S = q k^T and O = P v as bf16 mma.sync with float32 accumulation and a float32
+    """Autocast mode, at least 64 queries or the short time attention: S = q k^T and O = P v as bf16 mma.sync with float32 accumulation and a float32
     softmax on the accumulator registers (what the reference's attention does under torch.autocast) -- within the bf16
     bar of the float64 result, next to the float32 lane-per-query kernels; key counts that are not multiples of 64 and
     the multi-tile online softmax included."""
@@ -219,7 +219,7 @@ def test_autocast_attention_on_tensor_cores(shape):
     saved = _lib.lib.comet_get_option(_lib.OPT_ATTN_MMA)
     errs = []
     try:
-        for on in (0, 1):
+        for on in (0, 3):
             _lib.check(_lib.lib.comet_set_option(_lib.OPT_ATTN_MMA, on))
             n0 = _lib.lib.comet_launch_count()
             op = run.attention(q.view(-1, D), k.view(-1, D), v.view(-1, D), Bq, H, Lq, Lk, dh, Lq * D, D, Lk * D, D, Bq * Lq, D,
